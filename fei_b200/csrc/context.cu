@@ -1,0 +1,103 @@
+// Process/device context, error state and device buffers for libfeiscan.
+#include "common.h"
+#include <stdarg.h>
+#include <stdio.h>
+#include <atomic>
+
+namespace fei {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<size_t> g_dev_bytes{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  cudaGetLastError();  // clear sticky-less errors so the next call reports its own
+  return FEI_E_CUDA;
+}
+
+int DevBuf::alloc(size_t n) {
+  release();
+  if (n == 0) return FEI_OK;
+  cudaError_t e = cudaMalloc(&p, n);
+  if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); }
+  bytes = n;
+  g_dev_bytes += n;
+  return FEI_OK;
+}
+int DevBuf::ensure(size_t n) {
+  if (n <= bytes) return FEI_OK;
+  return alloc(n);
+}
+void DevBuf::release() {
+  if (p) { cudaFree(p); g_dev_bytes -= bytes; }
+  p = nullptr; bytes = 0;
+}
+size_t total_device_bytes() { return g_dev_bytes.load(); }
+
+Context& ctx() { static Context c; return c; }
+
+int require_ready() {
+  if (!ctx().ready) { set_error("fei_init() has not been called (or failed): no CUDA device bound; there is no CPU path"); return FEI_E_CUDA; }
+  return FEI_OK;
+}
+
+}  // namespace fei
+
+using namespace fei;
+
+extern "C" int fei_abi_version(void) { return FEI_ABI_VERSION; }
+extern "C" const char* fei_last_error(void) { return last_error(); }
+
+extern "C" int fei_init(int device) {
+  Context& c = ctx();
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no usable CUDA device (%s); libfeiscan has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return FEI_E_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (0..%d)", device, ndev - 1); return FEI_E_BADARG; }
+  if (c.ready && c.device == device) return FEI_OK;
+  FEI_CUDA(cudaSetDevice(device));
+  cudaDeviceProp p;
+  FEI_CUDA(cudaGetDeviceProperties(&p, device));
+  c.device = device;
+  c.sm_count = p.multiProcessorCount;
+  c.hbm_bytes = p.totalGlobalMem;
+  c.cc_major = p.major; c.cc_minor = p.minor;
+  if (p.major < 10) {
+    set_error("device %d is sm_%d%d; libfeiscan is built for sm_100a only", device, p.major, p.minor);
+    return FEI_E_CUDA;
+  }
+  if (!c.stream) FEI_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  if (!c.copy_stream) FEI_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  c.ready = true;
+  return FEI_OK;
+}
+
+extern "C" int fei_shutdown(void) {
+  Context& c = ctx();
+  if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
+  if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }
+  c.ready = false;
+  return FEI_OK;
+}
+
+extern "C" int fei_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc_major, int* cc_minor) {
+  FEI_TRY(require_ready());
+  Context& c = ctx();
+  if (sm_count) *sm_count = c.sm_count;
+  if (hbm_bytes) *hbm_bytes = c.hbm_bytes;
+  if (cc_major) *cc_major = c.cc_major;
+  if (cc_minor) *cc_minor = c.cc_minor;
+  return FEI_OK;
+}

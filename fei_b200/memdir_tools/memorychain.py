@@ -1,0 +1,314 @@
+"""Memorychain link-hash validation on the GPU.
+
+Mirror of the hot part of the reference's ``memdir_tools/memorychain.py``:
+
+* ``MemoryBlock``            — fields, ``calculate_hash``, ``to_dict`` / ``from_dict``
+  (reference :74-130, :263-327)
+* ``MemoryChain.validate_chain`` — same signature and log lines (reference :596-618)
+* ``validate_chain_blocks``  — the drop-in body for the reference's own class: works on
+  any sequence of objects exposing the reference's block attributes.
+
+All hashing goes through ``libfeiscan.so`` (``fei_chain_validate_cols``): the host only
+marshals the ten hashed fields into typed columns; canonical JSON is produced by the
+library's C++ serialiser and SHA-256 + the two comparisons run in the CUDA kernel
+(``fei_b200/csrc/chain.cu``).  There is no hashlib path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import threading
+from operator import attrgetter
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .. import _abi
+
+logger = logging.getLogger("memorychain")     # same logger name as the reference (:43)
+
+TASK_PROPOSED = "proposed"
+DIFFICULTY_LEVELS = {"easy": 1, "medium": 3, "hard": 5, "very_hard": 10, "extreme": 20}
+
+# sorted key order of the hashed dict (reference :117-128 with sort_keys=True)
+HASHED_FIELDS = ("difficulty", "index", "memory_id", "nonce", "previous_hash",
+                 "proposer_node", "responsible_node", "solver_node", "task_state", "timestamp")
+
+
+# --------------------------------------------------------------------------- marshalling
+class _Col:
+    """One typed JSON column (include/feiscan.h fei_json_col) with its backing arrays."""
+
+    __slots__ = ("tag", "uniform", "num", "blob", "off")
+
+    def __init__(self):
+        self.tag = None; self.uniform = _abi.J_NULL; self.num = None; self.blob = None; self.off = None
+
+    def fill(self, dst: _abi.JsonCol) -> None:
+        dst.tag = _abi.ptr(self.tag)
+        dst.uniform_tag = self.uniform
+        dst.num = _abi.ptr(self.num)
+        dst.str = _abi.ptr(self.blob)
+        dst.str_off = _abi.ptr(self.off)
+
+
+def _str_blob(vals: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    n = len(vals)
+    lens = np.fromiter(map(len, vals), dtype=np.int64, count=n)
+    blob = "".join(vals).encode("utf-8", "surrogatepass")
+    if len(blob) != int(lens.sum()):       # non-ASCII somewhere: byte lengths differ from str lengths
+        enc = [v.encode("utf-8", "surrogatepass") for v in vals]
+        lens = np.fromiter(map(len, enc), dtype=np.int64, count=n)
+        blob = b"".join(enc)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    arr = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, dtype=np.uint8)
+    return arr, off
+
+
+def _column(vals: Sequence[Any], what: str) -> _Col:
+    """Typed column for values json.dumps would emit as scalars."""
+    col = _Col()
+    n = len(vals)
+    kinds = set(map(type, vals))
+    if kinds == {str}:
+        col.uniform = _abi.J_STR
+        col.blob, col.off = _str_blob(vals)
+        return col
+    if kinds == {float}:
+        col.uniform = _abi.J_FLOAT
+        col.num = np.array(vals, dtype=np.float64).view(np.uint64)
+        return col
+    if kinds == {int}:
+        try:
+            col.num = np.array(vals, dtype=np.int64).view(np.uint64)
+            col.uniform = _abi.J_INT
+            return col
+        except OverflowError:
+            pass
+    if kinds == {type(None)}:
+        col.uniform = _abi.J_NULL
+        return col
+    # mixed / exotic: per-element tags
+    tag = np.zeros(n, dtype=np.uint8)
+    num = np.zeros(n, dtype=np.uint64)
+    strs: List[str] = [""] * n
+    for i, v in enumerate(vals):
+        if v is None:
+            tag[i] = _abi.J_NULL
+        elif v is True:
+            tag[i] = _abi.J_TRUE
+        elif v is False:
+            tag[i] = _abi.J_FALSE
+        elif isinstance(v, str):
+            tag[i] = _abi.J_STR; strs[i] = str.__str__(v)
+        elif isinstance(v, int):
+            iv = int(v)
+            if -(1 << 63) <= iv < (1 << 63):
+                tag[i] = _abi.J_INT; num[i] = np.int64(iv).view(np.uint64)
+            else:
+                tag[i] = _abi.J_BIGINT; strs[i] = int.__repr__(iv)
+        elif isinstance(v, float):
+            tag[i] = _abi.J_FLOAT; num[i] = np.float64(v).view(np.uint64)
+        else:
+            raise NotImplementedError(
+                f"block field {what!r} holds a {type(v).__name__}; only JSON scalars are hashed on the GPU")
+    col.tag, col.num = tag, num
+    col.blob, col.off = _str_blob(strs)
+    return col
+
+
+_get_direct = attrgetter("index", "nonce", "previous_hash", "proposer_node", "responsible_node", "timestamp", "memory_data", "hash")
+
+
+def _memory_id(md: Any) -> Any:
+    # self.memory_data.get("metadata", {}).get("unique_id", "")   (reference :120)
+    return md.get("metadata", {}).get("unique_id", "")
+
+
+def chain_columns(blocks: Sequence[Any]) -> Tuple[List[_Col], List[Any]]:
+    """Ten hashed columns (sorted key order) + the stored ``hash`` attributes."""
+    rows = list(map(_get_direct, blocks))
+    if rows:
+        index, nonce, prev, proposer, responsible, timestamp, mdata, stored = map(list, zip(*rows))
+    else:
+        index = nonce = prev = proposer = responsible = timestamp = mdata = stored = []
+    memory_id = list(map(_memory_id, mdata))
+    # getattr(self, "task_state", None) etc. (reference :124-126)
+    task_state = [getattr(b, "task_state", None) for b in blocks]
+    difficulty = [getattr(b, "difficulty", None) for b in blocks]
+    solver = [getattr(b, "solver_node", None) for b in blocks]
+    by_name = {"difficulty": difficulty, "index": index, "memory_id": memory_id, "nonce": nonce,
+               "previous_hash": prev, "proposer_node": proposer, "responsible_node": responsible,
+               "solver_node": solver, "task_state": task_state, "timestamp": timestamp}
+    return [_column(by_name[k], k) for k in HASHED_FIELDS], stored
+
+
+def _cols_struct(cols: List[_Col]):
+    arr = (_abi.JsonCol * _abi.CHAIN_NCOLS)()
+    for k, c in enumerate(cols):
+        c.fill(arr[k])
+    return arr
+
+
+def canonical_texts(blocks: Sequence[Any]) -> List[bytes]:
+    """The exact byte strings the reference feeds to sha256 (host serialiser only; used by tests)."""
+    cols, _ = chain_columns(blocks)
+    n = len(blocks)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    cap = max(1024, 1024 * n)
+    buf = np.zeros(cap, dtype=np.uint8)
+    arr = _cols_struct(cols)
+    _abi.check(_abi.lib().fei_chain_serialize_cols(arr, n, _abi.ptr(buf), cap, _abi.ptr(off)))
+    return [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(n)]
+
+
+def hash_and_validate(blocks: Sequence[Any], first_index: int = 0, want_digests: bool = False
+                      ) -> Tuple[int, int, Optional[np.ndarray]]:
+    """GPU pass over ``blocks``: returns (first_bad or -1, kind, digests[n,32] or None).
+
+    kind 1 = "invalid hash", 2 = "broken link to previous block"; element 0 is only used
+    as a predecessor (the reference never checks the genesis block, :604).
+    """
+    _abi.init()
+    n = len(blocks)
+    cols, stored = chain_columns(blocks)
+    if not all(isinstance(h, str) for h in stored):
+        # `!=` between arbitrary objects (None == None ...) has no string form
+        raise NotImplementedError("block.hash must be a str for GPU validation")
+    hash_blob, hash_off = _str_blob(stored)
+    first_bad, kind = C.c_int64(-1), C.c_int32(0)
+    digests = np.zeros((n, 32), dtype=np.uint8) if want_digests else None
+    arr = _cols_struct(cols)
+    _abi.check(_abi.lib().fei_chain_validate_cols(
+        arr, _abi.ptr(hash_blob), _abi.ptr(hash_off), n, first_index,
+        C.byref(first_bad), C.byref(kind), _abi.ptr(digests), None, 0, None))
+    return first_bad.value, kind.value, digests
+
+
+def validate_chain_blocks(chain: Sequence[Any], lock: Optional[Any] = None, log: logging.Logger = logger) -> bool:
+    """Drop-in body of ``MemoryChain.validate_chain`` (reference :596-618)."""
+    ctx = lock if lock is not None else threading.RLock()
+    with ctx:
+        if len(chain) < 2:
+            return True
+        first_bad, kind, _ = hash_and_validate(chain)
+    if first_bad < 0:
+        return True
+    if kind == 1:
+        log.error(f"Block {first_bad} has invalid hash")
+    else:
+        log.error(f"Block {first_bad} has broken link to previous block")
+    return False
+
+
+# --------------------------------------------------------------------------- reference-shaped classes
+class MemoryBlock:
+    """Same constructor, attributes and (de)serialisation as the reference block (:74-108, :263-327).
+
+    ``hash`` is computed lazily on first access (the reference hashes eagerly in the
+    constructor and again after ``from_dict`` overwrites it); the value is identical.
+    """
+
+    def __init__(self, index: int, timestamp: float, memory_data: Dict[str, Any],
+                 previous_hash: str, responsible_node: str, proposer_node: str):
+        self.index = index
+        self.timestamp = timestamp
+        self.memory_data = memory_data
+        self.previous_hash = previous_hash
+        self.responsible_node = responsible_node
+        self.proposer_node = proposer_node
+        self.nonce = 0
+        self.working_nodes: List[str] = []
+        self.solutions: List[Any] = []
+        self.difficulty = memory_data.get("task_difficulty", "medium")
+        self.reward = DIFFICULTY_LEVELS.get(self.difficulty, 3)
+        self.task_state = memory_data.get("task_state", TASK_PROPOSED)
+        self.solver_node = None
+        self.difficulty_votes: Dict[str, Any] = {}
+        self._hash: Optional[str] = None
+
+    @property
+    def hash(self) -> str:
+        if self._hash is None:
+            self._hash = self.calculate_hash()
+        return self._hash
+
+    @hash.setter
+    def hash(self, value: str) -> None:
+        self._hash = value
+
+    def calculate_hash(self) -> str:
+        probe = _HashProbe(self)
+        _, _, dig = hash_and_validate([probe], want_digests=True)
+        return bytes(dig[0]).hex()
+
+    def is_task(self) -> bool:
+        return self.memory_data.get("type") == "task"
+
+    def to_dict(self) -> Dict[str, Any]:
+        data = {"index": self.index, "timestamp": self.timestamp, "memory_data": self.memory_data,
+                "previous_hash": self.previous_hash, "responsible_node": self.responsible_node,
+                "proposer_node": self.proposer_node, "nonce": self.nonce, "hash": self.hash}
+        if self.is_task():
+            data.update({"working_nodes": self.working_nodes, "solutions": self.solutions,
+                         "difficulty": self.difficulty, "reward": self.reward, "task_state": self.task_state,
+                         "solver_node": self.solver_node, "difficulty_votes": self.difficulty_votes})
+        return data
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any]) -> "MemoryBlock":
+        block = cls(data["index"], data["timestamp"], data["memory_data"], data["previous_hash"],
+                    data["responsible_node"], data["proposer_node"])
+        block.nonce = data["nonce"]
+        block.hash = data["hash"]
+        if block.is_task():
+            block.working_nodes = data.get("working_nodes", [])
+            block.solutions = data.get("solutions", [])
+            block.difficulty = data.get("difficulty", "medium")
+            block.reward = data.get("reward", DIFFICULTY_LEVELS.get(block.difficulty, 3))
+            block.task_state = data.get("task_state", TASK_PROPOSED)
+            block.solver_node = data.get("solver_node")
+            block.difficulty_votes = data.get("difficulty_votes", {})
+        return block
+
+
+class _HashProbe:
+    """View of a block whose stored hash is irrelevant (single-block hashing)."""
+    hash = ""
+
+    def __init__(self, b: Any):
+        self.__dict__.update({k: getattr(b, k) for k in
+                              ("index", "nonce", "previous_hash", "proposer_node", "responsible_node",
+                               "timestamp", "memory_data")})
+        for k in ("task_state", "difficulty", "solver_node"):
+            if hasattr(b, k):
+                setattr(self, k, getattr(b, k))
+
+
+class MemoryChain:
+    """The slice of the reference's ``MemoryChain`` that validation touches (:501-526, :596-618).
+
+    Consensus, wallet, networking and persistence are out of scope.
+    """
+
+    def __init__(self, node_id: str = "validator", difficulty: int = 2, blocks: Optional[Iterable[Any]] = None):
+        self.chain: List[Any] = list(blocks) if blocks is not None else []
+        self.node_id = node_id
+        self.difficulty = difficulty
+        self.lock = threading.RLock()
+
+    def validate_chain(self) -> bool:
+        return validate_chain_blocks(self.chain, lock=self.lock, log=logger)
+
+
+def install(target_module: Any = None) -> None:
+    """Patch the reference's class in place: ``memdir_tools.memorychain.MemoryChain.validate_chain``."""
+    if target_module is None:
+        import importlib
+        target_module = importlib.import_module("memdir_tools.memorychain")
+
+    def validate_chain(self) -> bool:
+        return validate_chain_blocks(self.chain, lock=self.lock, log=target_module.logger)
+
+    target_module.MemoryChain.validate_chain = validate_chain

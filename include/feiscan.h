@@ -1,0 +1,220 @@
+/*
+ * feiscan.h — C ABI of libfeiscan.so, the sm_100a scan engine behind Fei's Memdir
+ * search / filter pipeline and Memorychain validation.
+ *
+ * The reference (david-strejc/fei) is pure Python and has no FFI of its own; each
+ * entry point below names the reference interface whose inner loop it replaces.
+ * The Python host layer (fei_b200/memdir_tools/) binds these with ctypes and keeps
+ * the reference's signatures; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative FEI_E_* code; the message is
+ *     available from fei_last_error() (thread local);
+ *   - plain pointers and sizes only; the caller owns all host arrays for the duration
+ *     of a call, the library copies what it keeps; device memory lives behind opaque
+ *     handles; outputs go to caller-provided buffers with explicit capacities;
+ *   - there is no CPU implementation behind any of the compute entry points: without
+ *     a usable CUDA device they fail with FEI_E_CUDA.
+ */
+#ifndef FEISCAN_H_
+#define FEISCAN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEI_ABI_VERSION 1
+
+enum {
+  FEI_OK = 0,
+  FEI_E_CUDA = -1,        /* CUDA runtime / driver error, or no device          */
+  FEI_E_NCCL = -2,        /* NCCL error or NCCL not loadable                    */
+  FEI_E_CAPACITY = -3,    /* caller buffer too small (required size is reported) */
+  FEI_E_UNSUPPORTED = -4, /* program uses a feature the kernels do not implement */
+  FEI_E_BADARG = -5,
+  FEI_E_STATE = -6        /* call sequence error (e.g. scan before load)         */
+};
+
+int fei_abi_version(void);
+const char* fei_last_error(void);
+
+/* ---- process / device ------------------------------------------------------ */
+/* One process drives one GPU (rank-local device index).                         */
+int fei_init(int device);
+int fei_shutdown(void);
+int fei_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc_major, int* cc_minor);
+
+/* ---- packed Memdir corpus ---------------------------------------------------
+ * Replaces the per-query file walk of memdir_tools.utils.list_memories
+ * (memdir_tools/utils.py:202-253): records are packed once, in the reference's
+ * listing order, and stay resident in HBM.
+ *
+ * Host-side canonical form (what the packer produces, struct of arrays):
+ *   hdr / hdr_off[n+1]    header text of record i = text before the first "---"
+ *                         (parse_memory_content, utils.py:105-118), newline-normalised
+ *   body / body_off[n+1]  body of record i, already .strip()ped (utils.py:120)
+ *   name / name_off[n+1]  file name "ts.uid.host:2,FLAGS" (utils.py:74-95); may be NULL
+ *   ts[n]                 filename timestamp (utils.py:90)
+ *   wall[n]               datetime.fromtimestamp(ts) as naive wall-clock seconds (utils.py:94)
+ *   flags8[n]             flag letters, byte k = k-th letter, byte 7 = count (<= 7)
+ *   fsb[n]                folder_id (bits 0-15) | status_id (16-23) | record bits (24-31)
+ */
+typedef struct fei_corpus fei_corpus;
+
+#define FEI_REC_NO_SEPARATOR  0x01u  /* no "---": headers = {}, body = whole text (utils.py:107-109) */
+#define FEI_REC_NONASCII      0x02u  /* record contains non-ASCII bytes                               */
+#define FEI_REC_LOWER_INEXACT 0x04u  /* str.lower() of the record is not per-code-point (U+0130, final sigma) */
+
+typedef struct fei_corpus_host {
+  uint64_t n;
+  uint64_t global_base;      /* index of record 0 in the unsharded corpus (hits are global indices) */
+  const uint8_t* hdr;   const uint64_t* hdr_off;
+  const uint8_t* body;  const uint64_t* body_off;
+  const uint8_t* name;  const uint64_t* name_off;
+  const int64_t* ts;
+  const int64_t* wall;
+  const uint64_t* flags8;
+  const uint32_t* fsb;
+} fei_corpus_host;
+
+int fei_corpus_create(fei_corpus** out);
+int fei_corpus_destroy(fei_corpus* c);
+/* Copies the canonical arrays to HBM (pageable or pinned host memory), builds the
+ * warp-transposed body tiles (DESIGN.md "data layout") and drops the canonical body. */
+int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h);
+/* Fills the corpus with records [first, first+n) of the deterministic synthetic
+ * Memdir (fei_b200/csrc/synth.cuh), generated on the GPU.                           */
+int fei_corpus_synth(fei_corpus* c, uint64_t seed, uint64_t first, uint64_t n);
+
+typedef struct fei_corpus_stats {
+  uint64_t n, global_base;
+  uint64_t hdr_bytes, body_bytes, tile_bytes, name_bytes;
+  uint64_t n_groups;
+  uint64_t device_bytes;     /* total HBM held by this corpus */
+} fei_corpus_stats;
+int fei_corpus_stats_get(const fei_corpus* c, fei_corpus_stats* out);
+
+/* Debug / materialisation: copy the canonical pieces of records [first, first+n) back
+ * to the host.  Bodies are un-tiled on the device first.  Any pointer may be NULL. */
+int fei_corpus_fetch(fei_corpus* c, uint64_t first, uint64_t n,
+                     uint8_t* hdr, uint64_t hdr_cap, uint64_t* hdr_off,
+                     uint8_t* body, uint64_t body_cap, uint64_t* body_off,
+                     int64_t* ts, int64_t* wall, uint64_t* flags8, uint32_t* fsb);
+
+/* ---- scan ---------------------------------------------------------------------
+ * Replaces the hot loops of memdir_tools.search.search_memories
+ * (memdir_tools/search.py:361-367 -> _memory_matches_query :244-335) and of
+ * FilterManager.process_memories / MemoryFilter.matches (memdir_tools/filter.py:229-233,
+ * :67-109).  `prog` is a compiled predicate program (fei_b200/program.py documents the
+ * binary layout; include/feiscan_prog.h declares it): up to 32 queries evaluated in one
+ * pass, each the AND of header/meta/content conditions.
+ *
+ * fei_scan_masks : mask[i] bit q = record i satisfies query q.  `masks` may be a host
+ *                  pointer (n entries) or NULL to keep the result on the device only.
+ * fei_scan_hits  : per query, the ordered list of matching GLOBAL record indices
+ *                  (ascending = the reference's listing order).  hits[q] has room for
+ *                  cap[q] entries; nhits[q] receives the true count; returns
+ *                  FEI_E_CAPACITY if any list was truncated.
+ */
+int fei_scan_masks(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint32_t* masks);
+int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_len,
+                  uint64_t* const* hits, const uint64_t* cap, uint64_t* nhits);
+/* Count-only variant (no index lists): nhits[q] for every query.                     */
+int fei_scan_count(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint64_t* nhits);
+
+/* Per-call timing of the last scan on this corpus, measured with CUDA events on the
+ * launching stream: ms spent in the head kernel, body kernel, compaction, copies.    */
+typedef struct fei_scan_timing {
+  float head_ms, body_ms, compact_ms, h2d_ms, d2h_ms, total_ms;
+  uint32_t kernel_launches;
+  uint64_t body_bytes_touched;   /* tile bytes of groups that had at least one live record */
+} fei_scan_timing;
+int fei_scan_last_timing(const fei_corpus* c, fei_scan_timing* out);
+
+/* ---- Memorychain validation -----------------------------------------------------
+ * Replaces the loop of MemoryChain.validate_chain (memdir_tools/memorychain.py:596-618)
+ * and its inline copy in receive_chain_update (:1059-1078):
+ *   for i in 1..n-1:  hash[i] == sha256(canonical_json(block i))   else "invalid hash"
+ *                     prev[i] == hash[i-1]                          else "broken link"
+ * first_bad = smallest failing i (or -1), bad_kind = 1 (invalid hash) / 2 (broken link).
+ * Block 0 (genesis) is never checked, exactly as in the reference.
+ *
+ * fei_chain_validate_msgs takes the canonical JSON texts (MemoryBlock.calculate_hash,
+ * memorychain.py:117-128) already serialised:
+ *   msgs/msg_off[n+1], stored hash strings hash/hash_off[n+1], previous_hash strings
+ *   prev/prev_off[n+1]; digests (32*n bytes, may be NULL) receives the raw SHA-256.
+ */
+int fei_chain_validate_msgs(const uint8_t* msgs, const uint64_t* msg_off,
+                            const uint8_t* hash, const uint64_t* hash_off,
+                            const uint8_t* prev, const uint64_t* prev_off,
+                            uint64_t n, uint64_t first_index,
+                            int64_t* first_bad, int32_t* bad_kind, uint8_t* digests);
+
+/* Column form: the ten hashed fields of every block as typed JSON scalars; the library
+ * serialises them to canonical JSON (json.dumps(sort_keys=True), memorychain.py:117-128)
+ * in C++ and validates on the GPU.  Field order in `cols` is the sorted key order:
+ * difficulty, index, memory_id, nonce, previous_hash, proposer_node, responsible_node,
+ * solver_node, task_state, timestamp.                                                */
+enum { FEI_J_NULL = 0, FEI_J_STR = 1, FEI_J_INT = 2, FEI_J_FLOAT = 3, FEI_J_TRUE = 4, FEI_J_FALSE = 5,
+       FEI_J_BIGINT = 6 /* decimal digits in the string blob */ };
+typedef struct fei_json_col {
+  const uint8_t* tag;        /* n tags, or NULL when every value has tag `uniform_tag` */
+  int32_t uniform_tag;
+  const uint64_t* num;       /* n entries: int64 or IEEE double bit patterns            */
+  const uint8_t* str;        /* UTF-8 blob                                              */
+  const uint64_t* str_off;   /* n+1 offsets                                             */
+} fei_json_col;
+#define FEI_CHAIN_NCOLS 10
+int fei_chain_validate_cols(const fei_json_col* cols /*[FEI_CHAIN_NCOLS]*/,
+                            const uint8_t* hash, const uint64_t* hash_off,
+                            uint64_t n, uint64_t first_index,
+                            int64_t* first_bad, int32_t* bad_kind, uint8_t* digests,
+                            uint8_t* msgs_out, uint64_t msgs_cap, uint64_t* msg_off_out);
+
+/* Resident form for benchmarking / streaming: messages and stored hashes uploaded
+ * once, validated repeatedly.                                                         */
+typedef struct fei_chain fei_chain;
+int fei_chain_create(fei_chain** out);
+int fei_chain_destroy(fei_chain* ch);
+int fei_chain_load_msgs(fei_chain* ch, const uint8_t* msgs, const uint64_t* msg_off,
+                        const uint8_t* hash, const uint64_t* hash_off,
+                        const uint8_t* prev, const uint64_t* prev_off, uint64_t n, uint64_t first_index);
+/* Synthetic chain blocks [first, first+n) (synth.cuh gen_block): canonical JSON and
+ * the SHA-256 links are produced on the GPU; `corrupt_at` >= 0 flips one stored digest. */
+int fei_chain_synth(fei_chain* ch, uint64_t seed, uint64_t first, uint64_t n, int64_t corrupt_at);
+int fei_chain_validate(fei_chain* ch, int64_t* first_bad, int32_t* bad_kind, uint8_t* digests, float* kernel_ms);
+int fei_chain_fetch(fei_chain* ch, uint64_t first, uint64_t n, uint8_t* msgs, uint64_t msgs_cap, uint64_t* msg_off,
+                    uint8_t* hash_hex /*64*n*/, uint8_t* prev_hex /*64*n*/);
+
+/* Host-only helper (no GPU): canonical JSON of the column form, for tests of the
+ * serialiser against json.dumps.                                                      */
+int fei_chain_serialize_cols(const fei_json_col* cols, uint64_t n,
+                             uint8_t* msgs_out, uint64_t msgs_cap, uint64_t* msg_off_out);
+
+/* ---- synthetic data on the host (same generator as the device one) --------------- */
+int fei_synth_record_host(uint64_t seed, uint64_t i,
+                          uint8_t* hdr, uint32_t hdr_cap, uint32_t* hdr_len,
+                          uint8_t* body, uint32_t body_cap, uint32_t* body_len,
+                          int64_t* ts, char* uid8, char* flags4, uint8_t* nflags, uint8_t* status, uint8_t* folder);
+int fei_synth_block_host(uint64_t seed, uint64_t i, double* timestamp, char* memory_id8,
+                         uint8_t* task_state, uint8_t* difficulty, uint8_t* is_task);
+
+/* ---- multi-GPU (one process per GPU; NCCL is dlopen()ed at first use) ------------- */
+#define FEI_NCCL_ID_BYTES 128
+int fei_comm_unique_id(uint8_t* id /*[FEI_NCCL_ID_BYTES]*/);
+int fei_comm_init(const uint8_t* id, int nranks, int rank);
+int fei_comm_destroy(void);
+/* all-gatherv of the per-query ordered hit lists left on the device by the last
+ * fei_scan_hits / fei_scan_count(keep) on this corpus: rank-order concatenation is the
+ * global listing order.  counts_out[r*nq + q] = hits of query q on rank r.             */
+int fei_comm_allgather_hits(fei_corpus* c, uint32_t nq, uint64_t* const* hits, const uint64_t* cap,
+                            uint64_t* nhits_total, uint64_t* counts_out);
+/* min-reduce of (first_bad, kind) over ranks for a range-sharded chain.               */
+int fei_comm_allreduce_first_bad(int64_t* first_bad, int32_t* bad_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEISCAN_H_ */
