@@ -41,7 +41,7 @@ class CorpusHost(C.Structure):
         ("n", C.c_uint64), ("global_base", C.c_uint64),
         ("hdr", C.c_void_p), ("hdr_off", C.c_void_p),
         ("body", C.c_void_p), ("body_off", C.c_void_p),
-        ("name", C.c_void_p), ("name_off", C.c_void_p),
+        ("name", C.c_void_p), ("name_off", C.c_void_p), ("name_spans", C.c_void_p),
         ("ts", C.c_void_p), ("wall", C.c_void_p), ("flags8", C.c_void_p), ("fsb", C.c_void_p),
     ]
 
@@ -72,6 +72,8 @@ _SIGS = {
     "fei_init": (C.c_int, [C.c_int]),
     "fei_shutdown": (C.c_int, []),
     "fei_device_info": (C.c_int, [_P, _P, _P, _P]),
+    "fei_host_register": (C.c_int, [_P, _U64]),
+    "fei_host_unregister": (C.c_int, [_P]),
     "fei_corpus_create": (C.c_int, [_P]),
     "fei_corpus_destroy": (C.c_int, [_P]),
     "fei_corpus_load": (C.c_int, [_P, _P]),

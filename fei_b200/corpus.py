@@ -1,0 +1,101 @@
+"""Handle on a packed corpus resident in HBM (include/feiscan.h fei_corpus_*, fei_scan_*)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+
+
+class Corpus:
+    """Pack once, scan many.  All compute goes through libfeiscan; there is no CPU path."""
+
+    def __init__(self):
+        _abi.init()
+        self._h = C.c_void_p()
+        _abi.check(_abi.lib().fei_corpus_create(C.byref(self._h)))
+        self.n = 0
+        self.global_base = 0
+
+    def close(self) -> None:
+        if self._h:
+            _abi.lib().fei_corpus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- filling
+    def load(self, a: Dict[str, Any]) -> "Corpus":
+        """`a`: canonical host arrays (fei_b200.synth.arrays_from_records / fei_b200.packer)."""
+        h = _abi.CorpusHost()
+        h.n = int(a["n"]); h.global_base = int(a.get("global_base", 0))
+        for k in ("hdr", "hdr_off", "body", "body_off", "name", "name_off", "name_spans", "ts", "wall", "flags8", "fsb"):
+            v = a.get(k)
+            setattr(h, k, _abi.ptr(np.ascontiguousarray(v)) if v is not None else None)
+        self._keep = a                      # arrays must outlive the call only, but keep them for materialisation
+        _abi.check(_abi.lib().fei_corpus_load(self._h, C.byref(h)))
+        self.n, self.global_base = h.n, h.global_base
+        return self
+
+    def synth(self, seed: int, first: int, n: int) -> "Corpus":
+        _abi.check(_abi.lib().fei_corpus_synth(self._h, seed, first, n))
+        self.n, self.global_base = n, first
+        return self
+
+    def stats(self) -> Dict[str, int]:
+        s = _abi.CorpusStats()
+        _abi.check(_abi.lib().fei_corpus_stats_get(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def fetch(self, first: int, n: int) -> Dict[str, Any]:
+        """Canonical pieces of records [first, first+n) copied back from the device (bodies un-tiled)."""
+        hdr_off = np.zeros(n + 1, dtype=np.uint64); body_off = np.zeros(n + 1, dtype=np.uint64)
+        ts = np.zeros(n, dtype=np.int64); wall = np.zeros(n, dtype=np.int64)
+        f8 = np.zeros(n, dtype=np.uint64); fsb = np.zeros(n, dtype=np.uint32)
+        l = _abi.lib()
+        _abi.check(l.fei_corpus_fetch(self._h, first, n, None, 0, _abi.ptr(hdr_off), None, 0, _abi.ptr(body_off),
+                                      _abi.ptr(ts), _abi.ptr(wall), _abi.ptr(f8), _abi.ptr(fsb)))
+        hdr = np.zeros(max(1, int(hdr_off[n])), dtype=np.uint8); body = np.zeros(max(1, int(body_off[n])), dtype=np.uint8)
+        _abi.check(l.fei_corpus_fetch(self._h, first, n, _abi.ptr(hdr), hdr.size, None, _abi.ptr(body), body.size, None,
+                                      None, None, None, None))
+        return {"hdr": hdr, "hdr_off": hdr_off, "body": body, "body_off": body_off, "ts": ts, "wall": wall, "flags8": f8, "fsb": fsb}
+
+    # ---- scanning
+    def scan_masks(self, prog: bytes) -> np.ndarray:
+        masks = np.zeros(max(1, self.n), dtype=np.uint32)
+        _abi.check(_abi.lib().fei_scan_masks(self._h, prog, len(prog), _abi.ptr(masks)))
+        return masks[:self.n]
+
+    def scan_count(self, prog: bytes, nq: int) -> np.ndarray:
+        counts = np.zeros(32, dtype=np.uint64)
+        _abi.check(_abi.lib().fei_scan_count(self._h, prog, len(prog), _abi.ptr(counts)))
+        return counts[:nq]
+
+    def scan_hits(self, prog: bytes, nq: int, cap: Optional[int] = None) -> List[np.ndarray]:
+        """Ordered global record indices per query."""
+        if cap is None:
+            counts = self.scan_count(prog, nq)
+            caps = [int(c) for c in counts]
+        else:
+            caps = [cap] * nq
+        bufs = [np.zeros(max(1, c), dtype=np.uint64) for c in caps]
+        ptrs = (C.c_void_p * 32)(*[_abi.ptr(b) for b in bufs])
+        cap_arr = np.zeros(32, dtype=np.uint64); cap_arr[:nq] = caps
+        nh = np.zeros(32, dtype=np.uint64)
+        _abi.check(_abi.lib().fei_scan_hits(self._h, prog, len(prog), ptrs, _abi.ptr(cap_arr), _abi.ptr(nh)))
+        return [bufs[q][:int(nh[q])] for q in range(nq)]
+
+    def timing(self) -> Dict[str, float]:
+        t = _abi.ScanTiming()
+        _abi.check(_abi.lib().fei_scan_last_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+    @property
+    def handle(self):
+        return self._h

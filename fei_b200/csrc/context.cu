@@ -101,3 +101,17 @@ extern "C" int fei_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc_major
   if (cc_minor) *cc_minor = c.cc_minor;
   return FEI_OK;
 }
+
+extern "C" int fei_host_register(void* p, uint64_t bytes) {
+  FEI_TRY(require_ready());
+  if (!p || !bytes) return FEI_OK;
+  FEI_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return FEI_OK;
+}
+
+extern "C" int fei_host_unregister(void* p) {
+  FEI_TRY(require_ready());
+  if (!p) return FEI_OK;
+  FEI_CUDA(cudaHostUnregister(p));
+  return FEI_OK;
+}

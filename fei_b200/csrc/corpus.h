@@ -1,0 +1,45 @@
+// Device-resident packed Memdir corpus (see DESIGN.md "data layout in HBM").
+//
+//   headers : canonical blob  hdr[hdr_off[i] .. hdr_off[i+1])           (4% of the bytes)
+//   meta    : SoA  ts[n], wall[n], flags8[n], fsb[n]
+//   names   : canonical blob (optional)
+//   bodies  : warp-transposed, length-sorted, ragged tiles:
+//       records are taken in windows of kWindow consecutive records; inside a window they
+//       are sorted by body length (16-byte units, descending, stable) and cut into groups
+//       of 32.  A group stores unit k of every member that still has a unit k, members in
+//       sorted order, as one contiguous row of m_k * 16 bytes, rows back to back:
+//           row_k = grp_base[g] + 16 * sum_{j<k} m_j ,   lane l's unit k at row_k + 16*l
+//       so a warp reading "unit k of its 32 records" issues ONE contiguous coalesced
+//       request of m_k*16 bytes, every lane gets the next 16 bytes of its own record in
+//       registers, and (lengths being sorted) lanes finish together.  No padding except the
+//       last unit of each record (<= 15 bytes, zero filled).
+//       grp_rec[g*32 + l] = record index (kInvalidRec for padding lanes), grp_len[...] = byte length.
+#pragma once
+#include "common.h"
+
+namespace fei {
+constexpr int kWindow = 1024;
+constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
+}
+
+struct fei_corpus {
+  uint64_t n = 0, global_base = 0;
+  uint64_t hdr_bytes = 0, body_bytes = 0, name_bytes = 0, tile_bytes = 0;
+  uint64_t n_groups = 0;
+  bool loaded = false;
+  fei::DevBuf hdr, hdr_off, name, name_off, name_spans, ts, wall, flags8, fsb;
+  fei::DevBuf tiles, grp_base, grp_rec, grp_len, rec_pos;
+  // scan scratch (grown on demand, reused across scans)
+  fei::DevBuf prog, hits, blk_counts, blk_offsets, totals, hit_lists, work_counter, scan_tmp;
+  uint64_t hit_list_stride = 0;          // entries per query in hit_lists (last fei_scan_hits)
+  uint32_t last_nq = 0;
+  uint64_t last_counts[32] = {0};
+  fei_scan_timing timing = {};
+  cudaEvent_t ev[8] = {nullptr};
+};
+
+namespace fei {
+// builds tiles from a canonical body blob already on the device (body has >= 32 bytes of slack)
+int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off, cudaStream_t s);
+int exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, DevBuf& tmp, cudaStream_t s);
+}

@@ -1,0 +1,614 @@
+// K1/K2: the Memdir scan kernels (sm_100a).
+//
+// Replaces the per-record loops of the reference:
+//   search_memories -> _memory_matches_query -> _get_field_value / _compare_values
+//       (memdir_tools/search.py:361-367, :244-335, :97-139, :141-242)
+//   FilterManager.process_memories -> MemoryFilter.matches      (memdir_tools/filter.py:229-233, :67-109)
+//   parse_memory_content header parsing                          (memdir_tools/utils.py:113-118)
+//
+// k_head : one thread per record.  Meta predicates (flags / date / folder / status), then the
+//          header text is parsed on the device exactly like the reference: lines split on '\n',
+//          first ':' splits key and value, both .strip()ped with Python's whitespace set,
+//          dict semantics (a repeated key keeps its last value), case-insensitive field lookup
+//          takes the first matching key.  Every string condition is an output bit of a byte DFA.
+//          Writes alive[i] = bitmask of queries whose non-content conditions all hold.
+// k_body : one warp per group of 32 records in the warp-transposed body tiles (corpus.h): each
+//          row is one contiguous coalesced request (ld.global.nc 16 B per lane); each lane walks
+//          its own record through the multi-pattern DFA whose tables were staged into shared
+//          memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier).  Groups with no live
+//          record are skipped without touching their bytes.  hits[i] = alive[i] & content bits.
+// k_count / k_scan_blocks / k_emit : order-preserving compaction of hits[] into per-query lists
+//          of global record indices (warp ballots + popc prefix, block offsets from a scan).
+#include "corpus.h"
+#include "../../include/feiscan_prog.h"
+#include <string.h>
+#include <vector>
+
+namespace fei {
+
+// ---------------------------------------------------------------- DFA view
+struct DfaView {
+  const uint16_t* trans;
+  const uint32_t* out;
+  const uint32_t* endout;
+  const uint8_t* cls;
+  uint32_t n_cols, start, acc_base, empty_acc;
+};
+
+__device__ __forceinline__ DfaView dfa_view(const uint8_t* blob, uint32_t off) {
+  const fei_prog_dfa* d = reinterpret_cast<const fei_prog_dfa*>(blob + off);
+  DfaView v;
+  v.trans = reinterpret_cast<const uint16_t*>(blob + d->off_trans);
+  v.out = reinterpret_cast<const uint32_t*>(blob + d->off_out);
+  v.endout = reinterpret_cast<const uint32_t*>(blob + d->off_endout);
+  v.cls = blob + d->off_cls;
+  v.n_cols = d->n_cols; v.start = d->start; v.acc_base = d->acc_base; v.empty_acc = d->empty_acc;
+  return v;
+}
+
+// generic (global-memory tables) run over a byte span; used by the head kernel on short fields
+__device__ uint32_t dfa_run(const DfaView& d, const uint8_t* p, uint32_t len) {
+  if (len == 0) return d.empty_acc;
+  uint32_t s = d.start;
+  uint32_t acc = s >= d.acc_base ? __ldg(d.out + s) : 0u;
+  const bool direct = d.n_cols == 256;
+  for (uint32_t i = 0; i < len; ++i) {
+    uint32_t b = p[i];
+    uint32_t col = direct ? b : __ldg(d.cls + b);
+    s = __ldg(d.trans + s * d.n_cols + col);
+    if (s >= d.acc_base) acc |= __ldg(d.out + s);
+  }
+  return acc | __ldg(d.endout + s);
+}
+
+// ---------------------------------------------------------------- Python str.strip() whitespace
+// str.isspace(): U+0009-000D, 001C-001F, 0020, 0085, 00A0, 1680, 2000-200A, 2028, 2029, 202F, 205F, 3000
+__device__ __forceinline__ int ws_len_at(const uint8_t* p, const uint8_t* end) {   // bytes of the whitespace char at p, or 0
+  uint32_t c = p[0];
+  if (c < 0x80) return ((c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x20)) ? 1 : 0;
+  if (c == 0xC2) return (p + 1 < end && (p[1] == 0x85 || p[1] == 0xA0)) ? 2 : 0;
+  if (p + 2 >= end) return 0;
+  uint32_t c1 = p[1], c2 = p[2];
+  if (c == 0xE1) return (c1 == 0x9A && c2 == 0x80) ? 3 : 0;
+  if (c == 0xE2) {
+    if (c1 == 0x80) return ((c2 >= 0x80 && c2 <= 0x8A) || c2 == 0xA8 || c2 == 0xA9 || c2 == 0xAF) ? 3 : 0;
+    if (c1 == 0x81) return c2 == 0x9F ? 3 : 0;
+    return 0;
+  }
+  if (c == 0xE3) return (c1 == 0x80 && c2 == 0x80) ? 3 : 0;
+  return 0;
+}
+__device__ __forceinline__ int ws_len_before(const uint8_t* begin, const uint8_t* p) {   // whitespace char ending right before p
+  if (p <= begin) return 0;
+  uint32_t c = p[-1];
+  if (c < 0x80) return ((c >= 0x09 && c <= 0x0D) || (c >= 0x1C && c <= 0x20)) ? 1 : 0;
+  if ((c & 0xC0) != 0x80) return 0;
+  if (p - begin >= 2 && p[-2] == 0xC2) return (c == 0x85 || c == 0xA0) ? 2 : 0;
+  if (p - begin >= 3) { int n = ws_len_at(p - 3, p); return n == 3 ? 3 : 0; }
+  return 0;
+}
+__device__ __forceinline__ void strip_span(const uint8_t*& a, const uint8_t*& b) {
+  for (;;) { if (a >= b) return; int n = ws_len_at(a, b); if (!n) break; a += n; }
+  for (;;) { if (a >= b) return; int n = ws_len_before(a, b); if (!n) break; b -= n; }
+}
+
+// ---------------------------------------------------------------- head kernel
+struct HeadArgs {
+  const uint8_t* prog;         // device copy of the program blob
+  const uint8_t* hdr; const uint64_t* hdr_off;
+  const uint8_t* name; const uint64_t* name_off; const uint16_t* name_spans;
+  const int64_t* wall; const uint64_t* flags8; const uint32_t* fsb;
+  uint64_t n;
+  uint32_t* alive;
+};
+
+__global__ void __launch_bounds__(128) k_head(HeadArgs a) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
+  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
+  const fei_prog_slot* slots = reinterpret_cast<const fei_prog_slot*>(a.prog + ph->off_slots);
+  const uint32_t nslots = ph->n_slots;
+
+  uint32_t slot_acc[FEI_MAX_SLOTS];
+  uint32_t present = 0;
+  if (nslots) {
+    uint32_t first_off[FEI_MAX_SLOTS], first_len[FEI_MAX_SLOTS];
+    uint32_t have_first = 0;
+    DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
+    const uint8_t* h = a.hdr + a.hdr_off[i];
+    const uint8_t* hend = a.hdr + a.hdr_off[i + 1];
+    const uint8_t* p = h;
+    while (p < hend) {
+      const uint8_t* eol = p; const uint8_t* colon = nullptr;
+      while (eol < hend && *eol != '\n') { if (!colon && *eol == ':') colon = eol; ++eol; }
+      if (colon) {                                             // `if ":" in line` (utils.py:116)
+        const uint8_t* ka = p; const uint8_t* kb = colon; strip_span(ka, kb);
+        const uint8_t* va = colon + 1; const uint8_t* vb = eol; strip_span(va, vb);
+        uint32_t km = dfa_run(keyd, ka, (uint32_t)(kb - ka));
+        while (km) {
+          int s = __ffs(km) - 1; km &= km - 1;
+          if (slots[s].mode == 0) {                            // first key that lower()-equals the field (search.py:121-122)
+            if (!(have_first >> s & 1)) { have_first |= 1u << s; first_off[s] = (uint32_t)(ka - h); first_len[s] = (uint32_t)(kb - ka); }
+            else {
+              bool same = first_len[s] == (uint32_t)(kb - ka);
+              for (uint32_t k = 0; same && k < first_len[s]; ++k) same = h[first_off[s] + k] == ka[k];
+              if (!same) continue;                             // a different spelling of the key: not the dict entry we read
+            }
+          }
+          DfaView vd = dfa_view(a.prog, slots[s].off_val_dfa);
+          slot_acc[s] = dfa_run(vd, va, (uint32_t)(vb - va));   // repeated key: last value wins (dict assignment)
+          present |= 1u << s;
+        }
+      }
+      p = eol + 1;
+    }
+    for (uint32_t s = 0; s < nslots; ++s)
+      if (!(present >> s & 1) && slots[s].empty_if_missing) {   // headers.get("Status", "")
+        slot_acc[s] = reinterpret_cast<const fei_prog_dfa*>(a.prog + slots[s].off_val_dfa)->empty_acc;
+        present |= 1u << s;
+      }
+  }
+
+  // flags string (search.py:105-106): up to 7 letters packed in flags8
+  uint32_t flags_acc = 0;
+  if (ph->off_flags_dfa) {
+    uint64_t f = a.flags8[i];
+    uint8_t fb[8];
+    uint32_t fl = (uint32_t)(f >> 56);
+    for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f >> (8 * k));
+    flags_acc = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, fl);
+  }
+  uint32_t name_acc[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    if (!ph->off_name_dfa[k]) continue;
+    const uint8_t* nb = a.name + a.name_off[i];
+    uint32_t nl = (uint32_t)(a.name_off[i + 1] - a.name_off[i]);
+    if (k > 0) { const uint16_t* sp = a.name_spans + 4 * i + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
+    name_acc[k] = dfa_run(dfa_view(a.prog, ph->off_name_dfa[k]), nb, nl);
+  }
+
+  uint32_t alive = 0;
+  const uint32_t fsb = a.fsb[i];
+  for (uint32_t q = 0; q < ph->n_queries; ++q) {
+    bool ok = true;
+    for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
+      const fei_prog_cond& cd = conds[c];
+      bool r;
+      switch (cd.kind) {
+        case FEI_C_BODY: continue;                              // evaluated by k_body
+        case FEI_C_CONST: r = cd.bit != 0; break;
+        case FEI_C_SLOT:
+          if (present >> cd.ref & 1) { r = ((slot_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; if (cd.if_missing == 2) ++c; }
+          else if (cd.if_missing == 2) continue;               // header absent: the next condition is the fallback field
+          else r = cd.if_missing != 0;
+          break;
+        case FEI_C_FLAGS: r = ((flags_acc >> cd.bit) & 1u) != cd.negate; break;
+        case FEI_C_NAME: r = ((name_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; break;
+        case FEI_C_DATE_CMP: {
+          int64_t v = a.wall[i] * 1000000ll, o = cd.i64;
+          switch (cd.cmp_op) {
+            case FEI_CMP_GT: r = v > o; break; case FEI_CMP_LT: r = v < o; break;
+            case FEI_CMP_GE: r = v >= o; break; case FEI_CMP_LE: r = v <= o; break;
+            case FEI_CMP_EQ: r = v == o; break; default: r = v != o; break;
+          }
+          break;
+        }
+        case FEI_C_FOLDER_SET: r = (cd.set64 >> (fsb & 0xFFFFu) & 1ull) != 0; break;
+        case FEI_C_STATUS_SET: r = (cd.set64 >> ((fsb >> 16) & 0xFFu) & 1ull) != 0; break;
+        default: r = false;
+      }
+      ok = r;
+    }
+    if (ok) alive |= 1u << q;
+  }
+  a.alive[i] = alive;
+}
+
+// ---------------------------------------------------------------- body kernel
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+struct BodyArgs {
+  const uint8_t* prog;
+  const uint8_t* tiles; const uint64_t* grp_base; const uint32_t* grp_rec; const uint32_t* grp_len;
+  uint64_t n_groups;
+  uint32_t* hits;              // in: alive masks (when has_alive), out: final hit masks
+  int has_alive;
+  unsigned long long* counter; // [0] = next group, [1] = tile bytes touched
+};
+
+constexpr int kBodyThreads = 1024;
+
+template <bool kDirect>
+__device__ __forceinline__ void dfa_bytes4(uint32_t w, int nbytes, uint32_t& s, uint32_t& acc,
+                                           const uint16_t* __restrict__ trans, const uint32_t* __restrict__ out,
+                                           const uint8_t* __restrict__ cls, uint32_t ncols, uint32_t acc_base) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < nbytes) {
+      uint32_t b = (w >> (8 * j)) & 0xFFu;
+      uint32_t col = kDirect ? b : cls[b];
+      s = trans[(kDirect ? (s << 8) : s * ncols) + col];
+      if (s >= acc_base) acc |= out[s];
+    }
+  }
+}
+
+template <bool kDirect>
+__global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const fei_prog_dfa* dd = reinterpret_cast<const fei_prog_dfa*>(a.prog + ph->off_body_dfa);
+  const uint32_t table_bytes = dd->table_bytes;
+  // ---- stage the automaton into shared memory with TMA bulk copies
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, table_bytes);
+    const uint8_t* src = a.prog + dd->off_trans;
+    for (uint32_t o = 0; o < table_bytes; o += 32768u) {
+      uint32_t nb = table_bytes - o < 32768u ? table_bytes - o : 32768u;
+      bulk_g2s(smem + o, src + o, nb, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem);
+  const uint32_t* out = reinterpret_cast<const uint32_t*>(smem + (dd->off_out - dd->off_trans));
+  const uint32_t* endout = reinterpret_cast<const uint32_t*>(smem + (dd->off_endout - dd->off_trans));
+  const uint8_t* cls = smem + (dd->off_cls - dd->off_trans);
+  const uint32_t ncols = dd->n_cols, acc_base = dd->acc_base, start = dd->start;
+  const uint32_t start_out = start >= acc_base ? out[start] : 0u;
+  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
+  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
+  const uint32_t nq = ph->n_queries;
+  const uint32_t all_q = nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1u);
+  const int lane = threadIdx.x & 31;
+  unsigned long long touched = 0;
+
+  for (;;) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(a.counter, 1ull);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= a.n_groups) break;
+    const uint32_t rec = a.grp_rec[g * 32 + lane];
+    const uint32_t len = a.grp_len[g * 32 + lane];
+    const uint32_t units = (len + 15) >> 4;
+    uint32_t alive = 0;
+    if (rec != kInvalidRec) alive = a.has_alive ? a.hits[rec] : all_q;
+    const bool live = alive != 0;
+    if (__ballot_sync(0xffffffffu, live) == 0) continue;      // nobody in this group can still match: skip its bytes
+    const uint8_t* row = a.tiles + a.grp_base[g] * 16;
+    const uint32_t maxu = __shfl_sync(0xffffffffu, units, 0);
+    if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
+    uint32_t s = start, acc = start_out;
+    for (uint32_t k = 0; k < maxu; ++k) {
+      const uint32_t m = __popc(__ballot_sync(0xffffffffu, k < units));
+      if (k < units && live) {
+        uint4 v = ldg_stream16(row + lane * 16);
+        int nb = (int)len - (int)(k * 16);
+        if (nb >= 16) {
+          dfa_bytes4<kDirect>(v.x, 4, s, acc, trans, out, cls, ncols, acc_base);
+          dfa_bytes4<kDirect>(v.y, 4, s, acc, trans, out, cls, ncols, acc_base);
+          dfa_bytes4<kDirect>(v.z, 4, s, acc, trans, out, cls, ncols, acc_base);
+          dfa_bytes4<kDirect>(v.w, 4, s, acc, trans, out, cls, ncols, acc_base);
+        } else {
+          dfa_bytes4<kDirect>(v.x, nb, s, acc, trans, out, cls, ncols, acc_base);
+          dfa_bytes4<kDirect>(v.y, nb - 4, s, acc, trans, out, cls, ncols, acc_base);
+          dfa_bytes4<kDirect>(v.z, nb - 8, s, acc, trans, out, cls, ncols, acc_base);
+          dfa_bytes4<kDirect>(v.w, nb - 12, s, acc, trans, out, cls, ncols, acc_base);
+        }
+      }
+      row += (uint64_t)m * 16;
+    }
+    if (live) {
+      acc |= endout[s];
+      uint32_t hit = 0;
+      for (uint32_t q = 0; q < nq; ++q) {
+        if (!(alive >> q & 1)) continue;
+        bool ok = true;
+        for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
+          const fei_prog_cond& cd = conds[c];
+          if (cd.kind == FEI_C_BODY) ok = ((acc >> cd.bit) & 1u) != cd.negate;
+        }
+        if (ok) hit |= 1u << q;
+      }
+      a.hits[rec] = hit;
+    } else if (rec != kInvalidRec && !a.has_alive) {
+      a.hits[rec] = 0;
+    }
+  }
+  if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
+}
+
+// ---------------------------------------------------------------- compaction
+constexpr int kCompactBlock = 256;          // threads
+constexpr int kCompactPer = 8;              // records per thread -> 2048 records per block
+
+// counts[block * nq + q] = records of this block that hit query q
+__global__ void __launch_bounds__(kCompactBlock)
+k_count(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t sh[32][8];
+  uint64_t base = (uint64_t)blockIdx.x * kCompactBlock * kCompactPer;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t cnt = 0;                        // lane q accumulates query q
+  for (int r = 0; r < kCompactPer; ++r) {
+    uint64_t i = base + (uint64_t)(warp * kCompactPer + r) * 32 + lane;
+    uint32_t m = i < n ? hits[i] : 0u;
+    for (uint32_t q = 0; q < nq; ++q) {
+      uint32_t b = __popc(__ballot_sync(0xffffffffu, (m >> q) & 1u));
+      if (lane == (int)q) cnt += b;
+    }
+  }
+  sh[lane][warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 32 && threadIdx.x < nq) {
+    uint32_t s = 0;
+    for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+    counts[(uint64_t)blockIdx.x * nq + threadIdx.x] = s;
+  }
+}
+
+// per query: exclusive scan over blocks (one thread block per query; n_blocks up to millions is fine)
+__global__ void k_scan_blocks(const uint32_t* __restrict__ counts, uint64_t nblocks, uint32_t nq,
+                              uint64_t* __restrict__ offsets, uint64_t* __restrict__ totals) {
+  __shared__ uint64_t sh[1024];
+  __shared__ uint64_t carry;
+  uint32_t q = blockIdx.x;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < nblocks; base += blockDim.x) {
+    uint64_t b = base + threadIdx.x;
+    uint64_t v = b < nblocks ? counts[b * nq + q] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+      uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    uint64_t incl = sh[threadIdx.x];
+    if (b < nblocks) offsets[b * nq + q] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[q] = carry;
+}
+
+// ordered emit: lists[q * stride + rank] = global_base + i
+__global__ void __launch_bounds__(kCompactBlock)
+k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_t* __restrict__ offsets,
+       uint64_t global_base, uint64_t stride, uint64_t* __restrict__ lists) {
+  __shared__ uint32_t wcnt[8][32];          // [warp][query] hits of this warp's records
+  uint64_t base = (uint64_t)blockIdx.x * kCompactBlock * kCompactPer;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t m[kCompactPer];
+  uint32_t cnt = 0;
+  for (int r = 0; r < kCompactPer; ++r) {
+    uint64_t i = base + (uint64_t)(warp * kCompactPer + r) * 32 + lane;
+    m[r] = i < n ? hits[i] : 0u;
+    for (uint32_t q = 0; q < nq; ++q) {
+      uint32_t b = __popc(__ballot_sync(0xffffffffu, (m[r] >> q) & 1u));
+      if (lane == (int)q) cnt += b;
+    }
+  }
+  wcnt[warp][lane] = cnt;
+  __syncthreads();
+  for (uint32_t q = 0; q < nq; ++q) {
+    uint64_t pos = offsets[(uint64_t)blockIdx.x * nq + q];
+    for (int w = 0; w < warp; ++w) pos += wcnt[w][q];
+    for (int r = 0; r < kCompactPer; ++r) {
+      uint32_t bal = __ballot_sync(0xffffffffu, (m[r] >> q) & 1u);
+      if ((m[r] >> q) & 1u) {
+        uint64_t i = base + (uint64_t)(warp * kCompactPer + r) * 32 + lane;
+        uint64_t rank = pos + __popc(bal & ((1u << lane) - 1u));
+        if (rank < stride) lists[q * stride + rank] = global_base + i;
+      }
+      pos += __popc(bal);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static int check_prog(const uint8_t* prog, uint64_t len) {
+  if (!prog || len < sizeof(fei_prog_hdr)) { set_error("program blob too small"); return FEI_E_BADARG; }
+  fei_prog_hdr h; memcpy(&h, prog, sizeof(h));
+  if (h.magic != FEI_PROG_MAGIC || h.version != FEI_PROG_VERSION) { set_error("bad program magic/version"); return FEI_E_BADARG; }
+  if (h.total_bytes != len) { set_error("program length mismatch (%u vs %llu)", h.total_bytes, (unsigned long long)len); return FEI_E_BADARG; }
+  if (h.n_queries == 0 || h.n_queries > FEI_MAX_QUERIES) { set_error("1..32 queries per program"); return FEI_E_BADARG; }
+  if (h.n_slots > FEI_MAX_SLOTS) { set_error("at most %d header slots per program", FEI_MAX_SLOTS); return FEI_E_UNSUPPORTED; }
+  auto in = [&](uint64_t off, uint64_t sz) { return off % 16 == 0 && off + sz <= len; };
+  if (!in(h.off_conds, (uint64_t)h.n_conds * sizeof(fei_prog_cond)) || !in(h.off_queries, (uint64_t)h.n_queries * sizeof(fei_prog_query)) ||
+      !in(h.off_slots, (uint64_t)h.n_slots * sizeof(fei_prog_slot))) { set_error("program section out of bounds"); return FEI_E_BADARG; }
+  auto dfa_ok = [&](uint32_t off) {
+    if (!off) return true;
+    if (!in(off, sizeof(fei_prog_dfa))) return false;
+    fei_prog_dfa d; memcpy(&d, prog + off, sizeof(d));
+    return in(d.off_trans, d.table_bytes) && d.start < d.n_states && d.n_cols >= 1 && d.n_cols <= 256 &&
+           d.off_out >= d.off_trans && d.off_endout >= d.off_trans && d.off_cls >= d.off_trans &&
+           d.off_out + 4ull * d.n_states <= (uint64_t)d.off_trans + d.table_bytes &&
+           d.off_endout + 4ull * d.n_states <= (uint64_t)d.off_trans + d.table_bytes &&
+           2ull * d.n_states * d.n_cols <= d.trans_bytes && d.n_states <= 65535;
+  };
+  if (!dfa_ok(h.off_key_dfa) || !dfa_ok(h.off_body_dfa) || !dfa_ok(h.off_flags_dfa) || !dfa_ok(h.off_name_dfa[0]) ||
+      !dfa_ok(h.off_name_dfa[1]) || !dfa_ok(h.off_name_dfa[2])) { set_error("bad DFA descriptor in program"); return FEI_E_BADARG; }
+  const fei_prog_slot* sl = reinterpret_cast<const fei_prog_slot*>(prog + h.off_slots);
+  for (uint32_t s = 0; s < h.n_slots; ++s) if (!sl[s].off_val_dfa || !dfa_ok(sl[s].off_val_dfa)) { set_error("bad slot DFA"); return FEI_E_BADARG; }
+  if (h.n_slots && !h.off_key_dfa) { set_error("slots without a key DFA"); return FEI_E_BADARG; }
+  const fei_prog_query* qs = reinterpret_cast<const fei_prog_query*>(prog + h.off_queries);
+  for (uint32_t q = 0; q < h.n_queries; ++q) if (qs[q].cond_begin > qs[q].cond_end || qs[q].cond_end > h.n_conds) { set_error("bad query range"); return FEI_E_BADARG; }
+  return FEI_OK;
+}
+
+static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
+  FEI_TRY(require_ready());
+  if (!c || !c->loaded) { set_error("corpus not loaded"); return FEI_E_STATE; }
+  FEI_TRY(check_prog(prog, prog_len));
+  Context& cx = ctx();
+  cudaStream_t s = cx.stream;
+  fei_prog_hdr h; memcpy(&h, prog, sizeof(h));
+  uint64_t n = c->n;
+  c->timing = fei_scan_timing{};
+  c->last_nq = h.n_queries;
+  FEI_TRY(c->prog.ensure(prog_len + 16));
+  FEI_TRY(c->hits.ensure((n ? n : 1) * sizeof(uint32_t)));
+  FEI_TRY(c->work_counter.ensure(2 * sizeof(unsigned long long)));
+  FEI_CUDA(cudaEventRecord(c->ev[0], s));
+  FEI_CUDA(cudaMemcpyAsync(c->prog.p, prog, prog_len, cudaMemcpyHostToDevice, s));
+  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(unsigned long long), s));
+  bool need_head = h.head_mask != 0;
+  bool need_body = h.off_body_dfa != 0 && h.body_mask != 0;
+  if ((h.off_name_dfa[0] || h.off_name_dfa[1] || h.off_name_dfa[2]) && !c->name.p) {
+    set_error("program reads filename / id / hostname but the corpus was packed without names"); return FEI_E_STATE;
+  }
+  FEI_CUDA(cudaEventRecord(c->ev[1], s));
+  uint32_t launches = 0;
+  if (n && need_head) {
+    HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
+               c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>()};
+    k_head<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+    ++launches;
+  }
+  FEI_CUDA(cudaEventRecord(c->ev[2], s));
+  if (n && need_body) {
+    fei_prog_dfa d; memcpy(&d, prog + h.off_body_dfa, sizeof(d));
+    size_t smem = d.table_bytes;
+    if (smem > 220 * 1024) { set_error("content automaton needs %zu bytes of shared memory (limit 220 KiB)", smem); return FEI_E_UNSUPPORTED; }
+    BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
+               c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>()};
+    unsigned grid = (unsigned)cx.sm_count;
+    if (d.n_cols == 256) {
+      FEI_CUDA(cudaFuncSetAttribute(k_body<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_body<true><<<grid, kBodyThreads, smem, s>>>(a);
+    } else {
+      FEI_CUDA(cudaFuncSetAttribute(k_body<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_body<false><<<grid, kBodyThreads, smem, s>>>(a);
+    }
+    ++launches;
+  } else if (n && !need_head) {
+    // no condition reads the corpus at all (constant queries): every record gets the constant verdict
+    // (program.py folds constants into head conditions, so this only happens for empty condition lists)
+    uint32_t all_q = h.n_queries >= 32 ? 0xFFFFFFFFu : ((1u << h.n_queries) - 1u);
+    std::vector<uint32_t> fill(n, all_q);
+    FEI_CUDA(cudaMemcpyAsync(c->hits.p, fill.data(), n * 4, cudaMemcpyHostToDevice, s));
+    FEI_CUDA(cudaStreamSynchronize(s));
+  }
+  FEI_CUDA(cudaEventRecord(c->ev[3], s));
+  FEI_CUDA(cudaGetLastError());
+  c->timing.kernel_launches = launches;
+  return FEI_OK;
+}
+
+static int finish_timing(fei_corpus* c, bool compacted) {
+  cudaStream_t s = ctx().stream;
+  FEI_CUDA(cudaEventRecord(c->ev[5], s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  float t;
+  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[1])); c->timing.h2d_ms = t;
+  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[1], c->ev[2])); c->timing.head_ms = t;
+  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[2], c->ev[3])); c->timing.body_ms = t;
+  if (compacted) { FEI_CUDA(cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); c->timing.compact_ms = t; }
+  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[compacted ? 4 : 3], c->ev[5])); c->timing.d2h_ms = t;
+  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5])); c->timing.total_ms = t;
+  unsigned long long touched = 0;
+  FEI_CUDA(cudaMemcpy(&touched, c->work_counter.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost));
+  c->timing.body_bytes_touched = touched;
+  return FEI_OK;
+}
+
+// counts (+ optional lists) on the device; totals copied to c->last_counts
+static int compact(fei_corpus* c, bool want_lists) {
+  Context& cx = ctx();
+  cudaStream_t s = cx.stream;
+  uint64_t n = c->n; uint32_t nq = c->last_nq;
+  uint64_t per_block = (uint64_t)kCompactBlock * kCompactPer;
+  uint64_t nblocks = (n + per_block - 1) / per_block;
+  for (uint32_t q = 0; q < 32; ++q) c->last_counts[q] = 0;
+  if (n == 0) { FEI_CUDA(cudaEventRecord(c->ev[4], s)); return FEI_OK; }
+  FEI_TRY(c->blk_counts.ensure(nblocks * nq * sizeof(uint32_t)));
+  FEI_TRY(c->blk_offsets.ensure(nblocks * nq * sizeof(uint64_t)));
+  FEI_TRY(c->totals.ensure(32 * sizeof(uint64_t)));
+  k_count<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(c->hits.as<uint32_t>(), n, nq, c->blk_counts.as<uint32_t>());
+  k_scan_blocks<<<nq, 1024, 0, s>>>(c->blk_counts.as<uint32_t>(), nblocks, nq, c->blk_offsets.as<uint64_t>(), c->totals.as<uint64_t>());
+  c->timing.kernel_launches += 2;
+  FEI_CUDA(cudaMemcpyAsync(c->last_counts, c->totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  if (want_lists) {
+    uint64_t stride = 1;
+    for (uint32_t q = 0; q < nq; ++q) if (c->last_counts[q] > stride) stride = c->last_counts[q];
+    c->hit_list_stride = stride;
+    FEI_TRY(c->hit_lists.ensure(stride * nq * sizeof(uint64_t)));
+    k_emit<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(c->hits.as<uint32_t>(), n, nq, c->blk_offsets.as<uint64_t>(), c->global_base, stride,
+                                                       c->hit_lists.as<uint64_t>());
+    c->timing.kernel_launches += 1;
+  }
+  FEI_CUDA(cudaEventRecord(c->ev[4], s));
+  FEI_CUDA(cudaGetLastError());
+  return FEI_OK;
+}
+
+}  // namespace fei
+
+using namespace fei;
+
+extern "C" int fei_scan_masks(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint32_t* masks) {
+  FEI_TRY(run_scan(c, prog, prog_len));
+  if (masks && c->n) FEI_CUDA(cudaMemcpyAsync(masks, c->hits.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
+  return finish_timing(c, false);
+}
+
+extern "C" int fei_scan_count(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint64_t* nhits) {
+  FEI_TRY(run_scan(c, prog, prog_len));
+  FEI_TRY(compact(c, true));                 // lists stay on the device for fei_comm_allgather_hits
+  if (nhits) for (uint32_t q = 0; q < c->last_nq; ++q) nhits[q] = c->last_counts[q];
+  return finish_timing(c, true);
+}
+
+extern "C" int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_len,
+                             uint64_t* const* hits, const uint64_t* cap, uint64_t* nhits) {
+  if (!hits || !cap || !nhits) { set_error("null argument"); return FEI_E_BADARG; }
+  FEI_TRY(run_scan(c, prog, prog_len));
+  FEI_TRY(compact(c, true));
+  cudaStream_t s = ctx().stream;
+  bool truncated = false;
+  for (uint32_t q = 0; q < c->last_nq; ++q) {
+    nhits[q] = c->last_counts[q];
+    uint64_t take = nhits[q] < cap[q] ? nhits[q] : cap[q];
+    if (take < nhits[q]) truncated = true;
+    if (take && hits[q]) FEI_CUDA(cudaMemcpyAsync(hits[q], c->hit_lists.as<uint64_t>() + q * c->hit_list_stride, take * 8, cudaMemcpyDeviceToHost, s));
+  }
+  FEI_TRY(finish_timing(c, true));
+  if (truncated) { set_error("hit buffer too small for at least one query (see nhits)"); return FEI_E_CAPACITY; }
+  return FEI_OK;
+}
+
+extern "C" int fei_scan_last_timing(const fei_corpus* c, fei_scan_timing* out) {
+  if (!c || !out) { set_error("null argument"); return FEI_E_BADARG; }
+  *out = c->timing;
+  return FEI_OK;
+}

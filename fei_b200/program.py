@@ -1,0 +1,198 @@
+"""Predicate programs: queries -> the binary blob `fei_scan_*` takes (include/feiscan_prog.h).
+
+A program holds up to 32 queries; a query is the AND of conditions.  Every string-valued
+condition becomes one output bit of the multi-output byte DFA of the field it reads
+(fei_b200.regexc), so all conditions of all queries on one field cost one pass over it.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .regexc import Dfa, Pattern, compile_patterns
+
+MAGIC, VERSION = 0x50494546, 1
+C_CONST, C_BODY, C_SLOT, C_FLAGS, C_NAME, C_DATE_CMP, C_FOLDER_SET, C_STATUS_SET = range(8)
+CMP = {">": 0, "<": 1, ">=": 2, "<=": 3, "=": 4, "!=": 5}
+NAME_FILENAME, NAME_ID, NAME_HOST = 0, 1, 2
+SMEM_TABLE_LIMIT = 200 * 1024          # body automaton must fit the CTA's shared memory
+
+
+@dataclass(frozen=True)
+class Cond:
+    """One condition.  kind + what it reads:
+       const(value) | body(pattern) | slot(field, mode, empty_if_missing, pattern) | flags(pattern)
+       | name(which, pattern) | date_cmp(op, micros) | folder_set(bits) | status_set(bits)"""
+    kind: int
+    pattern: Optional[Pattern] = None
+    negate: bool = False
+    field: str = ""              # header field name (slot)
+    mode: int = 0                # slot: 0 = case-insensitive first key, 1 = exact key
+    empty_if_missing: bool = False
+    if_missing: int = 0          # slot: 0/1 result when absent, 2 = next condition is the fallback
+    which: int = 0               # name field
+    op: int = 0                  # date_cmp
+    i64: int = 0
+    set64: int = 0
+    value: bool = False          # const
+
+
+def const(v: bool) -> Cond:
+    return Cond(C_CONST, value=bool(v))
+
+
+def _pad16(b: bytearray) -> None:
+    while len(b) % 16:
+        b.append(0)
+
+
+class _FieldDfa:
+    """Patterns that read the same field, deduplicated -> output bits."""
+
+    def __init__(self, what: str):
+        self.what = what
+        self.patterns: List[Pattern] = []
+        self.index: Dict[Tuple, int] = {}
+
+    def bit(self, p: Pattern) -> int:
+        key = (p.kind, p.text, int(p.flags))
+        b = self.index.get(key)
+        if b is None:
+            b = len(self.patterns)
+            if b >= 32:
+                raise NotImplementedError(f"more than 32 distinct patterns on {self.what} in one program")
+            self.index[key] = b
+            self.patterns.append(p)
+        return b
+
+    def compile(self) -> Dfa:
+        return compile_patterns(self.patterns)
+
+
+def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
+    """Append descriptor + tables; returns the descriptor offset.  States are renumbered so that
+    states with a non-empty `out` come last (the kernels test `state >= acc_base`)."""
+    n = d.n_states
+    if n > 65535:
+        raise NotImplementedError("automaton has more than 65535 states")
+    accepting = d.out != 0
+    order = np.concatenate([np.nonzero(~accepting)[0], np.nonzero(accepting)[0]])
+    new_id = np.empty(n, dtype=np.int64)
+    new_id[order] = np.arange(n)
+    acc_base = int((~accepting).sum())
+    direct = direct_limit and n * 512 + n * 8 + 256 <= direct_limit
+    if direct:
+        trans = new_id[d.trans[order]].astype(np.uint16)              # [n, 256]
+        ncols = 256
+    else:
+        trans = new_id[d.ctrans[order]].astype(np.uint16)             # [n, ncls]
+        ncols = trans.shape[1]
+    out = d.out[order].astype(np.uint32)
+    endout = d.endout[order].astype(np.uint32)
+    start = int(new_id[d.start])
+    _pad16(blob)
+    desc_off = len(blob)
+    blob.extend(b"\0" * 64)
+    _pad16(blob)
+    off_trans = len(blob)
+    blob.extend(trans.tobytes()); _pad16(blob)
+    trans_bytes = len(blob) - off_trans
+    off_out = len(blob); blob.extend(out.tobytes()); _pad16(blob)
+    off_endout = len(blob); blob.extend(endout.tobytes()); _pad16(blob)
+    off_cls = len(blob); blob.extend(d.cls.astype(np.uint8).tobytes()); _pad16(blob)
+    table_bytes = len(blob) - off_trans
+    empty_acc = int(out[start]) | int(endout[start])
+    struct.pack_into("<16I", blob, desc_off, n, ncols, start, acc_base, off_trans, trans_bytes, off_out, off_endout,
+                     off_cls, d.n_patterns, empty_acc, table_bytes, 0, 0, 0, 0)
+    return desc_off
+
+
+class ProgramBuilder:
+    def __init__(self):
+        self.queries: List[List[Cond]] = []
+
+    def add_query(self, conds: Sequence[Cond]) -> int:
+        if len(self.queries) >= 32:
+            raise NotImplementedError("at most 32 queries per program")
+        self.queries.append(list(conds) if conds else [const(True)])
+        return len(self.queries) - 1
+
+    def build(self) -> bytes:
+        body = _FieldDfa("content")
+        flags = _FieldDfa("flags")
+        names = [_FieldDfa("filename"), _FieldDfa("id"), _FieldDfa("hostname")]
+        slots: List[Tuple[str, int, bool]] = []          # (field, mode, empty_if_missing)
+        slot_dfas: List[_FieldDfa] = []
+        slot_index: Dict[Tuple, int] = {}
+        recs: List[Tuple] = []                           # packed cond tuples
+        qranges: List[Tuple[int, int]] = []
+        head_mask = body_mask = 0
+        for qi, conds in enumerate(self.queries):
+            begin = len(recs)
+            for c in conds:
+                ref = bit = 0
+                if c.kind == C_BODY:
+                    bit = body.bit(c.pattern); body_mask |= 1 << qi
+                else:
+                    head_mask |= 1 << qi
+                    if c.kind == C_SLOT:
+                        key = (c.field if c.mode == 1 else c.field.lower(), c.mode, c.empty_if_missing)
+                        ref = slot_index.get(key)
+                        if ref is None:
+                            ref = len(slots)
+                            if ref >= 16:
+                                raise NotImplementedError("more than 16 distinct header fields in one program")
+                            slot_index[key] = ref
+                            slots.append(key); slot_dfas.append(_FieldDfa(f"header {c.field}"))
+                        bit = slot_dfas[ref].bit(c.pattern)
+                    elif c.kind == C_FLAGS:
+                        bit = flags.bit(c.pattern)
+                    elif c.kind == C_NAME:
+                        ref = c.which; bit = names[c.which].bit(c.pattern)
+                    elif c.kind == C_CONST:
+                        bit = 1 if c.value else 0
+                recs.append((c.kind, ref, bit, 1 if c.negate else 0, c.if_missing, c.op, c.i64, c.set64))
+            qranges.append((begin, len(recs)))
+
+        blob = bytearray(96)
+        _pad16(blob)
+        off_conds = len(blob)
+        for kind, ref, bit, neg, ifm, op, i64, set64 in recs:
+            blob.extend(struct.pack("<6B2xqQQ", kind, ref, bit, neg, ifm, op, i64, set64 & 0xFFFFFFFFFFFFFFFF, 0))
+        _pad16(blob)
+        off_queries = len(blob)
+        for a, b in qranges:
+            blob.extend(struct.pack("<4I", a, b, 0, 0))
+        _pad16(blob)
+        off_slots = len(blob)
+        blob.extend(b"\0" * (16 * len(slots)))
+        off_key = 0
+        if slots:
+            key_pats = [Pattern("exact_equals", f) if mode == 1 else Pattern("equals", f) for f, mode, _e in slots]
+            off_key = serialize_dfa(compile_patterns(key_pats), blob)
+            for si, (f, mode, empty) in enumerate(slots):
+                off_val = serialize_dfa(slot_dfas[si].compile(), blob)
+                struct.pack_into("<4I", blob, off_slots + 16 * si, mode, off_val, 1 if empty else 0, 0)
+        off_body = serialize_dfa(body.compile(), blob, SMEM_TABLE_LIMIT) if body.patterns else 0
+        if off_body:
+            tb = struct.unpack_from("<I", blob, off_body + 44)[0]
+            if tb > 220 * 1024:
+                raise NotImplementedError(f"content automaton needs {tb} bytes of shared memory (limit 220 KiB)")
+        off_flags = serialize_dfa(flags.compile(), blob) if flags.patterns else 0
+        off_names = [serialize_dfa(nf.compile(), blob) if nf.patterns else 0 for nf in names]
+        _pad16(blob)
+        struct.pack_into("<17I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
+                         len(slots), off_slots, off_key, off_body, off_flags, off_names[0], off_names[1], off_names[2],
+                         head_mask, body_mask)
+        return bytes(blob)
+
+
+def content_batch_program(patterns: Sequence[Pattern]) -> bytes:
+    """One query per pattern, each a single `content` condition (BASELINE configs[2])."""
+    pb = ProgramBuilder()
+    for p in patterns:
+        pb.add_query([Cond(C_BODY, pattern=p)])
+    return pb.build()

@@ -255,7 +255,7 @@ class _RegexBuilder:
 class Pattern:
     """One predicate over a string value.  kind:
     regex(text, flags) | contains | startswith | endswith | equals | has_tag (all via str.lower()),
-    exact_contains (no folding) | cmp_gt | cmp_ge | cmp_lt | cmp_le (raw code-point order)."""
+    exact_contains | exact_equals (no folding) | cmp_gt | cmp_ge | cmp_lt | cmp_le (raw code-point order)."""
     kind: str
     text: str
     flags: int = 0
@@ -301,8 +301,8 @@ def add_pattern(n: Nfa, pid: int, pat: Pattern) -> None:
         acc = n.new(); n.e(end, acc, A_EOS)
         n.accept[acc] = pid
         return
-    if k == "equals":
-        end = _lit_chain(n, n.start, pat.text, True)
+    if k in ("equals", "exact_equals"):
+        end = _lit_chain(n, n.start, pat.text, k == "equals")
         acc = n.new(); n.e(end, acc, A_EOS)
         n.accept[acc] = pid
         return

@@ -45,6 +45,10 @@ const char* fei_last_error(void);
 int fei_init(int device);
 int fei_shutdown(void);
 int fei_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc_major, int* cc_minor);
+/* Page-lock a caller-owned host buffer so fei_corpus_load / fei_scan_hits copy at full PCIe
+ * speed and asynchronously (cudaHostRegister / cudaHostUnregister).                        */
+int fei_host_register(void* p, uint64_t bytes);
+int fei_host_unregister(void* p);
 
 /* ---- packed Memdir corpus ---------------------------------------------------
  * Replaces the per-query file walk of memdir_tools.utils.list_memories
@@ -56,6 +60,8 @@ int fei_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc_major, int* cc_m
  *                         (parse_memory_content, utils.py:105-118), newline-normalised
  *   body / body_off[n+1]  body of record i, already .strip()ped (utils.py:120)
  *   name / name_off[n+1]  file name "ts.uid.host:2,FLAGS" (utils.py:74-95); may be NULL
+ *   name_spans[4n]        where unique_id and hostname sit inside the name (the packer runs
+ *                         the reference's filename regex, utils.py:81); NULL iff name is NULL
  *   ts[n]                 filename timestamp (utils.py:90)
  *   wall[n]               datetime.fromtimestamp(ts) as naive wall-clock seconds (utils.py:94)
  *   flags8[n]             flag letters, byte k = k-th letter, byte 7 = count (<= 7)
@@ -73,6 +79,7 @@ typedef struct fei_corpus_host {
   const uint8_t* hdr;   const uint64_t* hdr_off;
   const uint8_t* body;  const uint64_t* body_off;
   const uint8_t* name;  const uint64_t* name_off;
+  const uint16_t* name_spans; /* 4 per record: unique_id start, length, hostname start, length inside the name */
   const int64_t* ts;
   const int64_t* wall;
   const uint64_t* flags8;

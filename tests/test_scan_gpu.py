@@ -1,0 +1,213 @@
+"""GPU parity of the scan kernels through the C ABI against the oracle (record-level restatement
+of search.py / filter.py) on seeded synthetic corpora plus adversarial records."""
+import re
+
+import numpy as np
+import pytest
+
+from fei_b200 import synth
+from fei_b200.program import (C_BODY, C_DATE_CMP, C_FLAGS, C_FOLDER_SET, C_NAME, C_SLOT, C_STATUS_SET, CMP, Cond, ProgramBuilder,
+                              content_batch_program, const)
+from fei_b200.regexc import Pattern
+from oracle import memdir_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+BATCH32 = ["python", "docker|kubernetes", "neural networks", "react", "angular", "rust", "django", "flask", "terraform", "ansible",
+           "microservices", "big data", "ci/cd", "git", "aws|azure|gcp", "spring boot", r"vue\.js", r"node\.js", "devops", "security",
+           "blockchain", "testing", "databases", "algorithms", "cloud computing", "mobile development", "computer vision",
+           "reinforcement learning", "ui/ux", "web development", "data structures", "machine learning"]
+
+
+def memories_of(recs):
+    return [mo.make_memory(r["filename"], r["folder"], r["status"], synth.file_text(r), True) for r in recs]
+
+
+@pytest.fixture(scope="module")
+def corpus3k(gpu):
+    from fei_b200.corpus import Corpus
+    n = 3000
+    arrays = synth.corpus_arrays(0xFE1, 0, n)
+    c = Corpus().load(arrays)
+    return c, arrays, memories_of(arrays["records"])
+
+
+def test_gpu_generator_and_tiler_roundtrip(gpu):
+    """fei_corpus_synth (device generator + tiler) == host generator, byte for byte, after un-tiling."""
+    from fei_b200.corpus import Corpus
+    n = 2500                                            # crosses window boundaries (1024) with a ragged tail
+    c = Corpus().synth(0xFE1, 100, n)
+    got = c.fetch(0, n)
+    want = synth.corpus_arrays(0xFE1, 100, n)
+    for k in ("hdr_off", "body_off", "ts", "wall", "flags8", "fsb"):
+        assert np.array_equal(got[k], want[k]), k
+    assert bytes(got["hdr"][:int(got["hdr_off"][n])]) == bytes(want["hdr"][:int(want["hdr_off"][n])])
+    assert bytes(got["body"][:int(got["body_off"][n])]) == bytes(want["body"][:int(want["body_off"][n])])
+    st = c.stats()
+    assert st["n"] == n and st["tile_bytes"] >= st["body_bytes"] and st["tile_bytes"] <= st["body_bytes"] + 16 * n
+
+
+def test_load_path_roundtrip_with_odd_lengths(gpu):
+    from fei_b200.corpus import Corpus
+    recs = []
+    for i, ln in enumerate([0, 1, 15, 16, 17, 31, 32, 33, 255, 256, 257, 1000, 5000, 0, 3, 64]):
+        r = synth.record(7, i)
+        r["body"] = bytes((j * 7 + i) % 251 + 1 for j in range(ln))
+        recs.append(r)
+    a = synth.arrays_from_records(recs)
+    c = Corpus().load(a)
+    got = c.fetch(0, len(recs))
+    assert np.array_equal(got["body_off"], a["body_off"])
+    assert bytes(got["body"][:int(a["body_off"][-1])]) == bytes(a["body"][:int(a["body_off"][-1])])
+
+
+def test_batch32_content_patterns_match_reference_semantics(corpus3k):
+    c, arrays, mems = corpus3k
+    prog = content_batch_program([Pattern("regex", p, re.IGNORECASE) for p in BATCH32])
+    masks = c.scan_masks(prog)
+    hits = c.scan_hits(prog, 32)
+    for q, p in enumerate(BATCH32):
+        want = mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}])
+        got = np.nonzero(masks >> np.uint32(q) & np.uint32(1))[0].tolist()
+        assert got == want, p
+        assert hits[q].tolist() == want, p
+
+
+def test_single_regex_with_gaps_and_class_indexed_tables(corpus3k):
+    c, arrays, mems = corpus3k
+    for p in [r"kubernetes.*docker|docker.*kubernetes", r"react|angular", r"\bgit\b", r"^# (research|book review)", r"(?m)^- clean code$",
+              r"\d{3}", r"learning\.$", r"(?s)overview.*summary", r"\w+ design\b", r"[aeiou]{3}"]:
+        pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", p, re.IGNORECASE))])
+        got = np.nonzero(c.scan_masks(pb.build()))[0].tolist()
+        want = mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}])
+        assert got == want, p
+
+
+def _search_prog(conds):
+    """Minimal host compile of reference-style conditions for the fields these tests use."""
+    out = []
+    for f, op, v in conds:
+        fl = f.lower()
+        if fl == "content":
+            kind = {"matches": "regex", "contains": "contains"}[op]
+            out.append(Cond(C_BODY, pattern=Pattern(kind, v if kind == "regex" else v.lower(), re.IGNORECASE if kind == "regex" else 0)))
+        elif fl == "flags":
+            out.append(Cond(C_FLAGS, pattern=Pattern("exact_contains", v.upper())))
+        elif fl == "date":
+            import calendar, dateutil.parser
+            d = dateutil.parser.parse(v)
+            out.append(Cond(C_DATE_CMP, op=CMP[op], i64=calendar.timegm(d.timetuple()) * 1000000 + d.microsecond))
+        else:
+            kind = {"has_tag": "has_tag", "contains": "contains", "matches": "regex", "=": "equals", "startswith": "startswith", "endswith": "endswith"}[op]
+            pat = Pattern(kind, v if kind == "regex" else v.lower(), re.IGNORECASE if kind == "regex" else 0)
+            status_hdr = f in ("Status", "status_value", "state")
+            out.append(Cond(C_SLOT, pattern=pat, field="Status" if status_hdr else f, mode=1 if status_hdr else 0, empty_if_missing=status_hdr))
+    return out
+
+
+def test_multi_field_filter_cfg2(corpus3k):
+    """BASELINE configs[1]: tags + flags + date + body regex (search.py semantics)."""
+    c, arrays, mems = corpus3k
+    import datetime
+    median_ts = int(np.median(arrays["ts"]))
+    t = datetime.datetime.utcfromtimestamp(median_ts).strftime("%Y-%m-%d %H:%M:%S")
+    cases = [
+        [("Tags", "has_tag", "python"), ("flags", "has_flag", "F"), ("date", ">", t), ("content", "matches", r"react|angular")],
+        [("Tags", "has_tag", "python")],
+        [("flags", "has_flag", "F")],
+        [("flags", "has_flag", "FS")],
+        [("date", ">", t)], [("date", "<=", t)],
+        [("Priority", "=", "HIGH"), ("Status", "=", "active")],
+        [("subject", "contains", "review"), ("content", "contains", "review")],
+        [("tags", "contains", "rust"), ("Priority", "contains", "i")],
+        [("Author", "startswith", "j")], [("Version", "endswith", ".0")], [("nope", "contains", "")], [("Tags", "contains", "")],
+        [("state", "matches", "^(active|pending)$")],
+    ]
+    for conds in cases:
+        pb = ProgramBuilder(); pb.add_query(_search_prog(conds))
+        got = np.nonzero(c.scan_masks(pb.build()))[0].tolist()
+        want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
+        assert got == want, conds
+    # all of them as one 14-query program: same masks, one pass
+    pb = ProgramBuilder()
+    for conds in cases:
+        pb.add_query(_search_prog(conds))
+    masks = c.scan_masks(pb.build())
+    for q, conds in enumerate(cases):
+        want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
+        assert np.nonzero(masks >> np.uint32(q) & np.uint32(1))[0].tolist() == want, conds
+
+
+ADVERSARIAL = [
+    # (header text, body) pairs exercising the parser quirks in SURVEY.md 8(a)
+    ("Subject: Beta ", " split here\nTags: x\n---\nbody after second sep"),          # '---' inside a header value
+    ("Tags: a,b\ntags: lower,c\nTags: final,python\n", "dup keys"),                      # duplicate-case keys, last value wins
+    ("  Subject  :  spaced out  \n\tTags\t:\tpython , rust\t\n", "Ünïcödé K ſ body\nwith KELVIN \u212a and long s \u017f"),
+    ("NoColonLine\nTags: python\n: emptykey\nKey:\n", ""),                               # line without colon, empty key, empty value
+    ("Tags:\u00a0python\u2003\n", "nbsp and em-space around the tag"),
+    ("Subject: x\nStatus: done\nStatus: ACTIVE\n", "status twice"),
+    ("", "no headers at all but a body mentioning python and docker then kubernetes"),
+    ("Tags: Python,\u212aelvin\nPriority: HIGH\n", "kelvin sign tag"),
+    ("Subject: caf\u00e9 R\u00c9SUM\u00c9\n", "caf\u00e9 r\u00e9sum\u00e9 \U0001F409 dragon\nline2 react"),
+    ("Tags: a\x0bb,\x1cpython\x1f\n", "odd whitespace controls"),
+]
+
+
+def test_adversarial_records_header_parser_and_unicode(gpu):
+    from fei_b200.corpus import Corpus
+    recs = []
+    for i, (h, b) in enumerate(ADVERSARIAL):
+        r = synth.record(11, i)
+        text = h + "---" + b if True else None
+        hdr_text, sep, rest = text.partition("---")
+        r["hdr"] = hdr_text.encode(); r["body"] = rest.strip().encode(); r["raw_text"] = text
+        recs.append(r)
+    # plus one record with no separator at all
+    r = synth.record(11, 99); r["hdr"] = b""; r["body"] = "just text: no separator python".encode(); r["raw_text"] = "just text: no separator python"
+    r["bits"] = 1
+    recs.append(r)
+    mems = [mo.make_memory(r["filename"], r["folder"], r["status"], r["raw_text"], True) for r in recs]
+    c = Corpus().load(synth.arrays_from_records(recs))
+    cases = [
+        [("Tags", "has_tag", "python")], [("tags", "has_tag", "final")], [("Tags", "has_tag", "lower")], [("tags", "contains", "c")],
+        [("Subject", "=", "beta")], [("subject", "contains", "spaced out")], [("subject", "=", "spaced out")], [("Key", "=", "")],
+        [("Status", "=", "active")], [("state", "=", "done")], [("Tags", "has_tag", "kelvin")], [("Tags", "has_tag", "b")],
+        [("content", "matches", r"\bk")], [("content", "matches", "s")], [("content", "contains", "k")], [("content", "contains", "s")],
+        [("content", "matches", r"caf. r.sum. \S dragon$")], [("content", "matches", r"(?m)^line2")], [("content", "matches", "^$")],
+        [("Subject", "contains", "résumé")], [("Subject", "matches", "RÉSUMÉ$")], [("content", "matches", r"docker.*kubernetes")],
+        [("Priority", "=", "high")], [("nokey", "=", "")], [("", "contains", "emptykey")],
+    ]
+    for conds in cases:
+        pb = ProgramBuilder(); pb.add_query(_search_prog(conds))
+        got = np.nonzero(c.scan_masks(pb.build()))[0].tolist()
+        want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
+        assert got == want, conds
+
+
+def test_filter_semantics_negate_and_missing(corpus3k):
+    """MemoryFilter.matches: exact-case header keys, negate, missing fields (filter.py:67-109)."""
+    c, arrays, mems = corpus3k
+    filters = [
+        [("Tags", r"python", False), ("content", r"python|django|flask", True)],
+        [("Tags", r"ai|machine[- ]learning|neural|llm", False)],
+        [("Tags", r"books|reading|learning", False), ("Subject", r"books|read|learning", False)],
+        [("Priority", r"high", False)], [("Status", r"completed|done|archived", False)], [("Tags", r"trash|delete|remove", False)],
+        [("Nope", r"x", True)], [("Nope", r"x", False)], [("tags", r"python", False)], [("Author", r"^j", True)], [("flags", r"f", False)],
+    ]
+    pb = ProgramBuilder()
+    for conds in filters:
+        cl = []
+        for f, p, neg in conds:
+            pat = Pattern("regex", p, re.IGNORECASE)
+            if f == "content":
+                cl.append(Cond(C_BODY, pattern=pat, negate=neg))
+            elif f == "flags":
+                cl.append(Cond(C_SLOT, pattern=pat, negate=neg, field=f, mode=1, if_missing=2))
+                cl.append(Cond(C_FLAGS, pattern=pat, negate=neg))
+            else:
+                cl.append(Cond(C_SLOT, pattern=pat, negate=neg, field=f, mode=1, if_missing=1 if neg else 0))
+        pb.add_query(cl)
+    masks = c.scan_masks(pb.build())
+    for q, conds in enumerate(filters):
+        want = [i for i, m in enumerate(mems) if mo.filter_accepts(m, [{"field": f, "pattern": p, "negate": n} for f, p, n in conds])]
+        assert np.nonzero(masks >> np.uint32(q) & np.uint32(1))[0].tolist() == want, conds
