@@ -32,7 +32,7 @@ struct DfaView {
   const uint32_t* out;
   const uint32_t* endout;
   const uint8_t* cls;
-  uint32_t n_cols, start, acc_base, empty_acc;
+  uint32_t n_cols, stride, start, n_acc, empty_acc;
 };
 
 __device__ __forceinline__ DfaView dfa_view(const uint8_t* blob, uint32_t off) {
@@ -42,7 +42,7 @@ __device__ __forceinline__ DfaView dfa_view(const uint8_t* blob, uint32_t off) {
   v.out = reinterpret_cast<const uint32_t*>(blob + d->off_out);
   v.endout = reinterpret_cast<const uint32_t*>(blob + d->off_endout);
   v.cls = blob + d->off_cls;
-  v.n_cols = d->n_cols; v.start = d->start; v.acc_base = d->acc_base; v.empty_acc = d->empty_acc;
+  v.n_cols = d->n_cols; v.stride = d->row_stride; v.start = d->start; v.n_acc = d->n_acc; v.empty_acc = d->empty_acc;
   return v;
 }
 
@@ -50,13 +50,13 @@ __device__ __forceinline__ DfaView dfa_view(const uint8_t* blob, uint32_t off) {
 __device__ uint32_t dfa_run(const DfaView& d, const uint8_t* p, uint32_t len) {
   if (len == 0) return d.empty_acc;
   uint32_t s = d.start;
-  uint32_t acc = s >= d.acc_base ? __ldg(d.out + s) : 0u;
+  uint32_t acc = s < d.n_acc ? __ldg(d.out + s) : 0u;
   const bool direct = d.n_cols == 256;
   for (uint32_t i = 0; i < len; ++i) {
     uint32_t b = p[i];
     uint32_t col = direct ? b : __ldg(d.cls + b);
-    s = __ldg(d.trans + s * d.n_cols + col);
-    if (s >= d.acc_base) acc |= __ldg(d.out + s);
+    s = __ldg(d.trans + s * d.stride + col);
+    if (s < d.n_acc) acc |= __ldg(d.out + s);
   }
   return acc | __ldg(d.endout + s);
 }
@@ -242,29 +242,69 @@ struct BodyArgs {
 
 constexpr int kBodyThreads = 1024;
 
-template <bool kDirect>
-__device__ __forceinline__ void dfa_bytes4(uint32_t w, int nbytes, uint32_t& s, uint32_t& acc,
-                                           const uint16_t* __restrict__ trans, const uint32_t* __restrict__ out,
-                                           const uint8_t* __restrict__ cls, uint32_t ncols, uint32_t acc_base) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (j < nbytes) {
-      uint32_t b = (w >> (8 * j)) & 0xFFu;
-      uint32_t col = kDirect ? b : cls[b];
-      s = trans[(kDirect ? (s << 8) : s * ncols) + col];
-      if (s >= acc_base) acc |= out[s];
-    }
-  }
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // PTX shl clamps: n >= 32 -> 0
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+  return r;
 }
 
-template <bool kDirect>
+// One DFA step.  kAcc selects how accepting states are recorded (they are numbered 0..n_acc-1):
+//   1 / 2 : branch-free, bit k of (a0,a1) = "accepting state k was visited" (n_acc <= 32 / <= 64):
+//           no second shared-memory lookup and no divergent branch in the byte loop; the pattern
+//           masks out[k] are OR-ed once per record from the visited-state bits;
+//   0     : generic: out[] lookup when the new state is accepting.
+// Address arithmetic is written so that it lands on the FMA pipe (IMAD) and only the byte extract
+// (PRMT) and the accept bits (SHL/LOP3) use the ALU pipe: the loop is ALU-pipe / LDS-wavefront bound.
+template <bool kDirect, int kAcc>
+struct BodyDfa {
+  uint32_t trans_s;            // shared-space address of the transition table
+  const uint32_t* out; const uint8_t* cls;
+  uint32_t stride2, n_acc;     // stride2 = row stride in bytes
+  uint32_t s, a0;
+  unsigned long long a64;
+  __device__ __forceinline__ void step(uint32_t b) {
+    uint32_t col = kDirect ? b : cls[b];
+    uint32_t t, addr;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(t) : "r"(col), "r"(trans_s));        // IMAD (FMA pipe)
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(s), "r"(stride2), "r"(t));
+    uint16_t nxt;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(nxt) : "r"(addr));
+    s = nxt;
+    if (kAcc == 1) a0 |= shl_clamp(1u, s);            // s >= 32 shifts out: no bit
+    if (kAcc == 2) { unsigned long long bit; asm("shl.b64 %0, %1, %2;" : "=l"(bit) : "l"(1ull), "r"(s)); a64 |= bit; }   // s >= 64: no bit
+    if (kAcc == 0) { if (s < n_acc) a0 |= out[s]; }
+  }
+  __device__ __forceinline__ void word(uint32_t w) {
+    step(__byte_perm(w, 0, 0x4440)); step(__byte_perm(w, 0, 0x4441)); step(__byte_perm(w, 0, 0x4442)); step(__byte_perm(w, 0, 0x4443));
+  }
+  __device__ __forceinline__ void word_partial(uint32_t w, int nbytes) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j < nbytes) step((w >> (8 * j)) & 0xFFu);
+  }
+  __device__ __forceinline__ void reset(uint32_t start) {
+    s = start; a0 = 0; a64 = 0;
+    if (kAcc == 0) a0 = start < n_acc ? out[start] : 0u;
+    if (kAcc == 1) a0 = shl_clamp(1u, start);
+    if (kAcc == 2) a64 = start < 64 ? 1ull << start : 0ull;
+  }
+  __device__ __forceinline__ uint32_t finish(const uint32_t* endout) const {
+    uint32_t acc = endout[s];
+    if (kAcc == 0) return acc | a0;
+    unsigned long long m = kAcc == 1 ? (unsigned long long)a0 : a64;
+    if (n_acc < 64) m &= (1ull << n_acc) - 1ull;
+    while (m) { int k = __ffsll((long long)m) - 1; m &= m - 1; acc |= out[k]; }
+    return acc;
+  }
+};
+
+template <bool kDirect, int kAcc>
 __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_dfa* dd = reinterpret_cast<const fei_prog_dfa*>(a.prog + ph->off_body_dfa);
   const uint32_t table_bytes = dd->table_bytes;
-  // ---- stage the automaton into shared memory with TMA bulk copies
+  // ---- stage the automaton into shared memory with TMA bulk copies (cp.async.bulk + mbarrier)
   if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -276,18 +316,19 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     }
   }
   mbar_wait(&bar, 0);
-  const uint16_t* trans = reinterpret_cast<const uint16_t*>(smem);
-  const uint32_t* out = reinterpret_cast<const uint32_t*>(smem + (dd->off_out - dd->off_trans));
   const uint32_t* endout = reinterpret_cast<const uint32_t*>(smem + (dd->off_endout - dd->off_trans));
-  const uint8_t* cls = smem + (dd->off_cls - dd->off_trans);
-  const uint32_t ncols = dd->n_cols, acc_base = dd->acc_base, start = dd->start;
-  const uint32_t start_out = start >= acc_base ? out[start] : 0u;
+  const uint32_t start = dd->start;
   const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
   const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
   const uint32_t nq = ph->n_queries;
   const uint32_t all_q = nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1u);
   const int lane = threadIdx.x & 31;
   unsigned long long touched = 0;
+  BodyDfa<kDirect, kAcc> d;
+  d.trans_s = smem_u32(smem);
+  d.out = reinterpret_cast<const uint32_t*>(smem + (dd->off_out - dd->off_trans));
+  d.cls = smem + (dd->off_cls - dd->off_trans);
+  d.stride2 = dd->row_stride * 2u; d.n_acc = dd->n_acc;
 
   for (;;) {
     unsigned long long g = 0;
@@ -304,28 +345,24 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     const uint8_t* row = a.tiles + a.grp_base[g] * 16;
     const uint32_t maxu = __shfl_sync(0xffffffffu, units, 0);
     if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
-    uint32_t s = start, acc = start_out;
+    d.reset(start);
+    // software pipeline: the next row's 16 bytes are in flight while this row runs through the DFA
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (0 < units && live) cur = ldg_stream16(row + lane * 16);
     for (uint32_t k = 0; k < maxu; ++k) {
       const uint32_t m = __popc(__ballot_sync(0xffffffffu, k < units));
+      const uint8_t* next_row = row + (uint64_t)m * 16;
+      uint4 nxt = make_uint4(0, 0, 0, 0);
+      if (k + 1 < units && live) nxt = ldg_stream16(next_row + lane * 16);
       if (k < units && live) {
-        uint4 v = ldg_stream16(row + lane * 16);
         int nb = (int)len - (int)(k * 16);
-        if (nb >= 16) {
-          dfa_bytes4<kDirect>(v.x, 4, s, acc, trans, out, cls, ncols, acc_base);
-          dfa_bytes4<kDirect>(v.y, 4, s, acc, trans, out, cls, ncols, acc_base);
-          dfa_bytes4<kDirect>(v.z, 4, s, acc, trans, out, cls, ncols, acc_base);
-          dfa_bytes4<kDirect>(v.w, 4, s, acc, trans, out, cls, ncols, acc_base);
-        } else {
-          dfa_bytes4<kDirect>(v.x, nb, s, acc, trans, out, cls, ncols, acc_base);
-          dfa_bytes4<kDirect>(v.y, nb - 4, s, acc, trans, out, cls, ncols, acc_base);
-          dfa_bytes4<kDirect>(v.z, nb - 8, s, acc, trans, out, cls, ncols, acc_base);
-          dfa_bytes4<kDirect>(v.w, nb - 12, s, acc, trans, out, cls, ncols, acc_base);
-        }
+        if (nb >= 16) { d.word(cur.x); d.word(cur.y); d.word(cur.z); d.word(cur.w); }
+        else { d.word_partial(cur.x, nb); d.word_partial(cur.y, nb - 4); d.word_partial(cur.z, nb - 8); d.word_partial(cur.w, nb - 12); }
       }
-      row += (uint64_t)m * 16;
+      cur = nxt; row = next_row;
     }
     if (live) {
-      acc |= endout[s];
+      const uint32_t acc = d.finish(endout);
       uint32_t hit = 0;
       for (uint32_t q = 0; q < nq; ++q) {
         if (!(alive >> q & 1)) continue;
@@ -342,6 +379,13 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     }
   }
   if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
+}
+
+template <bool kDirect, int kAcc>
+static int launch_body(const BodyArgs& a, unsigned grid, size_t smem, cudaStream_t s) {
+  FEI_CUDA(cudaFuncSetAttribute(k_body<kDirect, kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_body<kDirect, kAcc><<<grid, kBodyThreads, smem, s>>>(a);
+  return FEI_OK;
 }
 
 // ---------------------------------------------------------------- compaction
@@ -453,7 +497,7 @@ static int check_prog(const uint8_t* prog, uint64_t len) {
            d.off_out >= d.off_trans && d.off_endout >= d.off_trans && d.off_cls >= d.off_trans &&
            d.off_out + 4ull * d.n_states <= (uint64_t)d.off_trans + d.table_bytes &&
            d.off_endout + 4ull * d.n_states <= (uint64_t)d.off_trans + d.table_bytes &&
-           2ull * d.n_states * d.n_cols <= d.trans_bytes && d.n_states <= 65535;
+           d.row_stride >= d.n_cols && 2ull * d.n_states * d.row_stride <= d.trans_bytes && d.n_states <= 65535;
   };
   if (!dfa_ok(h.off_key_dfa) || !dfa_ok(h.off_body_dfa) || !dfa_ok(h.off_flags_dfa) || !dfa_ok(h.off_name_dfa[0]) ||
       !dfa_ok(h.off_name_dfa[1]) || !dfa_ok(h.off_name_dfa[2])) { set_error("bad DFA descriptor in program"); return FEI_E_BADARG; }
@@ -502,13 +546,13 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
     BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
                c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>()};
     unsigned grid = (unsigned)cx.sm_count;
-    if (d.n_cols == 256) {
-      FEI_CUDA(cudaFuncSetAttribute(k_body<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_body<true><<<grid, kBodyThreads, smem, s>>>(a);
-    } else {
-      FEI_CUDA(cudaFuncSetAttribute(k_body<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_body<false><<<grid, kBodyThreads, smem, s>>>(a);
-    }
+    uint32_t n_acc = d.n_acc;
+    int acc_mode = n_acc <= 32 ? 1 : n_acc <= 64 ? 2 : 0;
+    bool direct = d.n_cols == 256;
+    int rc;
+    if (direct) rc = acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
+    else rc = acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
+    FEI_TRY(rc);
     ++launches;
   } else if (n && !need_head) {
     // no condition reads the corpus at all (constant queries): every record gets the constant verdict

@@ -1,0 +1,198 @@
+"""Pack an on-disk Memdir into the canonical arrays of include/feiscan.h (the one-time ingest).
+
+Replaces the per-query walk of utils.list_memories (memdir_tools/utils.py:202-253): files are read
+once, in exactly the reference's listing order — folders in os.walk order (utils.py:48), statuses
+cur/new/tmp, inside a directory os.listdir order stably sorted by filename timestamp, newest first
+(utils.py:220,251) — decoded like `open(path, "r")` (UTF-8 strict, universal newlines; undecodable
+files are reported and skipped, utils.py:247-248), split at the first '---' (utils.py:105), body
+.strip()ped (utils.py:120).  Header *parsing* is left to the GPU (k_head); the host only parses the
+headers of records it has to materialise as result dicts.
+"""
+from __future__ import annotations
+
+import calendar
+import os
+import re
+from datetime import datetime
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .memdir_tools import utils as U
+
+REC_NO_SEPARATOR, REC_NONASCII, REC_LOWER_INEXACT = 1, 2, 4
+_LIST_RE = re.compile(r"\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*")          # utils.py:223
+
+
+def read_segment(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
+    path = os.path.join(base, folder, status) if folder else os.path.join(base, status)
+    if not os.path.exists(path):
+        return []
+    out = []
+    for name in os.listdir(path):
+        try:
+            if not _LIST_RE.match(name):
+                continue
+            m = U.FILENAME_RE.match(name)
+            if not m:
+                raise ValueError(f"Invalid memory filename: {name}")
+            with open(os.path.join(path, name), "r") as f:
+                text = f.read()
+            head, sep, rest = text.partition("---")
+            ts = int(m.group(1))
+            out.append({
+                "filename": name, "folder": folder, "status": status, "ts": ts,
+                "uid": m.group(2), "host": m.group(3), "flags": m.group(4),
+                "uid_span": (m.start(2), m.end(2)), "host_span": (m.start(3), m.end(3)),
+                "hdr_text": head if sep else "", "body_text": (rest if sep else text).strip(), "has_sep": bool(sep),
+                "date": datetime.fromtimestamp(ts),
+            })
+        except Exception as e:
+            print(f"Error processing {name}: {e}")
+    out.sort(key=lambda r: r["ts"], reverse=True)
+    return out
+
+
+def memory_dict(rec: Dict[str, Any], include_content: bool) -> Dict[str, Any]:
+    """The dict list_memories yields (utils.py:234-243); headers parsed on the host for materialisation."""
+    headers: Dict[str, str] = {}
+    if rec["has_sep"]:
+        for line in rec["hdr_text"].strip().split("\n"):
+            k, colon, v = line.partition(":")
+            if colon:
+                headers[k.strip()] = v.strip()
+    mem = {"filename": rec["filename"], "folder": rec["folder"], "status": rec["status"], "headers": headers,
+           "metadata": {"timestamp": rec["ts"], "unique_id": rec["uid"], "hostname": rec["host"], "flags": list(rec["flags"]),
+                        "date": rec["date"]}}
+    if include_content:
+        mem["content"] = rec["body_text"]
+    return mem
+
+
+def _flags8(flags: str, name: str) -> int:
+    if len(flags) > 7:
+        raise NotImplementedError(f"{name}: more than 7 flag letters are not supported by the packed layout")
+    v = len(flags) << 56
+    for k, ch in enumerate(flags):
+        v |= ord(ch) << (8 * k)
+    return v
+
+
+def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, int], global_base: int = 0) -> Dict[str, Any]:
+    n = len(recs)
+    hdr_parts = [r["hdr_text"].encode("utf-8") for r in recs]
+    body_parts = [r["body_text"].encode("utf-8") for r in recs]
+    name_parts = [os.fsencode(r["filename"]) for r in recs]
+
+    def blob(parts):
+        off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=n), out=off[1:])
+        data = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if n and off[n] else np.zeros(1, dtype=np.uint8)
+        return data, off
+
+    hdr, hdr_off = blob(hdr_parts)
+    body, body_off = blob(body_parts)
+    name, name_off = blob(name_parts)
+    spans = np.zeros((max(n, 1), 4), dtype=np.uint16)
+    bits = np.zeros(max(n, 1), dtype=np.uint32)
+    for i, r in enumerate(recs):
+        fname = r["filename"]
+        # spans are character offsets; convert to byte offsets when the name has non-ASCII characters
+        (a0, a1), (b0, b1) = r["uid_span"], r["host_span"]
+        if len(name_parts[i]) != len(fname):
+            a0, a1, b0, b1 = (len(os.fsencode(fname[:x])) for x in (a0, a1, b0, b1))
+        spans[i] = (a0, a1 - a0, b0, b1 - b0)
+        b = 0 if r["has_sep"] else REC_NO_SEPARATOR
+        text = r["hdr_text"] + r["body_text"]
+        if not text.isascii():
+            b |= REC_NONASCII
+            if "İ" in text or "Σ" in text:
+                b |= REC_LOWER_INEXACT
+        bits[i] = b
+    ts = np.array([r["ts"] for r in recs], dtype=np.int64)
+    wall = np.array([calendar.timegm(r["date"].timetuple()) for r in recs], dtype=np.int64)
+    f8 = np.array([_flags8(r["flags"], r["filename"]) for r in recs], dtype=np.uint64)
+    fsb = np.array([(folder_ids[r["folder"]] & 0xFFFF) | (U.STANDARD_FOLDERS.index(r["status"]) << 16) | (int(bits[i]) << 24)
+                    for i, r in enumerate(recs)], dtype=np.uint32)
+    return {"n": n, "global_base": global_base, "hdr": hdr, "hdr_off": hdr_off, "body": body, "body_off": body_off,
+            "name": name, "name_off": name_off, "name_spans": spans.reshape(-1), "ts": ts, "wall": wall, "flags8": f8, "fsb": fsb,
+            "any_lower_inexact": bool((bits & REC_LOWER_INEXACT).any()) if n else False}
+
+
+class PackedMemdir:
+    """Host bookkeeping for one packed tree: records in listing order + the device corpus."""
+
+    def __init__(self, base: str):
+        self.base = base
+        self.folders: List[str] = []
+        self.segments: Dict[Tuple[str, str], Tuple[int, int]] = {}
+        self.recs: List[Dict[str, Any]] = []
+        self.arrays: Dict[str, Any] = {}
+        self.corpus = None
+        self.signature: Tuple = ()
+
+    @staticmethod
+    def tree_signature(base: str) -> Tuple:
+        sig = []
+        for root, dirs, _ in os.walk(base):
+            for st in U.STANDARD_FOLDERS:
+                if st in dirs:
+                    p = os.path.join(root, st)
+                    s = os.stat(p)
+                    sig.append((p, s.st_mtime_ns))
+        return tuple(sig)
+
+    def build(self, upload: bool = True) -> "PackedMemdir":
+        self.signature = self.tree_signature(self.base)
+        self.folders = []
+        for root, dirs, _ in os.walk(self.base):
+            if any(st in dirs for st in U.STANDARD_FOLDERS):
+                rel = os.path.relpath(root, self.base)
+                self.folders.append("" if rel == "." else rel)
+        if len(self.folders) > 65535:
+            raise NotImplementedError("more than 65535 folders")
+        self.folder_ids = {f: i for i, f in enumerate(self.folders)}
+        self.recs = []
+        self.segments = {}
+        for folder in self.folders:
+            for st in U.STANDARD_FOLDERS:
+                seg = read_segment(self.base, folder, st)
+                self.segments[(folder, st)] = (len(self.recs), len(self.recs) + len(seg))
+                self.recs.extend(seg)
+        self.arrays = arrays_from_segments(self.recs, self.folder_ids)
+        if upload:
+            from .corpus import Corpus
+            self.corpus = Corpus().load(self.arrays)
+        return self
+
+    def ranges(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> List[Tuple[int, int]]:
+        """Index ranges of the requested (folder, status) pairs in the caller's order (search.py:361-363)."""
+        if folders is None:
+            folders = self.folders
+        if statuses is None:
+            statuses = U.STANDARD_FOLDERS
+        out = []
+        for f in folders:
+            for st in statuses:
+                if st not in U.STANDARD_FOLDERS:
+                    raise ValueError(f"Invalid status: {st}. Must be one of {U.STANDARD_FOLDERS}")
+                r = self.segments.get((f, st))
+                if r and r[1] > r[0]:
+                    out.append(r)
+        return out
+
+
+_cache: Dict[str, PackedMemdir] = {}
+
+
+def packed(base: Optional[str] = None) -> PackedMemdir:
+    """The packed corpus for a tree, rebuilt when any cur/new/tmp directory changed."""
+    base = base or U.MEMDIR_BASE
+    pm = _cache.get(base)
+    if pm is None or pm.signature != PackedMemdir.tree_signature(base):
+        if pm is not None and pm.corpus is not None:
+            pm.corpus.close()
+        pm = PackedMemdir(base).build()
+        _cache[base] = pm
+    return pm

@@ -74,22 +74,31 @@ class _FieldDfa:
 
 def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
     """Append descriptor + tables; returns the descriptor offset.  States are renumbered so that
-    states with a non-empty `out` come last (the kernels test `state >= acc_base`)."""
+    states with a non-empty `out` come first (the kernels test `state < n_acc`, and the body kernel
+    records accepting state k as bit k without a table lookup)."""
     n = d.n_states
     if n > 65535:
         raise NotImplementedError("automaton has more than 65535 states")
     accepting = d.out != 0
-    order = np.concatenate([np.nonzero(~accepting)[0], np.nonzero(accepting)[0]])
+    order = np.concatenate([np.nonzero(accepting)[0], np.nonzero(~accepting)[0]])
     new_id = np.empty(n, dtype=np.int64)
     new_id[order] = np.arange(n)
-    acc_base = int((~accepting).sum())
-    direct = direct_limit and n * 512 + n * 8 + 256 <= direct_limit
+    n_acc = int(accepting.sum())
+    direct = direct_limit and n * 516 + n * 8 + 256 <= direct_limit
     if direct:
         trans = new_id[d.trans[order]].astype(np.uint16)              # [n, 256]
         ncols = 256
     else:
         trans = new_id[d.ctrans[order]].astype(np.uint16)             # [n, ncls]
         ncols = trans.shape[1]
+    # pad rows so that (row_stride / 2) is odd: state s starts at bank (s * stride/2) % 32, which walks
+    # all 32 banks instead of piling every row onto the same ones (bank-conflict spreading)
+    stride = ncols + (ncols & 1)
+    if (stride // 2) % 2 == 0:
+        stride += 2
+    padded = np.zeros((n, stride), dtype=np.uint16)
+    padded[:, :ncols] = trans
+    trans = padded
     out = d.out[order].astype(np.uint32)
     endout = d.endout[order].astype(np.uint32)
     start = int(new_id[d.start])
@@ -105,8 +114,8 @@ def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
     off_cls = len(blob); blob.extend(d.cls.astype(np.uint8).tobytes()); _pad16(blob)
     table_bytes = len(blob) - off_trans
     empty_acc = int(out[start]) | int(endout[start])
-    struct.pack_into("<16I", blob, desc_off, n, ncols, start, acc_base, off_trans, trans_bytes, off_out, off_endout,
-                     off_cls, d.n_patterns, empty_acc, table_bytes, 0, 0, 0, 0)
+    struct.pack_into("<16I", blob, desc_off, n, ncols, start, n_acc, off_trans, trans_bytes, off_out, off_endout,
+                     off_cls, d.n_patterns, empty_acc, table_bytes, stride, 0, 0, 0)
     return desc_off
 
 

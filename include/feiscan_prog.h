@@ -51,15 +51,18 @@ typedef struct fei_prog_hdr {            /* 96 bytes */
 
 typedef struct fei_prog_dfa {            /* 64 bytes; tables follow at the given offsets            */
   uint32_t n_states, n_cols;             /* n_cols == 256: byte-indexed rows; else class-indexed     */
+                                         /* entry (s, col) lives at trans[s * row_stride + col]       */
   uint32_t start;
-  uint32_t acc_base;                     /* states >= acc_base have out != 0                          */
+  uint32_t n_acc;                        /* states 0 .. n_acc-1 are exactly those with out != 0       */
   uint32_t off_trans, trans_bytes;       /* uint16[n_states * n_cols]                                 */
   uint32_t off_out, off_endout;          /* uint32[n_states] each                                     */
   uint32_t off_cls;                      /* uint8[256] byte -> column (class-indexed tables only)     */
   uint32_t n_outputs;
   uint32_t empty_acc;                    /* result mask for the empty string: out[start]|endout[start] */
   uint32_t table_bytes;                  /* trans + out + endout + cls, contiguous from off_trans     */
-  uint32_t reserved[4];
+  uint32_t row_stride;                   /* entries per row; chosen so row_stride/2 is odd: consecutive
+                                            states start in different shared-memory banks              */
+  uint32_t reserved[3];
 } fei_prog_dfa;
 
 typedef struct fei_prog_cond {           /* 32 bytes */

@@ -1,0 +1,183 @@
+"""Memdir part of make_golden.py: run the unmodified reference's search / filter code over a
+seeded on-disk Memdir (synthetic records + adversarial files) and record what it returns."""
+from __future__ import annotations
+
+import base64
+import contextlib
+import io
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+SEED, N_SYNTH = 0xFE1, 400
+
+# (folder, status, filename, raw bytes) — parser and decode quirks
+ADVERSARIAL = [
+    ("", "cur", "1700000500.adv00001.hostA:2,FS", b"Subject: Beta --- split here\nTags: x\n---\nbody after second sep"),
+    ("", "cur", "1700000500.adv00002.hostA:2,", b"Tags: a,b\ntags: lower,c\nTags: final,python\n---\ndup keys"),
+    ("", "new", "1700000501.adv00003.hostB:2,S", "  Subject  :  spaced out  \n\tTags\t:\tpython , rust\t\n---\n\u00dcn\u00efc\u00f6d\u00e9 K \u017f body\nwith KELVIN \u212a and long s \u017f\n".encode()),
+    (".Projects/AI", "cur", "1700000502.adv00004.hostB:2,RSP", b"NoColonLine\nTags: python\n: emptykey\nKey:\n---\n"),
+    (".Projects/AI", "new", "1700000503.adv00005.host-c:2,P", "Tags:\u00a0python\u2003\n---\nnbsp and em-space around the tag".encode()),
+    ("", "cur", "1700000504.adv00006.hostA:2,F", b"Subject: x\r\nStatus: done\r\nStatus: ACTIVE\r\n---\r\ncrlf file\r\nsecond line react\r\n"),
+    ("", "cur", "1700000505.adv00007.hostA:2,", b"no separator at all: just text mentioning python and docker then kubernetes"),
+    (".ToDoLater/Learning", "cur", "1700000506.adv00008.hostA:2,SF", "Tags: Python,\u212aelvin\nPriority: HIGH\n---\nkelvin sign tag".encode()),
+    ("", "tmp", "1700000507.adv00009.hostA:2,", "Subject: caf\u00e9 R\u00c9SUM\u00c9\n---\ncaf\u00e9 r\u00e9sum\u00e9 \U0001F409 dragon\nline2 react".encode()),
+    ("", "cur", "1700000508.adv00010.hostA:2,F", b"Tags: a\x0bb,\x1cpython\x1f\n---\nodd whitespace controls"),
+    ("", "cur", "1700000509.adv00011.hostA:2,", b"Subject: broken utf8\n---\nbad byte \xff\xfe here python"),          # skipped by the reference
+    ("", "cur", "1700000510.adv00012.hostA:2,FRSP", b"Subject: all flags\nTags: python,learning\nDue: 2030-05-05\n---\n\n\n  padded body  \n\n"),
+    ("", "cur", "not-a-memory.txt", b"ignored: name does not match"),
+    ("", "cur", "1700000511.adv00013.hostA:2,Fjunk", b"Subject: trailing junk after flags\n---\nflags F then lowercase junk"),
+    (".Projects/Python", "new", "1700000512.adv00014.hostA:2,", b"---\n---\nbody starts with a separator"),
+    ("", "new", "1700000513.adv00015.hostA:2,", b"Subject: empty body\nTags: python\n---"),
+]
+
+QUERIES = [
+    # (name, [(field, op, value)...], include_content, folders, statuses)
+    ("cfg1_single_regex", [("content", "matches", r"kubernetes.*docker|docker.*kubernetes")], True, None, None),
+    ("cfg2_multi_field", [("Tags", "has_tag", "python"), ("flags", "has_flag", "F"), ("date", ">", "2023-11-14 22:14:00"), ("content", "matches", r"react|angular")], True, None, None),
+    ("tag_python", [("Tags", "has_tag", "python")], False, None, None),
+    ("tag_PYTHON_upper", [("tags", "has_tag", "PYTHON")], False, None, None),
+    ("tag_final_dupkeys", [("Tags", "has_tag", "final")], False, None, None),
+    ("tag_lower_dupkeys", [("tags", "has_tag", "lower")], False, None, None),
+    ("flags_FS", [("flags", "has_flag", "FS")], False, None, None),
+    ("flags_SF", [("flags", "has_flag", "SF")], False, None, None),
+    ("flags_eq_fs", [("flags", "=", "fs")], False, None, None),
+    ("id_eq_upper", [("id", "=", "ADV00001")], False, None, None),
+    ("filename_contains", [("filename", "contains", "hostb")], False, None, None),
+    ("content_without_flag", [("content", "contains", "python")], False, None, None),
+    ("content_with_flag", [("content", "contains", "python")], True, None, None),
+    ("content_matches_empty_nocontent", [("content", "matches", "")], False, None, None),
+    ("keyword_both", [("Subject", "contains", "review"), ("content", "contains", "review")], True, None, None),
+    ("status_hdr_active", [("Status", "=", "active")], False, None, None),
+    ("state_done", [("state", "=", "done")], False, None, None),
+    ("status_maildir_new", [("status", "=", "new")], False, None, None),
+    ("folder_contains_ai", [("folder", "contains", "ai")], False, None, None),
+    ("priority_gt_str", [("priority", ">", "=high")], False, None, None),
+    ("subject_startswith", [("Subject", "startswith", "research")], False, None, None),
+    ("author_endswith", [("author", "endswith", "ng")], False, None, None),
+    ("tags_contains_empty", [("Tags", "contains", "")], False, None, None),
+    ("nope_field", [("nope", "contains", "")], False, None, None),
+    ("empty_conditions", [], False, None, None),
+    ("date_lt", [("date", "<", "2023-11-14 22:14:30")], False, None, None),
+    ("date_eq", [("date", "=", "2023-11-14 22:21:40")], False, None, None),
+    ("date_gt_now", [("date", ">", "now-7d")], False, None, None),
+    ("date_garbage_ne", [("date", "!=", "garbage")], False, None, None),
+    ("kelvin_b", [("content", "matches", r"\bk")], True, None, None),
+    ("long_s", [("content", "matches", "s")], True, None, None),
+    ("multiline", [("content", "matches", r"(?m)^line2")], True, None, None),
+    ("bad_regex", [("content", "matches", r"(unclosed")], True, None, None),
+    ("only_new_root", [("Tags", "has_tag", "python")], False, [""], ["new"]),
+    ("folders_reordered", [("flags", "has_flag", "F")], False, [".Projects/AI", ""], ["new", "cur"]),
+    ("unique_id_meta", [("unique_id", "=", "adv00004")], False, None, None),
+    ("hostname_meta", [("hostname", "contains", "host-c")], False, None, None),
+    ("unknown_op", [("Tags", "fuzzy", "x")], False, None, None),
+    ("subject_ne", [("Subject", "!=", "x")], False, None, None),
+]
+
+RAISING = [
+    ("priority_gt_now", [("Priority", ">", "now-1d")], "TypeError"),
+    ("date_gt_aware", [("date", ">", "2023-11-14T22:14:00+02:00")], "TypeError"),
+]
+
+SORTED = [
+    ("sort_subject", [("Tags", "has_tag", "python")], "Subject", False, None, 0),
+    ("sort_subject_rev_page", [("Tags", "has_tag", "python")], "subject", True, 5, 2),
+    ("sort_date_meta", [("flags", "has_flag", "F")], "date", False, 10, 0),
+    ("sort_mixed_due", [("Tags", "has_tag", "python")], "due", False, None, 0),
+    ("offset_only", [("flags", "has_flag", "S")], None, False, None, 3),
+]
+
+PARSE = ["subject:python tags:learning", "content:/regex pattern/ date>2023-01-01", "priority:high status!=completed", "#python +FS review notes",
+         "date>=2020-01-01", "sort:date limit:5 python", "tags:a,b, c with_content", 'Subject:"quoted phrase" state:active status:new', "+X flags:F",
+         "status_value=done id=abc", "Priority<=low", 'plain words "and a phrase"', "x:/a/ y:// z:/", "status:pending status:cur"]
+
+FILTERS_EXTRA = [
+    {"name": "neg-missing", "conditions": [("Nope", "x", True)], "actions": [{"type": "copy", "target_folder": ".Archive"}]},
+    {"name": "flags-f", "conditions": [("flags", "f", False)], "actions": [{"type": "flag", "flags": "P", "mode": "add"}]},
+    {"name": "lowercase-key", "conditions": [("tags", "python", False)], "actions": [{"type": "move", "target_folder": ".Trash"}]},
+    {"name": "uid", "conditions": [("unique_id", "^adv", False), ("content", "python", True)], "actions": []},
+    {"name": "empty", "conditions": [], "actions": [{"type": "move", "target_folder": ".Trash"}]},
+]
+
+
+def build_corpus(base: str):
+    sys.path.insert(0, REPO)
+    from fei_b200 import synth
+    recs = [synth.record(SEED, i) for i in range(N_SYNTH)]
+    synth.write_memdir(base, recs)
+    for folder, status, name, raw in ADVERSARIAL:
+        d = os.path.join(base, folder, status) if folder else os.path.join(base, status)
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, name), "wb") as f:
+            f.write(raw)
+
+
+def key_of(m):
+    return [m["folder"], m["status"], m["filename"]]
+
+
+def make_memdir(scratch: str, import_reference):
+    ru, rs, rf, rm = import_reference(scratch)
+    base = os.path.join(scratch, "Memdir")
+    build_corpus(base)
+    assert ru.MEMDIR_BASE == base, (ru.MEMDIR_BASE, base)
+    out = {"generator": "tests/golden/make_golden.py memdir", "seed": SEED, "n_synth": N_SYNTH,
+           "adversarial": [[f, s, n, base64.b64encode(raw).decode()] for f, s, n, raw in ADVERSARIAL],
+           "folders": ru.get_memdir_folders(), "queries": [], "raising": [], "sorted": [], "parse": [], "filters": []}
+
+    def run(conds, include_content, folders, statuses, sort=None, rev=False, limit=None, offset=0):
+        q = rs.SearchQuery()
+        for f, op, v in conds:
+            q.add_condition(f, op, v)
+        q.with_content(include_content)
+        if sort:
+            q.set_sort(sort, rev)
+        if limit is not None or offset:
+            q.set_pagination(limit, offset)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = rs.search_memories(q, folders, statuses)
+        return res, buf.getvalue()
+
+    listing, printed = run([], True, None, None)
+    out["listing"] = [key_of(m) for m in listing]
+    out["listing_printed"] = printed
+    for name, conds, inc, folders, statuses in QUERIES:
+        res, printed = run(conds, inc, folders, statuses)
+        out["queries"].append({"name": name, "conditions": conds, "include_content": inc, "folders": folders, "statuses": statuses,
+                               "result": [key_of(m) for m in res], "has_content_key": ["content" in m for m in res][:3]})
+    for name, conds, exc in RAISING:
+        try:
+            run(conds, False, None, None)
+            got = None
+        except Exception as e:
+            got = type(e).__name__
+        assert got == exc, (name, got)
+        out["raising"].append({"name": name, "conditions": conds, "exception": got})
+    for name, conds, sort, rev, limit, offset in SORTED:
+        res, printed = run(conds, False, None, None, sort, rev, limit, offset)
+        out["sorted"].append({"name": name, "conditions": conds, "sort": sort, "reverse": rev, "limit": limit, "offset": offset,
+                              "result": [key_of(m) for m in res], "printed": printed})
+    for s in PARSE:
+        q = rs.parse_search_args(s)
+        out["parse"].append({"input": s, "conditions": q.conditions, "sort_by": q.sort_by, "sort_reverse": q.sort_reverse,
+                             "limit": q.limit, "offset": q.offset, "include_content": q.include_content})
+    # filters: default set + extras, dry run, several status selections
+    for statuses in (None, ["cur", "new", "tmp"], ["cur"]):
+        mgr = rf.create_default_filters()
+        for fx in FILTERS_EXTRA:
+            f = rf.MemoryFilter(fx["name"])
+            for fld, pat, neg in fx["conditions"]:
+                f.add_condition(fld, pat, neg)
+            for a in fx["actions"]:
+                f.add_action(a["type"], **{k: v for k, v in a.items() if k != "type"})
+            mgr.add_filter(f)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            stats = mgr.process_memories(statuses=statuses, dry_run=True)
+        out["filters"].append({"statuses": statuses, "stats": stats})
+    with open(os.path.join(HERE, "memdir_golden.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True, default=str)
+    print("wrote memdir_golden.json:", len(out["listing"]), "memories listed,", len(out["queries"]), "queries,", len(out["filters"]), "filter runs")

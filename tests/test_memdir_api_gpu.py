@@ -1,0 +1,139 @@
+"""GPU parity of the reference-shaped API (search_memories / FilterManager.process_memories / apply_filters)
+on an on-disk Memdir: vs the oracle on the same tree (exact order) and vs the reference-generated goldens."""
+import contextlib
+import io
+
+import pytest
+
+from oracle import memdir_oracle as mo
+from tests.memdir_util import build_tree, key_of, same_modulo_ties
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(gpu, tmp_path_factory):
+    base = str(tmp_path_factory.mktemp("memdir_api") / "Memdir")
+    g = build_tree(base)
+    from fei_b200.memdir_tools import utils as U
+    U.set_memdir_base(base)
+    return base, g
+
+
+def _query(conds, include_content, sort=None, rev=False, limit=None, offset=0):
+    from fei_b200.memdir_tools.search import SearchQuery
+    q = SearchQuery()
+    for f, op, v in conds:
+        q.add_condition(f, op, v)
+    q.with_content(include_content)
+    if sort:
+        q.set_sort(sort, rev)
+    if limit is not None or offset:
+        q.set_pagination(limit, offset)
+    return q
+
+
+def test_search_memories_matches_oracle_and_reference(api):
+    from fei_b200.memdir_tools.search import search_memories
+    base, g = api
+    for q in g["queries"]:
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = search_memories(_query(q["conditions"], q["include_content"]), q["folders"], q["statuses"])
+            mems = mo.listing(base, q["folders"], q["statuses"], q["include_content"])
+        want = [mems[i] for i in mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in q["conditions"]])]
+        assert [key_of(m) for m in res] == [key_of(m) for m in want], q["name"]
+        assert same_modulo_ties([key_of(m) for m in res], q["result"]), q["name"]
+        for a, b in zip(res[:5], want[:5]):                      # result dict shape (utils.py:234-243)
+            assert a["headers"] == b["headers"] and a["metadata"] == b["metadata"] and a.get("content") == b.get("content")
+
+
+def test_raising_queries_raise_typeerror(api):
+    from fei_b200.memdir_tools.search import search_memories
+    base, g = api
+    for q in g["raising"]:
+        with pytest.raises(TypeError):
+            search_memories(_query(q["conditions"], False))
+
+
+def test_sort_and_pagination(api):
+    from fei_b200.memdir_tools.search import search_memories
+    base, g = api
+    for q in g["sorted"]:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = search_memories(_query(q["conditions"], False, q["sort"], q["reverse"], q["limit"], q["offset"]))
+        assert len(res) == len(q["result"]), q["name"]
+        assert ("Unable to sort" in buf.getvalue()) == ("Unable to sort" in q["printed"]), q["name"]
+        if q["sort"] is None or "Unable to sort" in q["printed"]:
+            assert same_modulo_ties([key_of(m) for m in res], q["result"]), q["name"]
+        else:
+            assert sorted(map(tuple, map(key_of, res))) == sorted(map(tuple, q["result"])) or q["limit"] is not None, q["name"]
+
+
+def test_process_memories_and_apply_filters(api):
+    from fei_b200.memdir_tools import filter as F
+    from tests.golden.make_golden_memdir import FILTERS_EXTRA
+    base, g = api
+    for run in g["filters"]:
+        mgr = F.create_default_filters()
+        for fx in FILTERS_EXTRA:
+            f = F.MemoryFilter(fx["name"])
+            for fld, pat, neg in fx["conditions"]:
+                f.add_condition(fld, pat, neg)
+            for a in fx["actions"]:
+                f.add_action(a["type"], **{k: v for k, v in a.items() if k != "type"})
+            mgr.add_filter(f)
+        with contextlib.redirect_stdout(io.StringIO()):
+            stats = mgr.process_memories(statuses=run["statuses"], dry_run=True)
+            again = F.apply_filters(mgr, statuses=run["statuses"], dry_run=True)
+        want = run["stats"]
+        assert stats == again
+        for k in ("total_memories", "filters_applied", "actions_taken", "memories_modified"):
+            assert stats[k] == want[k], (run["statuses"], k)
+        by_id = {d["memory_id"]: d for d in want["details"]}
+        assert sorted(d["memory_id"] for d in stats["details"]) == sorted(by_id)
+        for d in stats["details"]:
+            assert d["filters_applied"] == by_id[d["memory_id"]]["filters_applied"] and d["subject"] == by_id[d["memory_id"]]["subject"]
+
+
+def test_single_record_matches_and_bad_regex(api):
+    import re
+    from fei_b200.memdir_tools import filter as F
+    base, g = api
+    with contextlib.redirect_stdout(io.StringIO()):
+        mems = mo.listing(base, [""], ["cur"], True)[:40]
+    flt = F.MemoryFilter("t").add_condition("Tags", "python").add_condition("content", "django", negate=True)
+    conds = [{"field": "Tags", "pattern": "python", "negate": False}, {"field": "content", "pattern": "django", "negate": True}]
+    for m in mems:
+        assert flt.matches(m) == mo.filter_accepts(m, conds)
+    with pytest.raises(re.error):
+        F.MemoryFilter("bad").add_condition("Tags", "(unclosed").matches(mems[0])
+
+
+def test_real_filter_actions_move_and_flag(gpu, tmp_path):
+    """Not a dry run: matched records are renamed exactly like the reference's apply_actions (filter.py:111-173)."""
+    import os
+    from fei_b200 import synth
+    from fei_b200.memdir_tools import filter as F, utils as U
+    base = str(tmp_path / "Memdir")
+    recs = [synth.record(5, i) for i in range(60)]
+    for r in recs:
+        r["status"], r["status_id"] = "new", 1
+    synth.write_memdir(base, recs)
+    old = U.MEMDIR_BASE
+    U.set_memdir_base(base)
+    try:
+        mgr = F.FilterManager()
+        mgr.add_filter(F.MemoryFilter("hp").add_condition("Priority", "high").add_action("flag", flags="FP", mode="add"))
+        with contextlib.redirect_stdout(io.StringIO()):
+            mems = mo.listing(base, None, ["new"], True)
+        want = [m for m in mems if mo.filter_accepts(m, [{"field": "Priority", "pattern": "high", "negate": False}])]
+        stats = mgr.process_memories(dry_run=False)
+        assert stats["filters_applied"] == len(want)
+        for m in want:
+            new_flags = "".join(sorted(set("".join(m["metadata"]["flags"]) + "FP")))
+            name = m["filename"].split(":2,")[0] + ":2," + new_flags
+            d = os.path.join(base, m["folder"], "new") if m["folder"] else os.path.join(base, "new")
+            assert os.path.exists(os.path.join(d, name)), name
+    finally:
+        U.set_memdir_base(old)

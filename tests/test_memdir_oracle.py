@@ -1,0 +1,86 @@
+"""CPU suite: the Memdir oracle (restated search.py / filter.py / utils.py) against the golden
+results recorded from the unmodified reference; host-side query parsing of the product."""
+import contextlib
+import io
+
+import pytest
+
+from oracle import memdir_oracle as mo
+from tests.memdir_util import build_tree, key_of, same_modulo_ties
+
+
+@pytest.fixture(scope="module")
+def tree(tmp_path_factory):
+    base = str(tmp_path_factory.mktemp("memdir") / "Memdir")
+    g = build_tree(base)
+    return base, g
+
+
+def _conds(c):
+    return [{"field": f, "operator": op, "value": v} for f, op, v in c]
+
+
+def test_listing_order_and_skipped_files(tree):
+    base, g = tree
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        mems = mo.listing(base, None, None, True)
+    assert same_modulo_ties([key_of(m) for m in mems], g["listing"])
+    assert "adv00011" in buf.getvalue() and "Error processing" in buf.getvalue()      # invalid UTF-8 file reported + skipped
+    assert sorted(mo.memdir_folders(base)) == sorted(g["folders"])
+
+
+def test_search_results_match_reference(tree):
+    base, g = tree
+    for q in g["queries"]:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mems = mo.listing(base, q["folders"], q["statuses"], q["include_content"])
+        got = [key_of(mems[i]) for i in mo.run_search(mems, _conds(q["conditions"]))]
+        assert same_modulo_ties(got, q["result"]), q["name"]
+
+
+def test_raising_queries(tree):
+    base, g = tree
+    with contextlib.redirect_stdout(io.StringIO()):
+        mems = mo.listing(base, None, None, False)
+    for q in g["raising"]:
+        with pytest.raises(TypeError):
+            mo.run_search(mems, _conds(q["conditions"]))
+
+
+def test_filter_statistics_match_reference(tree):
+    from tests.golden.make_golden_memdir import FILTERS_EXTRA
+    base, g = tree
+    defaults = [
+        {"name": "Python Content", "conditions": [("Tags", r"python", False), ("content", r"python|django|flask", True)], "actions": [{"type": "move"}, {"type": "flag"}]},
+        {"name": "AI Content", "conditions": [("Tags", r"ai|machine[- ]learning|neural|llm", False)], "actions": [{"type": "move"}]},
+        {"name": "Learning Content", "conditions": [("Tags", r"books|reading|learning", False), ("Subject", r"books|read|learning", False)], "actions": [{"type": "move"}]},
+        {"name": "High Priority", "conditions": [("Priority", r"high", False)], "actions": [{"type": "flag"}]},
+        {"name": "Completed Items", "conditions": [("Status", r"completed|done|archived", False)], "actions": [{"type": "move"}, {"type": "flag"}]},
+        {"name": "Trash Items", "conditions": [("Tags", r"trash|delete|remove", False)], "actions": [{"type": "move"}]},
+    ]
+    filters = [{"name": f["name"], "actions": f["actions"], "conditions": [{"field": a, "pattern": b, "negate": c} for a, b, c in f["conditions"]]}
+               for f in defaults + FILTERS_EXTRA]
+    for run in g["filters"]:
+        statuses = run["statuses"] or ["new"]
+        with contextlib.redirect_stdout(io.StringIO()):
+            mems = mo.listing(base, None, statuses, True)
+        stats = mo.run_filters(mems, filters)
+        want = run["stats"]
+        for k in ("total_memories", "filters_applied", "actions_taken", "memories_modified"):
+            assert stats[k] == want[k], (run["statuses"], k)
+        assert sorted(d["memory_id"] for d in stats["details"]) == sorted(d["memory_id"] for d in want["details"])
+        by_id = {d["memory_id"]: d for d in want["details"]}
+        for d in stats["details"]:
+            assert d["filters_applied"] == by_id[d["memory_id"]]["filters_applied"] and d["subject"] == by_id[d["memory_id"]]["subject"]
+
+
+def test_parse_search_args_matches_reference():
+    """Host-side query grammar of the product (fei_b200/memdir_tools/search.py) vs the reference's output."""
+    from fei_b200.memdir_tools.search import parse_search_args
+    from tests.conftest import load_golden
+    for case in load_golden("memdir_golden.json")["parse"]:
+        q = parse_search_args(case["input"])
+        assert q.conditions == case["conditions"], case["input"]
+        assert (q.sort_by, q.sort_reverse, q.limit, q.offset, q.include_content) == \
+               (case["sort_by"], case["sort_reverse"], case["limit"], case["offset"], case["include_content"]), case["input"]
