@@ -102,23 +102,94 @@ struct HeadArgs {
   uint32_t* alive;
 };
 
-__global__ void __launch_bounds__(128) k_head(HeadArgs a) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+constexpr int kHeadThreads = 256;
+constexpr uint32_t kHeadStageBytes = 56 * 1024;    // shared-memory window for one CTA's contiguous header span
+
+__device__ __forceinline__ bool eval_meta_cond(const fei_prog_cond& cd, uint32_t flags_acc, int64_t wall, uint32_t fsb) {
+  switch (cd.kind) {
+    case FEI_C_CONST: return cd.bit != 0;
+    case FEI_C_FLAGS: return ((flags_acc >> cd.bit) & 1u) != cd.negate;
+    case FEI_C_DATE_CMP: {
+      int64_t v = wall * 1000000ll, o = cd.i64;
+      switch (cd.cmp_op) {
+        case FEI_CMP_GT: return v > o; case FEI_CMP_LT: return v < o;
+        case FEI_CMP_GE: return v >= o; case FEI_CMP_LE: return v <= o;
+        case FEI_CMP_EQ: return v == o; default: return v != o;
+      }
+    }
+    case FEI_C_FOLDER_SET: return (cd.set64 >> (fsb & 0xFFFFu) & 1ull) != 0;
+    case FEI_C_STATUS_SET: return (cd.set64 >> ((fsb >> 16) & 0xFFu) & 1ull) != 0;
+    default: return true;                                      // slot / name / body: decided later
+  }
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count);
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
+
+__global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
+  extern __shared__ __align__(128) uint8_t stage[];
+  __shared__ uint64_t bar;
+  const uint64_t i0 = blockIdx.x * (uint64_t)kHeadThreads;
+  const uint64_t i = i0 + threadIdx.x;
+  const bool valid = i < a.n;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
   const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
   const fei_prog_slot* slots = reinterpret_cast<const fei_prog_slot*>(a.prog + ph->off_slots);
   const uint32_t nslots = ph->n_slots;
+  const uint32_t nq = ph->n_queries;
 
+  // ---- phase 1: meta predicates only (16-24 bytes per record); most records die here and never
+  //      have their header text read (the reference short-circuits the same way, search.py:328-331)
+  uint32_t flags_acc = 0, fsb = 0, pre = 0;
+  int64_t wall = 0;
+  if (valid) {
+    fsb = a.fsb[i]; wall = a.wall[i];
+    if (ph->off_flags_dfa) {                                   // flags string (search.py:105-106): up to 7 letters in flags8
+      uint64_t f = a.flags8[i];
+      uint8_t fb[8];
+      for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f >> (8 * k));
+      flags_acc = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, (uint32_t)(f >> 56));
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+      bool ok = true;
+      for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
+        const fei_prog_cond& cd = conds[c];
+        if (cd.kind == FEI_C_SLOT && cd.if_missing == 2) { ++c; continue; }   // header-or-fallback pair: decided in phase 2
+        ok = eval_meta_cond(cd, flags_acc, wall, fsb);
+      }
+      if (ok) pre |= 1u << q;
+    }
+  }
+  const bool need_hdr = nslots && (pre & ph->slot_mask);
+  // ---- stage this CTA's contiguous header span into shared memory with one TMA bulk copy
+  const uint8_t* hbase = a.hdr;                                // h = hbase + hdr_off[i]
+  if (__syncthreads_or(need_hdr)) {
+    const uint64_t last = i0 + kHeadThreads < a.n ? i0 + kHeadThreads : a.n;
+    const uint64_t lo = a.hdr_off[i0] & ~15ull, hi = a.hdr_off[last];
+    const uint64_t bytes = (hi - lo + 15) & ~15ull;
+    if (bytes && bytes <= kHeadStageBytes) {
+      if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+      __syncthreads();
+      if (threadIdx.x == 0) { mbar_expect_tx(&bar, (uint32_t)bytes); bulk_g2s(stage, a.hdr + lo, (uint32_t)bytes, &bar); }
+      mbar_wait(&bar, 0);
+      hbase = stage - lo;
+    }
+  }
+  if (!valid) return;
+  if (pre == 0) { a.alive[i] = 0; return; }
+
+  // ---- phase 2: header parse (only if some surviving query reads a header), names, full evaluation
   uint32_t slot_acc[FEI_MAX_SLOTS];
   uint32_t present = 0;
-  if (nslots) {
+  if (need_hdr) {
     uint32_t first_off[FEI_MAX_SLOTS], first_len[FEI_MAX_SLOTS];
     uint32_t have_first = 0;
     DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
-    const uint8_t* h = a.hdr + a.hdr_off[i];
-    const uint8_t* hend = a.hdr + a.hdr_off[i + 1];
+    const uint8_t* h = hbase + a.hdr_off[i];
+    const uint8_t* hend = hbase + a.hdr_off[i + 1];
     const uint8_t* p = h;
     while (p < hend) {
       const uint8_t* eol = p; const uint8_t* colon = nullptr;
@@ -144,60 +215,38 @@ __global__ void __launch_bounds__(128) k_head(HeadArgs a) {
       }
       p = eol + 1;
     }
-    for (uint32_t s = 0; s < nslots; ++s)
-      if (!(present >> s & 1) && slots[s].empty_if_missing) {   // headers.get("Status", "")
-        slot_acc[s] = reinterpret_cast<const fei_prog_dfa*>(a.prog + slots[s].off_val_dfa)->empty_acc;
-        present |= 1u << s;
-      }
   }
-
-  // flags string (search.py:105-106): up to 7 letters packed in flags8
-  uint32_t flags_acc = 0;
-  if (ph->off_flags_dfa) {
-    uint64_t f = a.flags8[i];
-    uint8_t fb[8];
-    uint32_t fl = (uint32_t)(f >> 56);
-    for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f >> (8 * k));
-    flags_acc = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, fl);
-  }
+  for (uint32_t s = 0; s < nslots; ++s)
+    if (!(present >> s & 1) && slots[s].empty_if_missing) {   // headers.get("Status", "")
+      slot_acc[s] = reinterpret_cast<const fei_prog_dfa*>(a.prog + slots[s].off_val_dfa)->empty_acc;
+      present |= 1u << s;
+    }
   uint32_t name_acc[3] = {0, 0, 0};
-  for (int k = 0; k < 3; ++k) {
-    if (!ph->off_name_dfa[k]) continue;
-    const uint8_t* nb = a.name + a.name_off[i];
-    uint32_t nl = (uint32_t)(a.name_off[i + 1] - a.name_off[i]);
-    if (k > 0) { const uint16_t* sp = a.name_spans + 4 * i + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
-    name_acc[k] = dfa_run(dfa_view(a.prog, ph->off_name_dfa[k]), nb, nl);
+  if (pre & ph->name_mask) {
+    for (int k = 0; k < 3; ++k) {
+      if (!ph->off_name_dfa[k]) continue;
+      const uint8_t* nb = a.name + a.name_off[i];
+      uint32_t nl = (uint32_t)(a.name_off[i + 1] - a.name_off[i]);
+      if (k > 0) { const uint16_t* sp = a.name_spans + 4 * i + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
+      name_acc[k] = dfa_run(dfa_view(a.prog, ph->off_name_dfa[k]), nb, nl);
+    }
   }
-
   uint32_t alive = 0;
-  const uint32_t fsb = a.fsb[i];
-  for (uint32_t q = 0; q < ph->n_queries; ++q) {
+  for (uint32_t q = 0; q < nq; ++q) {
+    if (!(pre >> q & 1)) continue;
     bool ok = true;
     for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
       const fei_prog_cond& cd = conds[c];
       bool r;
       switch (cd.kind) {
         case FEI_C_BODY: continue;                              // evaluated by k_body
-        case FEI_C_CONST: r = cd.bit != 0; break;
         case FEI_C_SLOT:
           if (present >> cd.ref & 1) { r = ((slot_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; if (cd.if_missing == 2) ++c; }
           else if (cd.if_missing == 2) continue;               // header absent: the next condition is the fallback field
           else r = cd.if_missing != 0;
           break;
-        case FEI_C_FLAGS: r = ((flags_acc >> cd.bit) & 1u) != cd.negate; break;
         case FEI_C_NAME: r = ((name_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; break;
-        case FEI_C_DATE_CMP: {
-          int64_t v = a.wall[i] * 1000000ll, o = cd.i64;
-          switch (cd.cmp_op) {
-            case FEI_CMP_GT: r = v > o; break; case FEI_CMP_LT: r = v < o; break;
-            case FEI_CMP_GE: r = v >= o; break; case FEI_CMP_LE: r = v <= o; break;
-            case FEI_CMP_EQ: r = v == o; break; default: r = v != o; break;
-          }
-          break;
-        }
-        case FEI_C_FOLDER_SET: r = (cd.set64 >> (fsb & 0xFFFFu) & 1ull) != 0; break;
-        case FEI_C_STATUS_SET: r = (cd.set64 >> ((fsb >> 16) & 0xFFu) & 1ull) != 0; break;
-        default: r = false;
+        default: r = eval_meta_cond(cd, flags_acc, wall, fsb);
       }
       ok = r;
     }
@@ -535,7 +584,8 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   if (n && need_head) {
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
                c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>()};
-    k_head<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+    FEI_CUDA(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadStageBytes));
+    k_head<<<(unsigned)((n + kHeadThreads - 1) / kHeadThreads), kHeadThreads, kHeadStageBytes, s>>>(a);
     ++launches;
   }
   FEI_CUDA(cudaEventRecord(c->ev[2], s));

@@ -138,7 +138,7 @@ class ProgramBuilder:
         slot_index: Dict[Tuple, int] = {}
         recs: List[Tuple] = []                           # packed cond tuples
         qranges: List[Tuple[int, int]] = []
-        head_mask = body_mask = 0
+        head_mask = body_mask = slot_mask = name_mask = 0
         for qi, conds in enumerate(self.queries):
             begin = len(recs)
             for c in conds:
@@ -148,6 +148,7 @@ class ProgramBuilder:
                 else:
                     head_mask |= 1 << qi
                     if c.kind == C_SLOT:
+                        slot_mask |= 1 << qi
                         key = (c.field if c.mode == 1 else c.field.lower(), c.mode, c.empty_if_missing)
                         ref = slot_index.get(key)
                         if ref is None:
@@ -160,6 +161,7 @@ class ProgramBuilder:
                     elif c.kind == C_FLAGS:
                         bit = flags.bit(c.pattern)
                     elif c.kind == C_NAME:
+                        name_mask |= 1 << qi
                         ref = c.which; bit = names[c.which].bit(c.pattern)
                     elif c.kind == C_CONST:
                         bit = 1 if c.value else 0
@@ -193,9 +195,9 @@ class ProgramBuilder:
         off_flags = serialize_dfa(flags.compile(), blob) if flags.patterns else 0
         off_names = [serialize_dfa(nf.compile(), blob) if nf.patterns else 0 for nf in names]
         _pad16(blob)
-        struct.pack_into("<17I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
+        struct.pack_into("<19I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
                          len(slots), off_slots, off_key, off_body, off_flags, off_names[0], off_names[1], off_names[2],
-                         head_mask, body_mask)
+                         head_mask, body_mask, slot_mask, name_mask)
         return bytes(blob)
 
 

@@ -46,7 +46,9 @@ typedef struct fei_prog_hdr {            /* 96 bytes */
   uint32_t off_name_dfa[3];
   uint32_t head_mask;                    /* queries that have at least one non-body condition        */
   uint32_t body_mask;                    /* queries that have at least one body condition            */
-  uint32_t reserved[7];
+  uint32_t slot_mask;                    /* queries that read at least one header slot                */
+  uint32_t name_mask;                    /* queries that read filename / id / hostname                */
+  uint32_t reserved[5];
 } fei_prog_hdr;
 
 typedef struct fei_prog_dfa {            /* 64 bytes; tables follow at the given offsets            */
