@@ -322,6 +322,7 @@ struct BodyDfa {
     if (kAcc == 1) a0 |= shl_clamp(1u, s);            // s >= 32 shifts out: no bit
     if (kAcc == 2) { unsigned long long bit; asm("shl.b64 %0, %1, %2;" : "=l"(bit) : "l"(1ull), "r"(s)); a64 |= bit; }   // s >= 64: no bit
     if (kAcc == 0) { if (s < n_acc) a0 |= out[s]; }
+    // kAcc == 3 ("sticky" single-pattern automaton): nothing to record, the verdict is endout[final state]
   }
   __device__ __forceinline__ void word(uint32_t w) {
     step(__byte_perm(w, 0, 0x4440)); step(__byte_perm(w, 0, 0x4441)); step(__byte_perm(w, 0, 0x4442)); step(__byte_perm(w, 0, 0x4443));
@@ -338,6 +339,7 @@ struct BodyDfa {
   }
   __device__ __forceinline__ uint32_t finish(const uint32_t* endout) const {
     uint32_t acc = endout[s];
+    if (kAcc == 3) return acc;
     if (kAcc == 0) return acc | a0;
     unsigned long long m = kAcc == 1 ? (unsigned long long)a0 : a64;
     if (n_acc < 64) m &= (1ull << n_acc) - 1ull;
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
   d.out = reinterpret_cast<const uint32_t*>(smem + (dd->off_out - dd->off_trans));
   d.cls = smem + (dd->off_cls - dd->off_trans);
   d.stride2 = dd->row_stride * 2u; d.n_acc = dd->n_acc;
+  const uint32_t sticky_state = dd->sticky ? dd->sticky - 1u : 0xFFFFFFFFu;
 
   for (;;) {
     unsigned long long g = 0;
@@ -409,6 +412,8 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
         else { d.word_partial(cur.x, nb); d.word_partial(cur.y, nb - 4); d.word_partial(cur.z, nb - 8); d.word_partial(cur.w, nb - 12); }
       }
       cur = nxt; row = next_row;
+      // sticky automaton: stop reading this group as soon as every live lane has either matched or ended
+      if (kAcc == 3 && __ballot_sync(0xffffffffu, live && k + 1 < units && d.s != sticky_state) == 0) break;
     }
     if (live) {
       const uint32_t acc = d.finish(endout);
@@ -597,11 +602,11 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
                c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>()};
     unsigned grid = (unsigned)cx.sm_count;
     uint32_t n_acc = d.n_acc;
-    int acc_mode = n_acc <= 32 ? 1 : n_acc <= 64 ? 2 : 0;
+    int acc_mode = d.sticky ? 3 : n_acc <= 32 ? 1 : n_acc <= 64 ? 2 : 0;
     bool direct = d.n_cols == 256;
     int rc;
-    if (direct) rc = acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
-    else rc = acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
+    if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
+    else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
     FEI_TRY(rc);
     ++launches;
   } else if (n && !need_head) {

@@ -68,8 +68,8 @@ class _FieldDfa:
             self.patterns.append(p)
         return b
 
-    def compile(self) -> Dfa:
-        return compile_patterns(self.patterns)
+    def compile(self, sticky: bool = False) -> Dfa:
+        return compile_patterns(self.patterns, sticky=sticky and len(self.patterns) == 1)
 
 
 def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
@@ -114,8 +114,11 @@ def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
     off_cls = len(blob); blob.extend(d.cls.astype(np.uint8).tobytes()); _pad16(blob)
     table_bytes = len(blob) - off_trans
     empty_acc = int(out[start]) | int(endout[start])
+    sticky = 0
+    if d.sticky_state >= -1:
+        sticky = 0xFFFFFFFF if d.sticky_state < 0 else 1 + int(new_id[d.sticky_state])
     struct.pack_into("<16I", blob, desc_off, n, ncols, start, n_acc, off_trans, trans_bytes, off_out, off_endout,
-                     off_cls, d.n_patterns, empty_acc, table_bytes, stride, 0, 0, 0)
+                     off_cls, d.n_patterns, empty_acc, table_bytes, stride, sticky, 0, 0)
     return desc_off
 
 
@@ -187,7 +190,7 @@ class ProgramBuilder:
             for si, (f, mode, empty) in enumerate(slots):
                 off_val = serialize_dfa(slot_dfas[si].compile(), blob)
                 struct.pack_into("<4I", blob, off_slots + 16 * si, mode, off_val, 1 if empty else 0, 0)
-        off_body = serialize_dfa(body.compile(), blob, SMEM_TABLE_LIMIT) if body.patterns else 0
+        off_body = serialize_dfa(body.compile(sticky=True), blob, SMEM_TABLE_LIMIT) if body.patterns else 0
         if off_body:
             tb = struct.unpack_from("<I", blob, off_body + 44)[0]
             if tb > 220 * 1024:

@@ -383,6 +383,7 @@ class Dfa:
     n_patterns: int
     cls: np.ndarray = field(default=None)     # [256] uint8 byte classes
     ctrans: np.ndarray = field(default=None)  # [n_states, n_cls] int32
+    sticky_state: int = -2                    # >= 0: absorbing "matched" state of a sticky DFA; -1: sticky, can never match
 
     @property
     def n_states(self) -> int:
@@ -399,13 +400,33 @@ class Dfa:
         return acc | int(self.endout[s])
 
 
-def compile_patterns(patterns: Sequence[Pattern], max_states: int = 30000) -> Dfa:
+def compile_patterns(patterns: Sequence[Pattern], max_states: int = 30000, sticky: bool = False) -> Dfa:
+    """sticky=True (single pattern only): once the pattern has matched the automaton parks in one absorbing
+    state whose `endout` carries the verdict, so a scan kernel needs no per-byte accept bookkeeping and can
+    stop reading a record early."""
     if len(patterns) > 32:
         raise ValueError("at most 32 patterns per DFA")
     n = Nfa()
     for pid, p in enumerate(patterns):
         add_pattern(n, pid, p)
-    return _determinize(n, len(patterns), max_states)
+    d = _determinize(n, len(patterns), max_states)
+    if sticky and len(patterns) == 1:
+        d = make_sticky(d)
+    return d
+
+
+def make_sticky(d: Dfa) -> Dfa:
+    acc = np.nonzero(d.out != 0)[0]
+    T = d.trans.copy(); out = d.out.copy(); endout = d.endout.copy()
+    T[acc, :] = acc[:, None]                      # self-loops: a match can never be lost again
+    endout[acc] |= out[acc]
+    out[:] = 0                                    # the verdict is read from endout only
+    T, out, endout, start = _minimize(T, out, endout, d.start)
+    nd = Dfa(trans=T, out=out, endout=endout, start=start, n_patterns=d.n_patterns)
+    _byte_classes(nd)
+    absorbing = np.nonzero((T == np.arange(T.shape[0])[:, None]).all(axis=1) & (endout != 0))[0]
+    nd.sticky_state = int(absorbing[0]) if absorbing.size else -1
+    return nd
 
 
 def _determinize(n: Nfa, npat: int, max_states: int) -> Dfa:

@@ -64,7 +64,9 @@ typedef struct fei_prog_dfa {            /* 64 bytes; tables follow at the given
   uint32_t table_bytes;                  /* trans + out + endout + cls, contiguous from off_trans     */
   uint32_t row_stride;                   /* entries per row; chosen so row_stride/2 is odd: consecutive
                                             states start in different shared-memory banks              */
-  uint32_t reserved[3];
+  uint32_t sticky;                       /* 0: not sticky.  Else 1 + id of the absorbing "matched" state (0xFFFFFFFF: sticky
+                                            but nothing can match): out[] is all zero, the verdict is endout[final state]     */
+  uint32_t reserved[2];
 } fei_prog_dfa;
 
 typedef struct fei_prog_cond {           /* 32 bytes */
