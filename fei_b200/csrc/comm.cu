@@ -90,46 +90,95 @@ extern "C" int fei_comm_destroy(void) {
   return FEI_OK;
 }
 
+// All-gatherv of the scan result of every rank.  Two wire formats, chosen per call from the gathered counts:
+//   sparse : the compacted per-query index lists (8 B per hit), one grouped ncclBroadcast per (rank, query)
+//            segment straight into its final position;
+//   dense  : when the lists would be larger than the per-record hit masks (4 B per record) — typical for
+//            many-pattern batches where most records hit — the masks are all-gathered instead (one
+//            ncclAllGather) and the global ordered lists are compacted from them on demand.
+// Either way rank-order concatenation is the global listing order.
 extern "C" int fei_comm_allgather_hits(fei_corpus* c, uint32_t nq, uint64_t* const* hits, const uint64_t* cap,
                                        uint64_t* nhits_total, uint64_t* counts_out) {
   FEI_TRY(require_ready());
   if (!c || nq == 0 || nq > 32 || nq != c->last_nq) { set_error("no matching scan result on this corpus (run fei_scan_count / fei_scan_hits first)"); return FEI_E_STATE; }
   if (!g.comm) { set_error("fei_comm_init() has not been called"); return FEI_E_STATE; }
   cudaStream_t s = ctx().stream;
-  int R = g.nranks;
-  // 1. counts: nq u64 per rank
-  FEI_TRY(g.counts_dev.ensure((size_t)(R + 1) * 32 * sizeof(uint64_t)));
-  uint64_t* mine = g.counts_dev.as<uint64_t>() + (size_t)R * 32;
-  FEI_CUDA(cudaMemcpyAsync(mine, c->last_counts, nq * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  FEI_NCCL(g.AllGather(mine, g.counts_dev.p, nq, ncclUint64, g.comm, s));
-  std::vector<uint64_t> counts((size_t)R * nq);
-  FEI_CUDA(cudaMemcpyAsync(counts.data(), g.counts_dev.p, counts.size() * 8, cudaMemcpyDeviceToHost, s));
+  const int R = g.nranks;
+  const uint32_t W = nq + 2;                                   // per-rank record: counts[nq], n, global_base
+  FEI_TRY(g.counts_dev.ensure((size_t)(R + 1) * 34 * sizeof(uint64_t)));
+  uint64_t mine_h[34];
+  for (uint32_t q = 0; q < nq; ++q) mine_h[q] = c->last_counts[q];
+  mine_h[nq] = c->n; mine_h[nq + 1] = c->global_base;
+  uint64_t* mine = g.counts_dev.as<uint64_t>() + (size_t)R * 34;
+  FEI_CUDA(cudaMemcpyAsync(mine, mine_h, W * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  FEI_NCCL(g.AllGather(mine, g.counts_dev.p, W, ncclUint64, g.comm, s));
+  std::vector<uint64_t> info((size_t)R * W);
+  FEI_CUDA(cudaMemcpyAsync(info.data(), g.counts_dev.p, info.size() * 8, cudaMemcpyDeviceToHost, s));
   FEI_CUDA(cudaStreamSynchronize(s));
-  if (counts_out) memcpy(counts_out, counts.data(), counts.size() * 8);
-  // 2. layout of the gathered lists: query-major, ranks concatenated in order
-  std::vector<uint64_t> qbase(nq + 1, 0), tot(nq, 0);
-  for (uint32_t q = 0; q < nq; ++q) { for (int r = 0; r < R; ++r) tot[q] += counts[(size_t)r * nq + q]; qbase[q + 1] = qbase[q] + tot[q]; }
-  FEI_TRY(g.gathered.ensure((qbase[nq] + 1) * sizeof(uint64_t)));
-  FEI_NCCL(g.GroupStart());
-  for (uint32_t q = 0; q < nq; ++q) {
-    uint64_t pos = qbase[q];
-    for (int r = 0; r < R; ++r) {
-      uint64_t cnt = counts[(size_t)r * nq + q];
-      if (cnt) {
-        const void* src = c->hit_lists.as<uint64_t>() + (size_t)q * c->hit_list_stride;   // only read on the root
-        FEI_NCCL(g.Broadcast(src, g.gathered.as<uint64_t>() + pos, cnt, ncclUint64, r, g.comm, s));
-      }
-      pos += cnt;
-    }
+  std::vector<uint64_t> tot(nq, 0);
+  uint64_t list_entries = 0, n_total = 0, n_max = 0;
+  for (int r = 0; r < R; ++r) {
+    for (uint32_t q = 0; q < nq; ++q) { uint64_t v = info[(size_t)r * W + q]; tot[q] += v; list_entries += v; if (counts_out) counts_out[(size_t)r * nq + q] = v; }
+    uint64_t nr = info[(size_t)r * W + nq];
+    n_total += nr; if (nr > n_max) n_max = nr;
   }
-  FEI_NCCL(g.GroupEnd());
+  for (uint32_t q = 0; q < nq; ++q) if (nhits_total) nhits_total[q] = tot[q];
+  const bool want_host = hits && cap;
+  const bool dense = list_entries * 8 > (uint64_t)R * n_max * 4;
   bool truncated = false;
-  for (uint32_t q = 0; q < nq; ++q) {
-    if (nhits_total) nhits_total[q] = tot[q];
-    if (hits && hits[q] && cap) {
+  if (!dense) {
+    std::vector<uint64_t> qbase(nq + 1, 0);
+    for (uint32_t q = 0; q < nq; ++q) qbase[q + 1] = qbase[q] + tot[q];
+    FEI_TRY(g.gathered.ensure((qbase[nq] + 1) * sizeof(uint64_t)));
+    FEI_NCCL(g.GroupStart());
+    for (uint32_t q = 0; q < nq; ++q) {
+      uint64_t pos = qbase[q];
+      for (int r = 0; r < R; ++r) {
+        uint64_t cnt = info[(size_t)r * W + q];
+        if (cnt) {
+          const void* src = c->hit_lists.as<uint64_t>() + (size_t)q * c->hit_list_stride;   // only read on the root
+          FEI_NCCL(g.Broadcast(src, g.gathered.as<uint64_t>() + pos, cnt, ncclUint64, r, g.comm, s));
+        }
+        pos += cnt;
+      }
+    }
+    FEI_NCCL(g.GroupEnd());
+    for (uint32_t q = 0; want_host && q < nq; ++q) {
+      if (!hits[q]) continue;
       uint64_t take = tot[q] < cap[q] ? tot[q] : cap[q];
       if (take < tot[q]) truncated = true;
       if (take) FEI_CUDA(cudaMemcpyAsync(hits[q], g.gathered.as<uint64_t>() + qbase[q], take * 8, cudaMemcpyDeviceToHost, s));
+    }
+  } else {
+    // dense: gather the masks (every rank contributes n_max entries; the tail of short shards is ignored)
+    if (c->hits.bytes < n_max * sizeof(uint32_t)) {            // shorter shard than the longest one: grow, keep contents
+      DevBuf nb;
+      FEI_TRY(nb.alloc(n_max * sizeof(uint32_t)));
+      FEI_CUDA(cudaMemsetAsync(nb.p, 0, n_max * sizeof(uint32_t), s));
+      if (c->n) FEI_CUDA(cudaMemcpyAsync(nb.p, c->hits.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      FEI_CUDA(cudaStreamSynchronize(s));
+      void* tp = nb.p; nb.p = c->hits.p; c->hits.p = tp;
+      size_t tb = nb.bytes; nb.bytes = c->hits.bytes; c->hits.bytes = tb;
+    }
+    FEI_TRY(g.gathered.ensure((size_t)R * n_max * sizeof(uint32_t)));
+    FEI_NCCL(g.AllGather(c->hits.p, g.gathered.p, n_max, 3 /* ncclUint32 */, g.comm, s));
+    if (want_host) {
+      static CompactScratch sc; static DevBuf lists;
+      std::vector<uint64_t> written(nq, 0);
+      for (int r = 0; r < R; ++r) {
+        uint64_t nr = info[(size_t)r * W + nq], gb = info[(size_t)r * W + nq + 1];
+        uint64_t cnt[32], stride = 1;
+        FEI_TRY(compact_masks(g.gathered.as<uint32_t>() + (size_t)r * n_max, nr, nq, gb, sc, cnt, &lists, &stride, nullptr, s));
+        for (uint32_t q = 0; q < nq; ++q) {
+          if (!hits[q] || !cnt[q]) continue;
+          uint64_t room = cap[q] > written[q] ? cap[q] - written[q] : 0;
+          uint64_t take = cnt[q] < room ? cnt[q] : room;
+          if (take < cnt[q]) truncated = true;
+          if (take) FEI_CUDA(cudaMemcpyAsync(hits[q] + written[q], lists.as<uint64_t>() + (size_t)q * stride, take * 8, cudaMemcpyDeviceToHost, s));
+          written[q] += take;
+        }
+        FEI_CUDA(cudaStreamSynchronize(s));
+      }
     }
   }
   FEI_CUDA(cudaStreamSynchronize(s));

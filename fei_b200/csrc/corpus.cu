@@ -125,13 +125,13 @@ int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off
   uint64_t n_groups = n_windows * (kWindow / 32);
   c->n_groups = n_groups;
   uint64_t slots = n_groups * 32;
-  DevBuf len, gunits;
-  FEI_TRY(len.alloc((n ? n : 1) * sizeof(uint32_t)));
-  FEI_TRY(gunits.alloc((n_groups ? n_groups : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->grp_rec.alloc((slots ? slots : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->grp_len.alloc((slots ? slots : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->rec_pos.alloc((n ? n : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->grp_base.alloc((n_groups + 1) * sizeof(uint64_t)));
+  DevBuf& len = c->tmp_len; DevBuf& gunits = c->tmp_gunits;
+  FEI_TRY(len.ensure((n ? n : 1) * sizeof(uint32_t)));
+  FEI_TRY(gunits.ensure((n_groups ? n_groups : 1) * sizeof(uint32_t)));
+  FEI_TRY(c->grp_rec.ensure((slots ? slots : 1) * sizeof(uint32_t)));
+  FEI_TRY(c->grp_len.ensure((slots ? slots : 1) * sizeof(uint32_t)));
+  FEI_TRY(c->rec_pos.ensure((n ? n : 1) * sizeof(uint32_t)));
+  FEI_TRY(c->grp_base.ensure((n_groups + 1) * sizeof(uint64_t)));
   if (n == 0) { FEI_CUDA(cudaMemsetAsync(c->grp_base.p, 0, sizeof(uint64_t), s)); c->tile_bytes = 0; return FEI_OK; }
   k_units<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_body_off, n, len.as<uint32_t>());
   k_window_sort<<<(unsigned)n_windows, kWindow, 0, s>>>(len.as<uint32_t>(), n, c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
@@ -141,7 +141,7 @@ int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off
   FEI_CUDA(cudaMemcpyAsync(&total_units, c->grp_base.as<uint64_t>() + n_groups, 8, cudaMemcpyDeviceToHost, s));
   FEI_CUDA(cudaStreamSynchronize(s));
   c->tile_bytes = total_units * 16;
-  FEI_TRY(c->tiles.alloc(c->tile_bytes + 64));
+  FEI_TRY(c->tiles.ensure(c->tile_bytes + 64));
   unsigned blocks = (unsigned)((n_groups * 32 + 255) / 256);
   k_tile_copy<<<blocks, 256, 0, s>>>(d_body, d_body_off, c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
                                      c->grp_base.as<uint64_t>(), n_groups, c->tiles.as<uint8_t>());
@@ -175,7 +175,7 @@ __global__ void k_synth_write(uint64_t seed, uint64_t first, uint64_t n, const u
 }
 
 static int upload(DevBuf& b, const void* src, size_t bytes, size_t slack, cudaStream_t s) {
-  FEI_TRY(b.alloc(bytes + slack + 16));
+  FEI_TRY(b.ensure(bytes + slack + 16));
   if (bytes) FEI_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
   if (slack) FEI_CUDA(cudaMemsetAsync((uint8_t*)b.p + bytes, 0, slack, s));
   return FEI_OK;
@@ -230,11 +230,14 @@ extern "C" int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h) {
   } else { c->name.release(); c->name_off.release(); c->name_spans.release(); c->name_bytes = 0; }
   for (uint64_t i = 0; i < n; ++i)
     if (boff[i + 1] - boff[i] > (32u << 20)) { set_error("record %llu: body larger than 32 MiB is not supported", (unsigned long long)i); return FEI_E_UNSUPPORTED; }
-  DevBuf body, body_off;
+  DevBuf& body = c->stage_body; DevBuf& body_off = c->stage_body_off;
   FEI_TRY(upload(body, h->body, c->body_bytes, 32, s));
   FEI_TRY(upload(body_off, boff, (n + 1) * 8, 0, s));
   FEI_CUDA(cudaEventRecord(c->ev[1], s));
   FEI_TRY(build_tiles(c, body.as<uint8_t>(), body_off.as<uint64_t>(), s));
+  // the canonical body is only a staging area: keep it for the next batch when it is small (streaming
+  // loads of host batches), drop it for big resident corpora so HBM holds one copy of the text
+  if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); }
   FEI_CUDA(cudaEventElapsedTime(&c->timing.h2d_ms, c->ev[0], c->ev[1]));
   c->loaded = true;
   return FEI_OK;

@@ -22,6 +22,10 @@ constexpr int kWindow = 1024;
 constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
 }
 
+namespace fei {
+struct CompactScratch { DevBuf blk_counts, blk_offsets, totals; };
+}
+
 struct fei_corpus {
   uint64_t n = 0, global_base = 0;
   uint64_t hdr_bytes = 0, body_bytes = 0, name_bytes = 0, tile_bytes = 0;
@@ -29,8 +33,10 @@ struct fei_corpus {
   bool loaded = false;
   fei::DevBuf hdr, hdr_off, name, name_off, name_spans, ts, wall, flags8, fsb;
   fei::DevBuf tiles, grp_base, grp_rec, grp_len, rec_pos;
+  fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
   // scan scratch (grown on demand, reused across scans)
-  fei::DevBuf prog, hits, blk_counts, blk_offsets, totals, hit_lists, work_counter, scan_tmp;
+  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp;
+  fei::CompactScratch compact;
   uint64_t hit_list_stride = 0;          // entries per query in hit_lists (last fei_scan_hits)
   uint32_t last_nq = 0;
   uint64_t last_counts[32] = {0};
@@ -42,4 +48,6 @@ namespace fei {
 // builds tiles from a canonical body blob already on the device (body has >= 32 bytes of slack)
 int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off, cudaStream_t s);
 int exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, DevBuf& tmp, cudaStream_t s);
+int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t global_base, CompactScratch& sc,
+                  uint64_t* counts_out, DevBuf* lists, uint64_t* stride_out, uint32_t* launches, cudaStream_t s);
 }

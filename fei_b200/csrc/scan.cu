@@ -640,34 +640,42 @@ static int finish_timing(fei_corpus* c, bool compacted) {
   return FEI_OK;
 }
 
-// counts (+ optional lists) on the device; totals copied to c->last_counts
-static int compact(fei_corpus* c, bool want_lists) {
-  Context& cx = ctx();
-  cudaStream_t s = cx.stream;
-  uint64_t n = c->n; uint32_t nq = c->last_nq;
+// Order-preserving compaction of a mask array into per-query lists of global indices.
+// counts_out[q] = hits of query q; when `lists` is given, lists[q * stride + k] = k-th hit (stride = max count).
+int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t global_base, CompactScratch& sc,
+                  uint64_t* counts_out, DevBuf* lists, uint64_t* stride_out, uint32_t* launches, cudaStream_t s) {
   uint64_t per_block = (uint64_t)kCompactBlock * kCompactPer;
   uint64_t nblocks = (n + per_block - 1) / per_block;
-  for (uint32_t q = 0; q < 32; ++q) c->last_counts[q] = 0;
-  if (n == 0) { FEI_CUDA(cudaEventRecord(c->ev[4], s)); return FEI_OK; }
-  FEI_TRY(c->blk_counts.ensure(nblocks * nq * sizeof(uint32_t)));
-  FEI_TRY(c->blk_offsets.ensure(nblocks * nq * sizeof(uint64_t)));
-  FEI_TRY(c->totals.ensure(32 * sizeof(uint64_t)));
-  k_count<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(c->hits.as<uint32_t>(), n, nq, c->blk_counts.as<uint32_t>());
-  k_scan_blocks<<<nq, 1024, 0, s>>>(c->blk_counts.as<uint32_t>(), nblocks, nq, c->blk_offsets.as<uint64_t>(), c->totals.as<uint64_t>());
-  c->timing.kernel_launches += 2;
-  FEI_CUDA(cudaMemcpyAsync(c->last_counts, c->totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  for (uint32_t q = 0; q < nq; ++q) counts_out[q] = 0;
+  if (stride_out) *stride_out = 1;
+  if (n == 0) return FEI_OK;
+  FEI_TRY(sc.blk_counts.ensure(nblocks * nq * sizeof(uint32_t)));
+  FEI_TRY(sc.blk_offsets.ensure(nblocks * nq * sizeof(uint64_t)));
+  FEI_TRY(sc.totals.ensure(32 * sizeof(uint64_t)));
+  k_count<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, sc.blk_counts.as<uint32_t>());
+  k_scan_blocks<<<nq, 1024, 0, s>>>(sc.blk_counts.as<uint32_t>(), nblocks, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());
+  if (launches) *launches += 2;
+  FEI_CUDA(cudaMemcpyAsync(counts_out, sc.totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   FEI_CUDA(cudaStreamSynchronize(s));
-  if (want_lists) {
+  if (lists) {
     uint64_t stride = 1;
-    for (uint32_t q = 0; q < nq; ++q) if (c->last_counts[q] > stride) stride = c->last_counts[q];
-    c->hit_list_stride = stride;
-    FEI_TRY(c->hit_lists.ensure(stride * nq * sizeof(uint64_t)));
-    k_emit<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(c->hits.as<uint32_t>(), n, nq, c->blk_offsets.as<uint64_t>(), c->global_base, stride,
-                                                       c->hit_lists.as<uint64_t>());
-    c->timing.kernel_launches += 1;
+    for (uint32_t q = 0; q < nq; ++q) if (counts_out[q] > stride) stride = counts_out[q];
+    if (stride_out) *stride_out = stride;
+    FEI_TRY(lists->ensure(stride * nq * sizeof(uint64_t)));
+    k_emit<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, sc.blk_offsets.as<uint64_t>(), global_base, stride, lists->as<uint64_t>());
+    if (launches) *launches += 1;
   }
-  FEI_CUDA(cudaEventRecord(c->ev[4], s));
   FEI_CUDA(cudaGetLastError());
+  return FEI_OK;
+}
+
+// counts + lists on the device; totals copied to c->last_counts
+static int compact(fei_corpus* c, bool want_lists) {
+  cudaStream_t s = ctx().stream;
+  for (uint32_t q = 0; q < 32; ++q) c->last_counts[q] = 0;
+  FEI_TRY(compact_masks(c->hits.as<uint32_t>(), c->n, c->last_nq, c->global_base, c->compact, c->last_counts,
+                        want_lists ? &c->hit_lists : nullptr, &c->hit_list_stride, &c->timing.kernel_launches, s));
+  FEI_CUDA(cudaEventRecord(c->ev[4], s));
   return FEI_OK;
 }
 
