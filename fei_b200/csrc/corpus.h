@@ -35,7 +35,7 @@ struct fei_corpus {
   fei::DevBuf tiles, grp_base, grp_rec, grp_len, rec_pos;
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
   // scan scratch (grown on demand, reused across scans)
-  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp;
+  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors;
   fei::CompactScratch compact;
   uint64_t hit_list_stride = 0;          // entries per query in hit_lists (last fei_scan_hits)
   uint32_t last_nq = 0;

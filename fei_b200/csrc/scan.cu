@@ -128,68 +128,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
 
-__global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
-  extern __shared__ __align__(128) uint8_t stage[];
-  __shared__ uint64_t bar;
-  const uint64_t i0 = blockIdx.x * (uint64_t)kHeadThreads;
-  const uint64_t i = i0 + threadIdx.x;
-  const bool valid = i < a.n;
+// Phase 2 for one record: header parse (if `hptr`), name fields, evaluation of the queries left in `pre`.
+__device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint32_t flags_acc, const uint8_t* hptr, uint32_t hlen, bool parse) {
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
   const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
   const fei_prog_slot* slots = reinterpret_cast<const fei_prog_slot*>(a.prog + ph->off_slots);
   const uint32_t nslots = ph->n_slots;
-  const uint32_t nq = ph->n_queries;
-
-  // ---- phase 1: meta predicates only (16-24 bytes per record); most records die here and never
-  //      have their header text read (the reference short-circuits the same way, search.py:328-331)
-  uint32_t flags_acc = 0, fsb = 0, pre = 0;
-  int64_t wall = 0;
-  if (valid) {
-    fsb = a.fsb[i]; wall = a.wall[i];
-    if (ph->off_flags_dfa) {                                   // flags string (search.py:105-106): up to 7 letters in flags8
-      uint64_t f = a.flags8[i];
-      uint8_t fb[8];
-      for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f >> (8 * k));
-      flags_acc = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, (uint32_t)(f >> 56));
-    }
-    for (uint32_t q = 0; q < nq; ++q) {
-      bool ok = true;
-      for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
-        const fei_prog_cond& cd = conds[c];
-        if (cd.kind == FEI_C_SLOT && cd.if_missing == 2) { ++c; continue; }   // header-or-fallback pair: decided in phase 2
-        ok = eval_meta_cond(cd, flags_acc, wall, fsb);
-      }
-      if (ok) pre |= 1u << q;
-    }
-  }
-  const bool need_hdr = nslots && (pre & ph->slot_mask);
-  // ---- stage this CTA's contiguous header span into shared memory with one TMA bulk copy
-  const uint8_t* hbase = a.hdr;                                // h = hbase + hdr_off[i]
-  if (__syncthreads_or(need_hdr)) {
-    const uint64_t last = i0 + kHeadThreads < a.n ? i0 + kHeadThreads : a.n;
-    const uint64_t lo = a.hdr_off[i0] & ~15ull, hi = a.hdr_off[last];
-    const uint64_t bytes = (hi - lo + 15) & ~15ull;
-    if (bytes && bytes <= kHeadStageBytes) {
-      if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-      __syncthreads();
-      if (threadIdx.x == 0) { mbar_expect_tx(&bar, (uint32_t)bytes); bulk_g2s(stage, a.hdr + lo, (uint32_t)bytes, &bar); }
-      mbar_wait(&bar, 0);
-      hbase = stage - lo;
-    }
-  }
-  if (!valid) return;
-  if (pre == 0) { a.alive[i] = 0; return; }
-
-  // ---- phase 2: header parse (only if some surviving query reads a header), names, full evaluation
   uint32_t slot_acc[FEI_MAX_SLOTS];
   uint32_t present = 0;
-  if (need_hdr) {
+  if (parse) {
     uint32_t first_off[FEI_MAX_SLOTS], first_len[FEI_MAX_SLOTS];
     uint32_t have_first = 0;
     DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
-    const uint8_t* h = hbase + a.hdr_off[i];
-    const uint8_t* hend = hbase + a.hdr_off[i + 1];
+    const uint8_t* h = hptr;
+    const uint8_t* hend = hptr + hlen;
     const uint8_t* p = h;
     while (p < hend) {
       const uint8_t* eol = p; const uint8_t* colon = nullptr;
@@ -225,14 +178,16 @@ __global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
   if (pre & ph->name_mask) {
     for (int k = 0; k < 3; ++k) {
       if (!ph->off_name_dfa[k]) continue;
-      const uint8_t* nb = a.name + a.name_off[i];
-      uint32_t nl = (uint32_t)(a.name_off[i + 1] - a.name_off[i]);
-      if (k > 0) { const uint16_t* sp = a.name_spans + 4 * i + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
+      const uint8_t* nb = a.name + a.name_off[rec];
+      uint32_t nl = (uint32_t)(a.name_off[rec + 1] - a.name_off[rec]);
+      if (k > 0) { const uint16_t* sp = a.name_spans + 4 * rec + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
       name_acc[k] = dfa_run(dfa_view(a.prog, ph->off_name_dfa[k]), nb, nl);
     }
   }
+  const int64_t wall = a.wall[rec];
+  const uint32_t fsb = a.fsb[rec];
   uint32_t alive = 0;
-  for (uint32_t q = 0; q < nq; ++q) {
+  for (uint32_t q = 0; q < ph->n_queries; ++q) {
     if (!(pre >> q & 1)) continue;
     bool ok = true;
     for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
@@ -252,7 +207,100 @@ __global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
     }
     if (ok) alive |= 1u << q;
   }
-  a.alive[i] = alive;
+  a.alive[rec] = alive;
+}
+
+// Phase 1 for one record: meta predicates only (20 bytes per record).  Returns the queries still possible.
+__device__ __forceinline__ uint32_t head_meta(const HeadArgs& a, uint64_t i, uint32_t& flags_acc) {
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
+  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
+  const uint32_t fsb = a.fsb[i]; const int64_t wall = a.wall[i];
+  flags_acc = 0;
+  if (ph->off_flags_dfa) {                                     // flags string (search.py:105-106): up to 7 letters in flags8
+    uint64_t f = a.flags8[i];
+    uint8_t fb[8];
+    for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f >> (8 * k));
+    flags_acc = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, (uint32_t)(f >> 56));
+  }
+  uint32_t pre = 0;
+  for (uint32_t q = 0; q < ph->n_queries; ++q) {
+    bool ok = true;
+    for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
+      const fei_prog_cond& cd = conds[c];
+      if (cd.kind == FEI_C_SLOT && cd.if_missing == 2) { ++c; continue; }     // header-or-fallback pair: decided in phase 2
+      ok = eval_meta_cond(cd, flags_acc, wall, fsb);
+    }
+    if (ok) pre |= 1u << q;
+  }
+  return pre;
+}
+
+// Dense variant (many records survive the meta predicates): one CTA = 256 consecutive records whose
+// contiguous header span is staged into shared memory by a single TMA bulk copy; every thread then
+// parses its own record from shared memory.
+__global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
+  extern __shared__ __align__(128) uint8_t stage[];
+  __shared__ uint64_t bar;
+  const uint64_t i0 = blockIdx.x * (uint64_t)kHeadThreads;
+  const uint64_t i = i0 + threadIdx.x;
+  const bool valid = i < a.n;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  uint32_t flags_acc = 0, pre = 0;
+  if (valid) pre = head_meta(a, i, flags_acc);
+  const bool need_hdr = ph->n_slots && (pre & ph->slot_mask);
+  bool staged = false;
+  uint64_t lo = 0;
+  if (__syncthreads_or(need_hdr)) {
+    const uint64_t last = i0 + kHeadThreads < a.n ? i0 + kHeadThreads : a.n;
+    lo = a.hdr_off[i0] & ~15ull;
+    const uint64_t bytes = (a.hdr_off[last] - lo + 15) & ~15ull;
+    staged = bytes && bytes <= kHeadStageBytes;
+    if (staged) {
+      if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+      __syncthreads();
+      if (threadIdx.x == 0) { mbar_expect_tx(&bar, (uint32_t)bytes); bulk_g2s(stage, a.hdr + lo, (uint32_t)bytes, &bar); }
+      mbar_wait(&bar, 0);
+    }
+  }
+  if (!valid) return;
+  if (pre == 0) { a.alive[i] = 0; return; }
+  const uint64_t off = a.hdr_off[i];
+  head_finish(a, i, pre, flags_acc, staged ? stage + (off - lo) : a.hdr + off, (uint32_t)(a.hdr_off[i + 1] - off), need_hdr);
+}
+
+// Sparse variant, used when the meta predicates are selective: k_head_meta streams the 20-byte meta
+// columns, finalises every record that needs no header text and appends the few survivors to a work
+// list; k_head_parse then gives each survivor its own thread at full occupancy (a survivor's serial
+// header parse no longer pins a CTA full of already-finished threads), and the dead records' header
+// text is never read.
+struct Survivor { uint32_t rec, pre, flags_acc; };
+
+__global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restrict__ list, unsigned int* __restrict__ count) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  uint32_t flags_acc = 0, pre = 0;
+  const bool valid = i < a.n;
+  if (valid) pre = head_meta(a, i, flags_acc);
+  const bool later = valid && (pre & (ph->slot_mask | ph->name_mask)) != 0;
+  if (valid && !later) a.alive[i] = pre;                       // no header / name condition left: pre is the verdict
+  const uint32_t bal = __ballot_sync(0xffffffffu, later);
+  if (bal) {
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(count, (unsigned int)__popc(bal));   // one atomic per warp
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (later) list[base + __popc(bal & ((1u << lane) - 1u))] = Survivor{(uint32_t)i, pre, flags_acc};
+  }
+}
+
+__global__ void __launch_bounds__(128) k_head_parse(HeadArgs a, const Survivor* __restrict__ list, unsigned int n_list) {
+  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_list) return;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const Survivor sv = list[t];
+  const uint64_t off = a.hdr_off[sv.rec];
+  head_finish(a, sv.rec, sv.pre, sv.flags_acc, a.hdr + off, (uint32_t)(a.hdr_off[sv.rec + 1] - off), (sv.pre & ph->slot_mask) != 0);
 }
 
 // ---------------------------------------------------------------- body kernel
@@ -575,10 +623,10 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   c->last_nq = h.n_queries;
   FEI_TRY(c->prog.ensure(prog_len + 16));
   FEI_TRY(c->hits.ensure((n ? n : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->work_counter.ensure(2 * sizeof(unsigned long long)));
+  FEI_TRY(c->work_counter.ensure(4 * sizeof(unsigned long long)));
   FEI_CUDA(cudaEventRecord(c->ev[0], s));
   FEI_CUDA(cudaMemcpyAsync(c->prog.p, prog, prog_len, cudaMemcpyHostToDevice, s));
-  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(unsigned long long), s));
+  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, 4 * sizeof(unsigned long long), s));
   bool need_head = h.head_mask != 0;
   bool need_body = h.off_body_dfa != 0 && h.body_mask != 0;
   if ((h.off_name_dfa[0] || h.off_name_dfa[1] || h.off_name_dfa[2]) && !c->name.p) {
@@ -589,9 +637,23 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   if (n && need_head) {
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
                c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>()};
-    FEI_CUDA(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadStageBytes));
-    k_head<<<(unsigned)((n + kHeadThreads - 1) / kHeadThreads), kHeadThreads, kHeadStageBytes, s>>>(a);
+    // selective meta predicates first: stream the meta columns, collect survivors
+    FEI_TRY(c->survivors.ensure((n + 32) * sizeof(Survivor)));
+    unsigned int* d_count = reinterpret_cast<unsigned int*>(c->work_counter.as<unsigned long long>() + 2);
+    k_head_meta<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
     ++launches;
+    unsigned int n_surv = 0;
+    FEI_CUDA(cudaMemcpyAsync(&n_surv, d_count, sizeof(n_surv), cudaMemcpyDeviceToHost, s));
+    FEI_CUDA(cudaStreamSynchronize(s));
+    if ((uint64_t)n_surv * 4 > n) {
+      // most records need their header anyway: the span-staging kernel redoes the (cheap) meta phase for everybody
+      FEI_CUDA(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadStageBytes));
+      k_head<<<(unsigned)((n + kHeadThreads - 1) / kHeadThreads), kHeadThreads, kHeadStageBytes, s>>>(a);
+      ++launches;
+    } else if (n_surv) {
+      k_head_parse<<<(n_surv + 127) / 128, 128, 0, s>>>(a, c->survivors.as<Survivor>(), n_surv);
+      ++launches;
+    }
   }
   FEI_CUDA(cudaEventRecord(c->ev[2], s));
   if (n && need_body) {

@@ -27,9 +27,23 @@ def ts_of(key):
 
 
 def same_modulo_ties(a, b):
-    """Equal as ordered lists up to permutations among entries of one (folder, status, timestamp) group:
-    os.listdir order is file-system specific and the reference's sort is stable on timestamp only."""
-    if len(a) != len(b):
+    """Equal up to what is file-system specific: the order in which os.walk / os.listdir enumerate
+    directories and files.  Inside one (folder, status) directory the reference's order is newest
+    timestamp first with ties in listdir order; across directories it is os.walk order.  So: same
+    multiset, and inside every (folder, status) group the same timestamp sequence, groups contiguous."""
+    if sorted(map(tuple, a)) != sorted(map(tuple, b)):
         return False
-    norm = lambda lst: [(k[0], k[1], ts_of(k)) for k in lst]
-    return norm(a) == norm(b) and sorted(map(tuple, a)) == sorted(map(tuple, b))
+
+    def groups(lst):
+        out, seen = {}, []
+        for k in lst:
+            g = (k[0], k[1])
+            if g not in out:
+                out[g] = []
+                seen.append(g)
+            elif seen[-1] != g:
+                return None                     # a (folder, status) group must be contiguous
+            out[g].append(ts_of(k))
+        return out
+    ga, gb = groups(a), groups(b)
+    return ga is not None and gb is not None and ga == gb
