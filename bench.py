@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -161,7 +161,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entries", type=int, default=10_000_000, help="synthetic Memdir entries per GPU")
@@ -240,12 +240,13 @@ def main():
             return tot[:nq]
         return counts
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                # sampled through warm-up (same workload) and the timed region
+        time.sleep(0.3)
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     wall0 = time.perf_counter()
     dev_ms = body_ms = compact_ms = 0.0
     launches = 0

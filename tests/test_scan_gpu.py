@@ -211,3 +211,50 @@ def test_filter_semantics_negate_and_missing(corpus3k):
     for q, conds in enumerate(filters):
         want = [i for i, m in enumerate(mems) if mo.filter_accepts(m, [{"field": f, "pattern": p, "negate": n} for f, p, n in conds])]
         assert np.nonzero(masks >> np.uint32(q) & np.uint32(1))[0].tolist() == want, conds
+
+
+def test_empty_and_tiny_corpora(gpu):
+    """n = 0, n = 1, empty bodies / headers, 32 queries in one program."""
+    from fei_b200.corpus import Corpus
+    prog = content_batch_program([Pattern("regex", p, re.IGNORECASE) for p in BATCH32])
+    empty = Corpus().load(synth.arrays_from_records([]))
+    assert empty.scan_masks(prog).size == 0
+    assert [h.tolist() for h in empty.scan_hits(prog, 32)] == [[]] * 32
+    pb = ProgramBuilder(); pb.add_query(_search_prog([("Tags", "has_tag", "python"), ("flags", "has_flag", "F")]))
+    assert empty.scan_count(pb.build(), 1).tolist() == [0]
+    r = synth.record(3, 0); r["hdr"] = b""; r["body"] = b""
+    one = Corpus().load(synth.arrays_from_records([r]))
+    pb = ProgramBuilder()
+    pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "", re.IGNORECASE))])            # matches the empty body
+    pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "x", re.IGNORECASE))])
+    pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "^$", re.IGNORECASE))])
+    pb.add_query(_search_prog([("Status", "=", "")]))                                     # headers.get("Status", "") == ""
+    pb.add_query(_search_prog([("Tags", "contains", "")]))                                # missing header -> None -> False
+    pb.add_query([])                                                                       # no conditions: matches everything
+    assert int(one.scan_masks(pb.build())[0]) == 0b101101
+
+
+def test_hits_capacity_error_and_counts(corpus3k):
+    from fei_b200 import _abi
+    c, arrays, mems = corpus3k
+    pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "python", re.IGNORECASE))])
+    prog = pb.build()
+    n_hits = int(c.scan_count(prog, 1)[0])
+    assert n_hits == len(mo.run_search(mems, [{"field": "content", "operator": "matches", "value": "python"}]))
+    with pytest.raises(_abi.FeiCapacityError):
+        c.scan_hits(prog, 1, cap=10)
+    t = c.timing()
+    assert t["kernel_launches"] >= 3 and t["total_ms"] > 0
+
+
+def test_global_base_offsets_hits(gpu):
+    """A shard reports GLOBAL record indices (global_base + local index)."""
+    from fei_b200.corpus import Corpus
+    a = synth.corpus_arrays(0xFE1, 5000, 300)
+    c = Corpus().load(a)
+    pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "rust", re.IGNORECASE))])
+    hits = c.scan_hits(pb.build(), 1)[0]
+    mems = memories_of(a["records"])
+    assert hits.tolist() == [5000 + i for i in mo.run_search(mems, [{"field": "content", "operator": "matches", "value": "rust"}])]
+    c2 = Corpus().synth(0xFE1, 5000, 300)
+    assert c2.scan_hits(pb.build(), 1)[0].tolist() == hits.tolist()
