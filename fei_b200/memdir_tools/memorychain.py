@@ -301,6 +301,29 @@ class MemoryChain:
     def validate_chain(self) -> bool:
         return validate_chain_blocks(self.chain, lock=self.lock, log=logger)
 
+    def receive_chain_update(self, chain_data: List[Dict[str, Any]]) -> bool:
+        """Validation half of the reference's chain sync (:1037-1085): the same two checks as
+        validate_chain (one GPU pass, log level warning), then the prefix test against the local chain.
+        Persisting the accepted chain (save_chain) is the caller's business (out of scope here)."""
+        new_chain = [MemoryBlock.from_dict(d) for d in chain_data]
+        if len(new_chain) <= len(self.chain):
+            logger.info("Received chain is not longer than current chain, ignoring")
+            return False
+        if len(new_chain) > 1:
+            first_bad, kind, _ = hash_and_validate(new_chain)
+            if first_bad >= 0:
+                what = "has invalid hash" if kind == 1 else "has broken link to previous block"
+                logger.warning(f"Rejecting chain update: Block {first_bad} {what}")
+                return False
+        with self.lock:
+            for mine, theirs in zip(self.chain, new_chain):
+                if mine.hash != theirs.hash:
+                    logger.warning("Rejecting chain update: Chains have diverged")
+                    return False
+            self.chain = new_chain
+        logger.info(f"Chain updated to {len(self.chain)} blocks")
+        return True
+
 
 def install(target_module: Any = None) -> None:
     """Patch the reference's class in place: ``memdir_tools.memorychain.MemoryChain.validate_chain``."""

@@ -107,3 +107,31 @@ def test_synthetic_chain_100k_properties(gpu):
                 assert bytes(dig[i]).hex() == b.hash
         finally:
             _abi.lib().fei_chain_destroy(ch)
+
+
+def test_receive_chain_update_checks(gpu, chain_golden, caplog):
+    """The inline copy of the validation in receive_chain_update (memorychain.py:1059-1078) shares the kernel."""
+    from fei_b200.memdir_tools import memorychain as mc
+    case = chain_golden["chains"][0]
+    chain = base_chain(case)
+    dicts = []
+    for b in chain:
+        d = {"index": b.index, "timestamp": b.timestamp, "memory_data": b.memory_data, "previous_hash": b.previous_hash,
+             "responsible_node": b.responsible_node, "proposer_node": b.proposer_node, "nonce": b.nonce, "hash": b.hash}
+        if b.memory_data.get("type") == "task":               # what MemoryBlock.to_dict adds for task blocks (:282-291)
+            d.update({"difficulty": b.difficulty, "task_state": b.task_state, "solver_node": b.solver_node})
+        dicts.append(d)
+    local = mc.MemoryChain(blocks=[mc.MemoryBlock.from_dict(d) for d in dicts[:100]])
+    assert local.receive_chain_update(dicts[:50]) is False                 # not longer
+    assert local.receive_chain_update(dicts) is True and len(local.chain) == len(dicts)
+    bad = [dict(d) for d in dicts] + [dict(dicts[-1], index=999, hash="0" * 64)]
+    with caplog.at_level(logging.WARNING, logger="memorychain"):
+        assert local.receive_chain_update(bad) is False
+    assert any("Block 300 has invalid hash" in r.getMessage() for r in caplog.records)
+    diverged = [dict(d) for d in dicts]
+    diverged[5] = dict(diverged[5], nonce=1)
+    other = mc.MemoryChain(blocks=[mc.MemoryBlock.from_dict(d) for d in dicts[:10]])
+    caplog.clear()
+    with caplog.at_level(logging.WARNING, logger="memorychain"):
+        assert other.receive_chain_update(diverged) is False
+    assert any("Block 5 has invalid hash" in r.getMessage() for r in caplog.records)
