@@ -144,7 +144,7 @@ _ANY_ALL: RangeSet = ((0, MAX_CP),)
 
 # --------------------------------------------------------------------------- code point NFA
 # assertion codes on epsilon edges
-A_BOS, A_BOL, A_EOS, A_EOL, A_WB_U, A_NWB_U, A_WB_A, A_NWB_A = range(1, 9)
+A_BOS, A_BOL, A_EOS, A_EOL, A_WB_U, A_NWB_U, A_WB_A, A_NWB_A, A_NEXTNL = range(1, 10)
 
 
 class Nfa:
@@ -156,6 +156,8 @@ class Nfa:
         self._leaf_ids: Dict[RangeSet, int] = {}
         self.start = self.new()
         self.uses: set = set()
+        self.dollar_edges: List[Tuple[int, int]] = []   # non-multiline `$` edges (need the trailing-newline rule)
+        self.end_only: set = set()                      # states whose accept only counts at end of input
 
     def new(self) -> int:
         self.eps.append([]); self.chars.append([])
@@ -178,6 +180,38 @@ class Nfa:
 
     def c(self, a: int, rs: RangeSet, b: int) -> None:
         self.chars[a].append((self.leaf(rs), b))
+
+    def add_trailing_newline_rule(self) -> None:
+        """Non-multiline `$` also matches just before a newline that ends the string (two characters of
+        look-ahead).  Modelled with two shadow copies of the automaton: level 1 = "continuing from a `$`
+        taken before a '\\n', valid only if that newline is the last character", level 2 = "that newline has
+        been consumed; valid only at end of input".  Level-2 accepts count at end of input only."""
+        if not self.dollar_edges:
+            return
+        N = len(self.eps)
+        nl = self.leaf(_NL)
+        base_eps = [list(e) for e in self.eps]
+        base_chars = [list(c) for c in self.chars]
+        base_accept = dict(self.accept)
+        for _ in range(2 * N):
+            self.new()
+        for q in range(N):
+            for d, cond in base_eps[q]:
+                self.eps[q + N].append((d + N, cond))
+                self.eps[q + 2 * N].append((d + 2 * N, cond))
+            for leaf_id, d in base_chars[q]:
+                if any(lo <= 0x0A <= hi for lo, hi in self.leaves[leaf_id]):
+                    self.chars[q + N].append((nl, d + 2 * N))          # consumes the final newline itself
+            p = base_accept.get(q)
+            if p is not None:
+                acc2 = self.new()
+                self.accept[acc2] = p; self.end_only.add(acc2)
+                self.chars[q + N].append((nl, acc2))                   # matched before the final newline
+                self.accept[q + 2 * N] = p; self.end_only.add(q + 2 * N)
+        for a, b in self.dollar_edges:
+            self.eps[a].append((b + N, A_NEXTNL))
+            self.eps[a + N].append((b + N, A_NEXTNL))
+        self.uses.add(A_NEXTNL)
 
 
 class _RegexBuilder:
@@ -233,7 +267,7 @@ class _RegexBuilder:
             cond = {
                 _K.AT_BEGINNING: A_BOL if multi else A_BOS,
                 _K.AT_BEGINNING_STRING: A_BOS,
-                _K.AT_END: A_EOL if multi else A_EOS,     # `$` == `\Z` on strip()ped values (see module doc / packer)
+                _K.AT_END: A_EOL if multi else A_EOS,     # + the trailing-newline rule, see Nfa.add_trailing_newline_rule
                 _K.AT_END_STRING: A_EOS,
                 _K.AT_BOUNDARY: A_WB_A if ascii_ else A_WB_U,
                 _K.AT_NON_BOUNDARY: A_NWB_A if ascii_ else A_NWB_U,
@@ -241,6 +275,8 @@ class _RegexBuilder:
             if cond is None:
                 raise NotImplementedError(f"regex assertion {av} is not supported on the GPU")
             n.e(a, b, cond)
+            if av == _K.AT_END and not multi:
+                n.dollar_edges.append((a, b))
             return b
         if op in (_K.ASSERT, _K.ASSERT_NOT):
             raise NotImplementedError("look-ahead / look-behind is not regular: not supported on the GPU")
@@ -409,6 +445,7 @@ def compile_patterns(patterns: Sequence[Pattern], max_states: int = 30000, stick
     n = Nfa()
     for pid, p in enumerate(patterns):
         add_pattern(n, pid, p)
+    n.add_trailing_newline_rule()
     d = _determinize(n, len(patterns), max_states)
     if sticky and len(patterns) == 1:
         d = make_sticky(d)
@@ -431,7 +468,7 @@ def make_sticky(d: Dfa) -> Dfa:
 
 def _determinize(n: Nfa, npat: int, max_states: int) -> Dfa:
     uses = n.uses
-    need_nl = A_BOL in uses or A_EOL in uses
+    need_nl = A_BOL in uses or A_EOL in uses or A_NEXTNL in uses
     need_uw = A_WB_U in uses or A_NWB_U in uses
     need_aw = A_WB_A in uses or A_NWB_A in uses
     leaves = list(n.leaves)
@@ -470,6 +507,8 @@ def _determinize(n: Nfa, npat: int, max_states: int) -> Dfa:
             return nxt[0] == 3
         if cond == A_EOL:
             return nxt[0] == 3 or nxt[0] == 1
+        if cond == A_NEXTNL:
+            return nxt[0] == 1
         if prev[0] == 2 and nxt[0] == 3:
             return False                                 # empty input: neither \b nor \B matches (CPython 3.12)
         k = 1 if cond in (A_WB_U, A_NWB_U) else 2
@@ -498,12 +537,13 @@ def _determinize(n: Nfa, npat: int, max_states: int) -> Dfa:
         return out
 
     acc = n.accept
+    end_only = n.end_only
 
-    def mask_of(states: FrozenSet[int]) -> int:
+    def mask_of(states, at_end: bool = False) -> int:
         m = 0
         for s in states:
             p = acc.get(s)
-            if p is not None:
+            if p is not None and (at_end or s not in end_only):
                 m |= 1 << p
         return m
 
@@ -572,7 +612,7 @@ def _determinize(n: Nfa, npat: int, max_states: int) -> Dfa:
     ncp = len(order)
     cp_trans = np.array(rows, dtype=np.int32).reshape(ncp, ncls)
     cp_out = np.array([k[2] for k in order], dtype=np.uint32)
-    cp_end = np.array([mask_of(closure(k[0], k[1], END_CTX)) for k in order], dtype=np.uint32)
+    cp_end = np.array([mask_of(closure(k[0], k[1], END_CTX), at_end=True) for k in order], dtype=np.uint32)
     # the mask emitted on entry is also valid at the end (it was already counted); fold nothing more
     return _to_bytes(cp_trans, cp_out, cp_end, bounds, cls_of, ncls, npat)
 
