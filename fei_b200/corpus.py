@@ -43,6 +43,31 @@ class Corpus:
         self.n, self.global_base = h.n, h.global_base
         return self
 
+    def load_raw(self, a: Dict[str, Any]) -> np.ndarray:
+        """Raw ingest (fei_corpus_load_raw): `a` holds raw file bytes + meta columns.  Returns the validity flags;
+        the corpus is loaded only when every file is valid UTF-8."""
+        h = _abi.CorpusHost()
+        h.n = int(a["n"]); h.global_base = int(a.get("global_base", 0))
+        for k in ("name", "name_off", "name_spans", "ts", "wall", "flags8", "fsb"):
+            v = a.get(k)
+            setattr(h, k, _abi.ptr(np.ascontiguousarray(v)) if v is not None else None)
+        valid = np.zeros(max(1, h.n), dtype=np.uint8)
+        rc = _abi.lib().fei_corpus_load_raw(self._h, C.byref(h), _abi.ptr(a["raw"]), _abi.ptr(a["raw_off"]), _abi.ptr(valid))
+        valid = valid[:h.n].astype(bool)
+        if rc != 0 and valid.all():
+            _abi.check(rc)
+        if rc == 0:
+            self._keep = a
+            self.n, self.global_base = h.n, h.global_base
+        return valid
+
+    def fetch_meta(self) -> Dict[str, np.ndarray]:
+        n = self.n
+        ts = np.zeros(n, dtype=np.int64); wall = np.zeros(n, dtype=np.int64)
+        f8 = np.zeros(n, dtype=np.uint64); fsb = np.zeros(n, dtype=np.uint32)
+        _abi.check(_abi.lib().fei_corpus_fetch(self._h, 0, n, None, 0, None, None, 0, None, _abi.ptr(ts), _abi.ptr(wall), _abi.ptr(f8), _abi.ptr(fsb)))
+        return {"ts": ts, "wall": wall, "flags8": f8, "fsb": fsb}
+
     def synth(self, seed: int, first: int, n: int) -> "Corpus":
         _abi.check(_abi.lib().fei_corpus_synth(self._h, seed, first, n))
         self.n, self.global_base = n, first

@@ -53,8 +53,47 @@ def read_segment(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
     return out
 
 
+def read_segment_raw(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
+    """Like read_segment but leaves the file *text* work (decode, newline folding, '---' split, strip) to the
+    GPU ingest kernels (fei_corpus_load_raw): files are read as bytes; only the file-name grammar and the
+    listing order are handled here."""
+    path = os.path.join(base, folder, status) if folder else os.path.join(base, status)
+    if not os.path.exists(path):
+        return []
+    out = []
+    for name in os.listdir(path):
+        try:
+            if not _LIST_RE.match(name):
+                continue
+            m = U.FILENAME_RE.match(name)
+            if not m:
+                raise ValueError(f"Invalid memory filename: {name}")
+            with open(os.path.join(path, name), "rb") as f:
+                raw = f.read()
+            ts = int(m.group(1))
+            out.append({"filename": name, "folder": folder, "status": status, "ts": ts, "uid": m.group(2), "host": m.group(3),
+                        "flags": m.group(4), "uid_span": (m.start(2), m.end(2)), "host_span": (m.start(3), m.end(3)),
+                        "raw": raw, "date": datetime.fromtimestamp(ts)})
+        except Exception as e:
+            print(f"Error processing {name}: {e}")
+    out.sort(key=lambda r: r["ts"], reverse=True)
+    return out
+
+
+def _ensure_text(rec: Dict[str, Any]) -> None:
+    """Host-side text of one record (hits only): what open(path, "r").read() + parse_memory_content see."""
+    if "hdr_text" in rec:
+        return
+    text = rec["raw"].decode("utf-8").replace("\r\n", "\n").replace("\r", "\n")
+    head, sep, rest = text.partition("---")
+    rec["hdr_text"] = head if sep else ""
+    rec["body_text"] = (rest if sep else text).strip()
+    rec["has_sep"] = bool(sep)
+
+
 def memory_dict(rec: Dict[str, Any], include_content: bool) -> Dict[str, Any]:
     """The dict list_memories yields (utils.py:234-243); headers parsed on the host for materialisation."""
+    _ensure_text(rec)
     headers: Dict[str, str] = {}
     if rec["has_sep"]:
         for line in rec["hdr_text"].strip().split("\n"):
@@ -120,6 +159,35 @@ def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, i
             "any_lower_inexact": bool((bits & REC_LOWER_INEXACT).any()) if n else False}
 
 
+def raw_arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, int], global_base: int = 0) -> Dict[str, Any]:
+    """Host arrays for fei_corpus_load_raw: raw file bytes + meta columns + names (no text processing)."""
+    n = len(recs)
+    name_parts = [os.fsencode(r["filename"]) for r in recs]
+
+    def blob(parts):
+        off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=n), out=off[1:])
+        data = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if n and off[n] else np.zeros(1, dtype=np.uint8)
+        return data, off
+
+    raw, raw_off = blob([r["raw"] for r in recs])
+    name, name_off = blob(name_parts)
+    spans = np.zeros((max(n, 1), 4), dtype=np.uint16)
+    for i, r in enumerate(recs):
+        fname = r["filename"]
+        (a0, a1), (b0, b1) = r["uid_span"], r["host_span"]
+        if len(name_parts[i]) != len(fname):
+            a0, a1, b0, b1 = (len(os.fsencode(fname[:x])) for x in (a0, a1, b0, b1))
+        spans[i] = (a0, a1 - a0, b0, b1 - b0)
+    ts = np.array([r["ts"] for r in recs], dtype=np.int64)
+    wall = np.array([calendar.timegm(r["date"].timetuple()) for r in recs], dtype=np.int64)
+    f8 = np.array([_flags8(r["flags"], r["filename"]) for r in recs], dtype=np.uint64)
+    fsb = np.array([(folder_ids[r["folder"]] & 0xFFFF) | (U.STANDARD_FOLDERS.index(r["status"]) << 16) for r in recs], dtype=np.uint32)
+    return {"n": n, "global_base": global_base, "raw": raw, "raw_off": raw_off, "name": name, "name_off": name_off,
+            "name_spans": spans.reshape(-1), "ts": ts, "wall": wall, "flags8": f8, "fsb": fsb}
+
+
 class PackedMemdir:
     """Host bookkeeping for one packed tree: records in listing order + the device corpus."""
 
@@ -143,7 +211,13 @@ class PackedMemdir:
                     sig.append((p, s.st_mtime_ns))
         return tuple(sig)
 
-    def build(self, upload: bool = True) -> "PackedMemdir":
+    def build(self, upload: bool = True, gpu_text: Optional[bool] = None) -> "PackedMemdir":
+        """gpu_text (default on; FEI_PACK_HOST_TEXT=1 turns it off): decode / newline folding / '---' split / strip run in the
+        ingest kernels (fei_corpus_load_raw) instead of Python."""
+        if gpu_text is None:
+            gpu_text = os.environ.get("FEI_PACK_HOST_TEXT", "0") != "1"
+        if gpu_text and upload:
+            return self._build_raw()
         self.signature = self.tree_signature(self.base)
         self.folders = []
         for root, dirs, _ in os.walk(self.base):
@@ -164,6 +238,51 @@ class PackedMemdir:
         if upload:
             from .corpus import Corpus
             self.corpus = Corpus().load(self.arrays)
+        return self
+
+    def _build_raw(self) -> "PackedMemdir":
+        from .corpus import Corpus
+        self.signature = self.tree_signature(self.base)
+        self.folders = []
+        for root, dirs, _ in os.walk(self.base):
+            if any(st in dirs for st in U.STANDARD_FOLDERS):
+                rel = os.path.relpath(root, self.base)
+                self.folders.append("" if rel == "." else rel)
+        if len(self.folders) > 65535:
+            raise NotImplementedError("more than 65535 folders")
+        self.folder_ids = {f: i for i, f in enumerate(self.folders)}
+        segs: Dict[Tuple[str, str], List[Dict[str, Any]]] = {}
+        for folder in self.folders:
+            for st in U.STANDARD_FOLDERS:
+                segs[(folder, st)] = read_segment_raw(self.base, folder, st)
+        corpus = Corpus()
+        while True:
+            recs = [r for folder in self.folders for st in U.STANDARD_FOLDERS for r in segs[(folder, st)]]
+            arrays = raw_arrays_from_segments(recs, self.folder_ids)
+            valid = corpus.load_raw(arrays)
+            if valid.all():
+                break
+            for r, ok in zip(recs, valid.tolist()):            # undecodable files: reported and skipped (utils.py:247-248)
+                if not ok:
+                    try:
+                        r["raw"].decode("utf-8")
+                        msg = "invalid UTF-8"
+                    except UnicodeDecodeError as e:
+                        msg = str(e)
+                    print(f"Error processing {r['filename']}: {msg}")
+                    segs[(r["folder"], r["status"])].remove(r)
+        self.recs = recs
+        self.segments = {}
+        pos = 0
+        for folder in self.folders:
+            for st in U.STANDARD_FOLDERS:
+                k = len(segs[(folder, st)])
+                self.segments[(folder, st)] = (pos, pos + k)
+                pos += k
+        self.corpus = corpus
+        fsb = corpus.fetch_meta()["fsb"] if corpus.n else np.zeros(0, dtype=np.uint32)
+        arrays["any_lower_inexact"] = bool(((fsb >> 24) & REC_LOWER_INEXACT).any())
+        self.arrays = arrays
         return self
 
     def ranges(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> List[Tuple[int, int]]:

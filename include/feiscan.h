@@ -91,6 +91,14 @@ int fei_corpus_destroy(fei_corpus* c);
 /* Copies the canonical arrays to HBM (pageable or pinned host memory), builds the
  * warp-transposed body tiles (DESIGN.md "data layout") and drops the canonical body. */
 int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h);
+/* Raw ingest: like fei_corpus_load, but the text work of utils.list_memories / parse_memory_content
+ * (memdir_tools/utils.py:229-232, :105-120) runs on the GPU.  raw/raw_off[n+1] = file contents as read from disk
+ * (bytes); h->hdr / h->body (+ offsets) are ignored.  The kernels validate UTF-8 strictly (what open(path,"r")
+ * would decode), fold "\r\n" / "\r" to "\n", split at the first "---", .strip() the body with Python's whitespace
+ * set and set the record bits.  valid_out[n] (may be NULL) receives 1 for decodable files; if any file is not,
+ * nothing is loaded and FEI_E_BADARG is returned so the caller can drop them (the reference reports and skips
+ * such files, utils.py:247-248) and call again.                                                                */
+int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out);
 /* Fills the corpus with records [first, first+n) of the deterministic synthetic
  * Memdir (fei_b200/csrc/synth.cuh), generated on the GPU.                           */
 int fei_corpus_synth(fei_corpus* c, uint64_t seed, uint64_t first, uint64_t n);

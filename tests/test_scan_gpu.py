@@ -258,3 +258,51 @@ def test_global_base_offsets_hits(gpu):
     assert hits.tolist() == [5000 + i for i in mo.run_search(mems, [{"field": "content", "operator": "matches", "value": "rust"}])]
     c2 = Corpus().synth(0xFE1, 5000, 300)
     assert c2.scan_hits(pb.build(), 1)[0].tolist() == hits.tolist()
+
+
+def test_raw_ingest_matches_python_text_semantics(gpu):
+    """fei_corpus_load_raw: UTF-8 validation, universal newlines, '---' split and .strip() on the GPU must give
+    exactly what open(path, "r").read() + parse_memory_content give (utils.py:229-232, :105-120)."""
+    from fei_b200.corpus import Corpus
+    raws = [
+        b"Subject: a\nTags: x\n---\nbody\n",
+        b"Subject: crlf\r\nTags: y\r\n---\r\n\r\n  body line 1\r\nline 2\r\n\r\n",
+        b"lone\rcarriage\rreturns---\r\rtext\r",
+        b"no separator at all \n just text \t\n",
+        b"", b"---", b"------", b"a---b---c", b" \n\t ", b"--- \xc2\xa0\xe2\x80\x83 padded \xe3\x80\x80\n",
+        "Ünï: cödé\n---\n  日本語 \U0001F409  ".encode(), b"--", b"-\r\n--", b"x\r\n---\r\ny",
+        "h---\x1c\x1d body\x1f\x85".encode(), "İstanbul Σ\n---\nς".encode(), b"k: v\n--- \r",
+    ]
+    bad = [b"bad \xff byte---x", b"trunc \xe2\x82", b"overlong \xc0\xaf", b"surrogate \xed\xa0\x80", b"too big \xf4\x90\x80\x80", b"cont \x80"]
+    recs = []
+    for i, raw in enumerate(raws + bad):
+        r = synth.record(9, i); r["raw"] = raw
+        recs.append(r)
+    n = len(recs)
+
+    def arrays(rs):
+        off = np.zeros(len(rs) + 1, dtype=np.uint64); np.cumsum([len(r["raw"]) for r in rs], out=off[1:])
+        base = synth.arrays_from_records(rs)
+        return {"n": len(rs), "raw": np.frombuffer(b"".join(r["raw"] for r in rs) or b"\0", dtype=np.uint8).copy(), "raw_off": off,
+                "ts": base["ts"], "wall": base["wall"], "flags8": base["flags8"], "fsb": base["fsb"]}
+    c = Corpus()
+    valid = c.load_raw(arrays(recs))
+    assert valid.tolist() == [True] * len(raws) + [False] * len(bad)
+    for raw, ok in zip(raws + bad, valid.tolist()):
+        try:
+            raw.decode("utf-8"); want = True
+        except UnicodeDecodeError:
+            want = False
+        assert ok == want
+    good = recs[:len(raws)]
+    assert c.load_raw(arrays(good)).all()
+    got = c.fetch(0, len(good))
+    bits = (got["fsb"] >> 24).tolist()
+    for i, raw in enumerate(raws):
+        text = raw.decode("utf-8").replace("\r\n", "\n").replace("\r", "\n")
+        head, sep, rest = text.partition("---")
+        want_h = (head if sep else "").encode(); want_b = (rest if sep else text).strip().encode()
+        h = bytes(got["hdr"][int(got["hdr_off"][i]):int(got["hdr_off"][i + 1])])
+        b = bytes(got["body"][int(got["body_off"][i]):int(got["body_off"][i + 1])])
+        assert (h, b) == (want_h, want_b), raw
+        assert bool(bits[i] & 1) == (not sep) and bool(bits[i] & 2) == (not text.isascii()) and bool(bits[i] & 4) == ("İ" in text or "Σ" in text), raw
