@@ -451,6 +451,21 @@ def run_extra(args, corpus, st, peak, lib, _abi):
                          "sample": f"validate_chain oracle (json.dumps + hashlib, memorychain.py:596-618) over {min(nb, 50_000)} blocks, {cpu_dt:.2f} s"},
     }
     lib.fei_chain_destroy(ch)
+    # ---- the same path end to end through the reference-shaped Python API: block objects -> typed columns (host marshal)
+    #      -> C++ canonical JSON -> H2D -> SHA-256 + link kernel -> verdict
+    from fei_b200 import synth
+    from fei_b200.memdir_tools import memorychain as mc
+    from oracle import chain_oracle as co
+    nb_api = min(nb, 100_000)
+    blocks = co.build_chain(synth.chain_specs(CHAIN_SEED, 0, nb_api))      # plain objects with the reference's block attributes
+    chain_obj = mc.MemoryChain(blocks=blocks)
+    chain_obj.validate_chain()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); ok = chain_obj.validate_chain(); ts.append(time.perf_counter() - t0)
+    out["cfg4_validate_chain"]["e2e_python_api"] = {
+        "value": (nb_api - 1) / min(ts), "unit": "chain blocks/s", "blocks": nb_api, "valid": bool(ok),
+        "path": "MemoryChain.validate_chain(): attribute marshal in Python -> fei_chain_validate_cols (C++ JSON, H2D, kernel)"}
     return out
 
 

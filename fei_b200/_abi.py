@@ -94,6 +94,7 @@ _SIGS = {
     "fei_chain_validate": (C.c_int, [_P, _P, _P, _P, _P]),
     "fei_chain_fetch": (C.c_int, [_P, _U64, _U64, _P, _U64, _P, _P, _P]),
     "fei_chain_serialize_cols": (C.c_int, [_P, _U64, _P, _U64, _P]),
+    "fei_chain_mine": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _U64, C.c_uint32, _U64, _P, _P, _P]),
     "fei_synth_record_host": (C.c_int, [_U64, _U64, _P, C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "fei_synth_block_host": (C.c_int, [_U64, _U64, _P, _P, _P, _P, _P]),
     "fei_comm_unique_id": (C.c_int, [_P]),

@@ -18,6 +18,7 @@
 #include "chain_json.h"
 #include <vector>
 #include <string.h>
+#include <stdio.h>
 
 namespace fei {
 
@@ -173,6 +174,55 @@ k_sha256_validate(const uint8_t* __restrict__ padded, const uint64_t* __restrict
   }
   int kind = !ok ? 1 : ((fl & 2) ? 0 : 2);
   if (kind) atomicMin(verdict, (unsigned long long)(i * 4 + kind));
+}
+
+// ------------------------------------------------------------------ proof of work ("next" row 2)
+// MemoryBlock.mine_block (memdir_tools/memorychain.py:132-143): smallest nonce >= the current one whose
+// hexdigest starts with `difficulty` zeros.  The canonical text is prefix + decimal(nonce) + suffix (the
+// nonce sits between "memory_id" and "previous_hash" in the sorted key order); one candidate per thread.
+constexpr int kMineMaxFixed = 1024;                    // prefix + suffix bytes kept in shared memory
+
+__global__ void __launch_bounds__(256)
+k_mine(const uint8_t* __restrict__ fixed, uint32_t plen, uint32_t slen, unsigned long long base, unsigned long long count,
+       uint32_t zero_nibbles, unsigned long long* __restrict__ best) {
+  __shared__ uint8_t sh[kMineMaxFixed];
+  for (uint32_t k = threadIdx.x; k < plen + slen; k += blockDim.x) sh[k] = fixed[k];
+  __syncthreads();
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < count; idx += stride) {
+    const unsigned long long nonce = base + idx;
+    if (nonce >= *reinterpret_cast<volatile unsigned long long*>(best)) continue;   // a smaller winner is already known
+    char dg[20]; uint32_t nd = 0;
+    { unsigned long long v = nonce; char tmp[20]; do { tmp[nd++] = (char)('0' + v % 10); v /= 10; } while (v); for (uint32_t k = 0; k < nd; ++k) dg[k] = tmp[nd - 1 - k]; }
+    const uint32_t total = plen + nd + slen;
+    const uint32_t nblk = (total + 9 + 63) >> 6;
+    const unsigned long long bits = (unsigned long long)total << 3;
+    uint32_t st[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (uint32_t b = 0; b < nblk; ++b) {
+      uint32_t w[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t pos = b * 64 + t * 4 + j;
+          uint32_t byte;
+          if (pos < plen) byte = sh[pos];
+          else if (pos < plen + nd) byte = (uint8_t)dg[pos - plen];
+          else if (pos < total) byte = sh[pos - nd];
+          else if (pos == total) byte = 0x80;
+          else if (pos >= nblk * 64 - 8) byte = (uint32_t)(bits >> (8 * (nblk * 64 - 1 - pos))) & 0xFFu;
+          else byte = 0;
+          word = word << 8 | byte;
+        }
+        w[t] = word;
+      }
+      sha256_compress(st, w);
+    }
+    bool ok = true;                                       // `zero_nibbles` leading hex zeros
+    for (uint32_t k = 0; ok && k < zero_nibbles; ++k) ok = ((st[k >> 3] >> (28 - 4 * (k & 7))) & 0xFu) == 0;
+    if (ok) atomicMin(best, nonce);
+  }
 }
 
 // ------------------------------------------------------------------ resident chain
@@ -441,5 +491,51 @@ extern "C" int fei_chain_fetch(fei_chain* ch, uint64_t first, uint64_t n, uint8_
     FEI_CUDA(cudaMemcpyAsync(prev_hex, ch->prev.as<uint8_t>() + poff[0], 64 * n, cudaMemcpyDeviceToHost, c.stream));
   }
   FEI_CUDA(cudaStreamSynchronize(c.stream));
+  return FEI_OK;
+}
+
+extern "C" int fei_chain_mine(const uint8_t* prefix, uint32_t prefix_len, const uint8_t* suffix, uint32_t suffix_len,
+                              uint64_t start_nonce, uint32_t difficulty, uint64_t max_tries,
+                              uint64_t* nonce_out, uint8_t* digest_out, uint64_t* tried_out) {
+  FEI_TRY(require_ready());
+  if (!nonce_out || (prefix_len && !prefix) || (suffix_len && !suffix)) { set_error("null argument"); return FEI_E_BADARG; }
+  if (prefix_len + suffix_len > kMineMaxFixed) { set_error("block text longer than %d bytes is not supported by the miner", kMineMaxFixed); return FEI_E_UNSUPPORTED; }
+  if (difficulty > 64) { set_error("difficulty above 64 hex digits can never be met"); return FEI_E_BADARG; }
+  Context& c = ctx();
+  cudaStream_t s = c.stream;
+  DevBuf fixed, best;
+  FEI_TRY(fixed.alloc(kMineMaxFixed)); FEI_TRY(best.alloc(16));
+  std::vector<uint8_t> host(prefix_len + suffix_len + 1);
+  if (prefix_len) memcpy(host.data(), prefix, prefix_len);
+  if (suffix_len) memcpy(host.data() + prefix_len, suffix, suffix_len);
+  FEI_CUDA(cudaMemcpyAsync(fixed.p, host.data(), prefix_len + suffix_len, cudaMemcpyHostToDevice, s));
+  FEI_CUDA(cudaMemsetAsync(best.p, 0xFF, sizeof(unsigned long long), s));
+  const unsigned long long batch = 1ull << 22;
+  unsigned long long tried = 0, found = ~0ull, base = start_nonce;
+  while (tried < max_tries) {
+    unsigned long long cnt = max_tries - tried < batch ? max_tries - tried : batch;
+    if (base + cnt < base) cnt = ~0ull - base;             // do not wrap the 64-bit nonce space
+    if (cnt == 0) break;
+    k_mine<<<c.sm_count * 8, 256, 0, s>>>(fixed.as<uint8_t>(), prefix_len, suffix_len, base, cnt, difficulty, best.as<unsigned long long>());
+    FEI_CUDA(cudaGetLastError());
+    FEI_CUDA(cudaMemcpyAsync(&found, best.p, sizeof(found), cudaMemcpyDeviceToHost, s));
+    FEI_CUDA(cudaStreamSynchronize(s));
+    tried += cnt; base += cnt;
+    if (found != ~0ull) break;
+  }
+  if (tried_out) *tried_out = tried;
+  if (found == ~0ull) { set_error("no nonce found within %llu tries", (unsigned long long)max_tries); return FEI_E_CAPACITY; }
+  *nonce_out = found;
+  if (digest_out) {                                        // hash of the winning text, through the validate kernel's path
+    char dg[24]; int nd = snprintf(dg, sizeof dg, "%llu", found);
+    std::vector<uint8_t> msg(prefix_len + nd + suffix_len);
+    if (prefix_len) memcpy(msg.data(), prefix, prefix_len);
+    memcpy(msg.data() + prefix_len, dg, nd);
+    if (suffix_len) memcpy(msg.data() + prefix_len + nd, suffix, suffix_len);
+    uint64_t moff[2] = {0, msg.size()}, hoff[2] = {0, 1};
+    uint8_t dummy = '0';
+    int64_t fb; int32_t kind;
+    FEI_TRY(fei_chain_validate_msgs(msg.data(), moff, &dummy, hoff, &dummy, hoff, 1, 0, &fb, &kind, digest_out));
+  }
   return FEI_OK;
 }

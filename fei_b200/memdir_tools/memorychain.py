@@ -243,6 +243,30 @@ class MemoryBlock:
         _, _, dig = hash_and_validate([probe], want_digests=True)
         return bytes(dig[0]).hex()
 
+    def mine_block(self, difficulty: int = 2, max_tries: int = 1 << 40) -> None:
+        """Proof of work on the GPU (reference :132-143): smallest nonce >= the current one whose hash starts with
+        `difficulty` zeros.  The canonical text only differs in the nonce digits, so the host serialises it twice
+        (nonce 0 and 1) to cut prefix / suffix and the kernel tries one candidate nonce per thread."""
+        if not isinstance(self.nonce, int) or isinstance(self.nonce, bool) or self.nonce < 0:
+            raise NotImplementedError("mine_block needs a non-negative int nonce")
+        keep = self.nonce
+        try:
+            self.nonce = 0
+            t0 = canonical_texts([_HashProbe(self)])[0]
+            self.nonce = 1
+            t1 = canonical_texts([_HashProbe(self)])[0]
+        finally:
+            self.nonce = keep
+        pos = next(i for i in range(len(t0)) if t0[i] != t1[i])
+        prefix, suffix = t0[:pos], t0[pos + 1:]
+        _abi.init()
+        nonce, tried = C.c_uint64(), C.c_uint64()
+        digest = np.zeros(32, dtype=np.uint8)
+        _abi.check(_abi.lib().fei_chain_mine(prefix, len(prefix), suffix, len(suffix), keep, int(difficulty), int(max_tries),
+                                             C.byref(nonce), _abi.ptr(digest), C.byref(tried)))
+        self.nonce = int(nonce.value)
+        self.hash = bytes(digest).hex()
+
     def is_task(self) -> bool:
         return self.memory_data.get("type") == "task"
 

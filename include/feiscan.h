@@ -203,6 +203,13 @@ int fei_chain_validate(fei_chain* ch, int64_t* first_bad, int32_t* bad_kind, uin
 int fei_chain_fetch(fei_chain* ch, uint64_t first, uint64_t n, uint8_t* msgs, uint64_t msgs_cap, uint64_t* msg_off,
                     uint8_t* hash_hex /*64*n*/, uint8_t* prev_hex /*64*n*/);
 
+/* Proof of work, MemoryBlock.mine_block (memdir_tools/memorychain.py:132-143): the block's canonical text is
+ * prefix + decimal(nonce) + suffix; finds the smallest nonce >= start_nonce whose SHA-256 hexdigest starts with
+ * `difficulty` zeros (FEI_E_CAPACITY if none within max_tries).  digest_out (32 bytes, may be NULL) = its digest. */
+int fei_chain_mine(const uint8_t* prefix, uint32_t prefix_len, const uint8_t* suffix, uint32_t suffix_len,
+                   uint64_t start_nonce, uint32_t difficulty, uint64_t max_tries,
+                   uint64_t* nonce_out, uint8_t* digest_out, uint64_t* tried_out);
+
 /* Host-only helper (no GPU): canonical JSON of the column form, for tests of the
  * serialiser against json.dumps.                                                      */
 int fei_chain_serialize_cols(const fei_json_col* cols, uint64_t n,

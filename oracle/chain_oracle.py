@@ -79,6 +79,14 @@ def validate(chain: Sequence[Any]) -> Tuple[bool, int, int]:
     return True, -1, 0
 
 
+def mine(b: Any, difficulty: int = 2) -> None:
+    """MemoryBlock.mine_block (memorychain.py:132-143): bump the nonce until the hash has `difficulty` leading zeros."""
+    target = "0" * difficulty
+    while b.hash[:difficulty] != target:
+        b.nonce += 1
+        b.hash = block_hash(b)
+
+
 def build_chain(specs: Sequence[Dict[str, Any]]) -> List[Block]:
     """Link a list of {index,timestamp,memory_data,responsible_node,proposer_node[,nonce]} dicts."""
     out: List[Block] = []

@@ -164,6 +164,15 @@ def make_chain(scratch: str):
                    ("genesis_hash", m_genesis), ("two_faults", m_two), ("solver_33", m_solver), ("short_hash_5", m_short),
                    ("upper_hash_6", m_upper), ("last_block", m_last), ("first_checked", m_first)]:
         variant(nm, fn)
+    # proof of work: MemoryBlock.mine_block of the reference (memorychain.py:132-143)
+    out["mined"] = []
+    for k, (diff, start) in enumerate([(1, 0), (2, 0), (3, 0), (2, 5000), (4, 0), (0, 7), (3, 123456)]):
+        s = specs[10 + k]
+        b = rm.MemoryBlock(s["index"], s["timestamp"], s["memory_data"], "ab" * 32, s["responsible_node"], s["proposer_node"])
+        b.nonce = start
+        b.hash = b.calculate_hash()
+        b.mine_block(diff)
+        out["mined"].append({"spec_index": 10 + k, "previous_hash": "ab" * 32, "difficulty": diff, "start_nonce": start, "nonce": b.nonce, "hash": b.hash})
     with open(os.path.join(HERE, "chain_kats.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True, default=str)
     print("wrote chain_kats.json:", len(out["single"]), "single blocks,", len(out["chains"]), "chains")

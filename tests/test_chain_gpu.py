@@ -135,3 +135,25 @@ def test_receive_chain_update_checks(gpu, chain_golden, caplog):
     with caplog.at_level(logging.WARNING, logger="memorychain"):
         assert other.receive_chain_update(diverged) is False
     assert any("Block 5 has invalid hash" in r.getMessage() for r in caplog.records)
+
+
+def test_mine_block_matches_reference(gpu, chain_golden):
+    """Proof of work on the GPU (fei_chain_mine) finds the same nonce and hash as MemoryBlock.mine_block."""
+    from fei_b200 import synth
+    from fei_b200.memdir_tools import memorychain as mc
+    for m in chain_golden["mined"]:
+        s = synth.block(0xC4A1, m["spec_index"])
+        b = mc.MemoryBlock(s["index"], s["timestamp"], s["memory_data"], m["previous_hash"], s["responsible_node"], s["proposer_node"])
+        b.nonce = m["start_nonce"]
+        b.mine_block(m["difficulty"])
+        assert (b.nonce, b.hash) == (m["nonce"], m["hash"]), m
+        assert b.hash == b.calculate_hash()
+    # a harder one, checked against the oracle's definition only
+    s = synth.block(0xC4A1, 3)
+    b = mc.MemoryBlock(s["index"], s["timestamp"], s["memory_data"], "0" * 64, s["responsible_node"], s["proposer_node"])
+    b.mine_block(5)
+    assert b.hash.startswith("00000") and b.hash == co.block_hash(b)
+    probe = co.Block(s["index"], s["timestamp"], s["memory_data"], "0" * 64, s["responsible_node"], s["proposer_node"])
+    for n in range(max(0, b.nonce - 3000), b.nonce):          # no smaller nonce in the window before it
+        probe.nonce = n
+        assert not co.block_hash(probe).startswith("00000")

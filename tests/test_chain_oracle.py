@@ -81,3 +81,12 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         getattr(l, name)
     assert declared == set(_abi.EXPORTS)
+
+
+def test_oracle_mining_matches_reference(chain_golden):
+    from fei_b200 import synth
+    for m in chain_golden["mined"]:
+        s = synth.block(0xC4A1, m["spec_index"])
+        b = co.Block(s["index"], s["timestamp"], s["memory_data"], m["previous_hash"], s["responsible_node"], s["proposer_node"], nonce=m["start_nonce"])
+        co.mine(b, m["difficulty"])
+        assert (b.nonce, b.hash) == (m["nonce"], m["hash"]), m
