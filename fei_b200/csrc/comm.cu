@@ -35,7 +35,9 @@ struct Nccl {
   const char* (*GetErrorString)(int) = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 0, rank = -1;
-  DevBuf counts_dev, gathered, scratch;
+  DevBuf counts_dev, gathered, scratch, lists;
+  CompactScratch compact;
+  std::mutex mu;                 // one collective at a time per communicator
 };
 Nccl g;
 
@@ -85,7 +87,8 @@ extern "C" int fei_comm_init(const uint8_t* id, int nranks, int rank) {
 
 extern "C" int fei_comm_destroy(void) {
   if (g.comm) { g.CommDestroy(g.comm); g.comm = nullptr; }
-  g.counts_dev.release(); g.gathered.release(); g.scratch.release();
+  g.counts_dev.release(); g.gathered.release(); g.scratch.release(); g.lists.release();
+  g.compact.blk_counts.release(); g.compact.blk_offsets.release(); g.compact.totals.release();
   g.nranks = 0; g.rank = -1;
   return FEI_OK;
 }
@@ -102,6 +105,8 @@ extern "C" int fei_comm_allgather_hits(fei_corpus* c, uint32_t nq, uint64_t* con
   FEI_TRY(require_ready());
   if (!c || nq == 0 || nq > 32 || nq != c->last_nq) { set_error("no matching scan result on this corpus (run fei_scan_count / fei_scan_hits first)"); return FEI_E_STATE; }
   if (!g.comm) { set_error("fei_comm_init() has not been called"); return FEI_E_STATE; }
+  std::lock_guard<std::mutex> lock(g.mu);
+  std::lock_guard<std::mutex> clock(c->mu);
   cudaStream_t s = ctx().stream;
   const int R = g.nranks;
   const uint32_t W = nq + 2;                                   // per-rank record: counts[nq], n, global_base
@@ -163,7 +168,7 @@ extern "C" int fei_comm_allgather_hits(fei_corpus* c, uint32_t nq, uint64_t* con
     FEI_TRY(g.gathered.ensure((size_t)R * n_max * sizeof(uint32_t)));
     FEI_NCCL(g.AllGather(c->hits.p, g.gathered.p, n_max, 3 /* ncclUint32 */, g.comm, s));
     if (want_host) {
-      static CompactScratch sc; static DevBuf lists;
+      CompactScratch& sc = g.compact; DevBuf& lists = g.lists;
       std::vector<uint64_t> written(nq, 0);
       for (int r = 0; r < R; ++r) {
         uint64_t nr = info[(size_t)r * W + nq], gb = info[(size_t)r * W + nq + 1];

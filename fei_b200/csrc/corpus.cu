@@ -202,6 +202,8 @@ extern "C" int fei_corpus_destroy(fei_corpus* c) {
 }
 
 extern "C" int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(require_ready());
   if (!c || !h) { set_error("null argument"); return FEI_E_BADARG; }
   if (h->n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }
@@ -244,6 +246,8 @@ extern "C" int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h) {
 }
 
 extern "C" int fei_corpus_synth(fei_corpus* c, uint64_t seed, uint64_t first, uint64_t n) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(require_ready());
   if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
   if (n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }
@@ -290,6 +294,8 @@ extern "C" int fei_corpus_fetch(fei_corpus* c, uint64_t first, uint64_t n,
                                 uint8_t* hdr, uint64_t hdr_cap, uint64_t* hdr_off,
                                 uint8_t* body, uint64_t body_cap, uint64_t* body_off,
                                 int64_t* ts, int64_t* wall, uint64_t* flags8, uint32_t* fsb) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(require_ready());
   if (!c || !c->loaded) { set_error("corpus not loaded"); return FEI_E_STATE; }
   if (first + n > c->n) { set_error("range out of bounds"); return FEI_E_BADARG; }

@@ -16,6 +16,7 @@
 //       grp_rec[g*32 + l] = record index (kInvalidRec for padding lanes), grp_len[...] = byte length.
 #pragma once
 #include "common.h"
+#include <mutex>
 
 namespace fei {
 constexpr int kWindow = 1024;
@@ -27,6 +28,7 @@ struct CompactScratch { DevBuf blk_counts, blk_offsets, totals; };
 }
 
 struct fei_corpus {
+  std::mutex mu;                         // one scan / load at a time per handle (callers may be concurrent threads)
   uint64_t n = 0, global_base = 0;
   uint64_t hdr_bytes = 0, body_bytes = 0, name_bytes = 0, tile_bytes = 0;
   uint64_t n_groups = 0;

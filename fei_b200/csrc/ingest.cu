@@ -125,6 +125,8 @@ using namespace fei;
 // All n files must be valid records to be loaded; the call first reports validity so the host can drop the
 // undecodable ones (and print the reference's message) and call again with the survivors.
 extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(require_ready());
   if (!c || !h || !raw_off || (h->n && !raw)) { set_error("null argument"); return FEI_E_BADARG; }
   if (h->n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }

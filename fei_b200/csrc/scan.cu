@@ -716,12 +716,16 @@ static int compact(fei_corpus* c, bool want_lists) {
 using namespace fei;
 
 extern "C" int fei_scan_masks(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint32_t* masks) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(run_scan(c, prog, prog_len));
   if (masks && c->n) FEI_CUDA(cudaMemcpyAsync(masks, c->hits.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
   return finish_timing(c, false);
 }
 
 extern "C" int fei_scan_count(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint64_t* nhits) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(run_scan(c, prog, prog_len));
   FEI_TRY(compact(c, true));                 // lists stay on the device for fei_comm_allgather_hits
   if (nhits) for (uint32_t q = 0; q < c->last_nq; ++q) nhits[q] = c->last_counts[q];
@@ -730,6 +734,8 @@ extern "C" int fei_scan_count(fei_corpus* c, const uint8_t* prog, uint64_t prog_
 
 extern "C" int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_len,
                              uint64_t* const* hits, const uint64_t* cap, uint64_t* nhits) {
+  if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
   if (!hits || !cap || !nhits) { set_error("null argument"); return FEI_E_BADARG; }
   FEI_TRY(run_scan(c, prog, prog_len));
   FEI_TRY(compact(c, true));
