@@ -306,3 +306,81 @@ def test_raw_ingest_matches_python_text_semantics(gpu):
         b = bytes(got["body"][int(got["body_off"][i]):int(got["body_off"][i + 1])])
         assert (h, b) == (want_h, want_b), raw
         assert bool(bits[i] & 1) == (not sep) and bool(bits[i] & 2) == (not text.isascii()) and bool(bits[i] & 4) == ("İ" in text or "Σ" in text), raw
+
+
+def test_random_headers_differential(gpu):
+    """Seeded fuzz of the device header parser (k_head / k_head_parse) against the oracle: random key spellings,
+    duplicate keys, odd whitespace (incl. multi-byte), missing colons, colons in values, empty keys / values."""
+    import random
+    from fei_b200.corpus import Corpus
+    rng = random.Random(4242)
+    keys = ["Tags", "tags", "TAGS", "Subject", "subject", "Status", "status", "Priority", "X-Note", "", " Tags", "Tags ", "Ta gs", "Täg", "Key"]
+    ws = ["", " ", "  ", "\t", " ", " ", "\x0b", "\x1c", " \t "]
+    vals = ["python", "Python, rust", "a,b , c", "", "done", "ACTIVE", "high", "x: y: z", "café", "Kelvin,python", "rust ,python", ",", " , ,", "py thon"]
+    recs = []
+    for i in range(600):
+        lines = []
+        for _ in range(rng.randint(0, 7)):
+            r = rng.random()
+            if r < 0.1:
+                lines.append(rng.choice(["no colon here", "", "   ", "---x"[:3 * 0] + "plain"]))
+            else:
+                lines.append(rng.choice(ws) + rng.choice(keys) + rng.choice(ws) + ":" + rng.choice(ws) + rng.choice(vals) + rng.choice(ws))
+        hdr = "\n".join(lines) + ("\n" if lines and rng.random() < 0.7 else "")
+        if "---" in hdr:
+            hdr = hdr.replace("---", "-")
+        body = rng.choice(["", "body python", "react here", "x"])
+        r = synth.record(77, i)
+        r["hdr"] = hdr.encode(); r["body"] = body.encode(); r["raw_text"] = hdr + "---" + body
+        if rng.random() < 0.5:
+            r["flags"] = "".join(rng.sample("FRSP", rng.randint(0, 4)))
+        recs.append(r)
+    mems = [mo.make_memory(r["filename"], r["folder"], r["status"], r["raw_text"], True) for r in recs]
+    for m, r in zip(mems, recs):
+        m["metadata"]["flags"] = list(r["flags"])
+    c = Corpus().load(synth.arrays_from_records(recs))
+    cases = [
+        [("Tags", "has_tag", "python")], [("tags", "has_tag", "rust")], [("TAGS", "contains", "b")], [("Tags", "=", "python")], [("Tags", "has_tag", "")],
+        [("Status", "=", "done")], [("state", "=", "active")], [("status_value", "contains", "")], [("Subject", "contains", "y:")], [("", "=", "python")],
+        [("x-note", "startswith", "py")], [("priority", "endswith", "gh")], [("Tags", "matches", r"^\w+$")], [("Tags", "matches", r",\s*c$")],
+        [("täg", "contains", "")], [("key", "contains", "")], [("Tags", "has_tag", "kelvin")], [("Ta gs", "=", "done")], [("Tags", "!=", "python")],
+        [("Tags", "has_tag", "python"), ("flags", "has_flag", "F"), ("content", "contains", "python")],
+        [("flags", "has_flag", "SP")], [("flags", "=", "f")], [("flags", "contains", "rs")], [("Priority", ">", "h")], [("Priority", "<=", "high")],
+    ]
+    pb = ProgramBuilder()
+    for conds in cases:
+        pb.add_query(_search_prog2(conds))
+    masks = c.scan_masks(pb.build())
+    for q, conds in enumerate(cases):
+        want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
+        got = np.nonzero(masks >> np.uint32(q) & np.uint32(1))[0].tolist()
+        assert got == want, conds
+
+
+def _search_prog2(conds):
+    """Compile through the product's own query compiler (fei_b200.memdir_tools.search.compile_conditions)."""
+    from fei_b200.memdir_tools.search import compile_conditions
+
+    class _PM:                       # only what compile_conditions touches for these fields
+        folders = [""]
+        arrays = {}
+    out = compile_conditions([{"field": f, "operator": op, "value": v} for f, op, v in conds], True, _PM())
+    assert all(isinstance(x, Cond) for x in out), out
+    return out
+
+
+def test_sharded_scan_equals_unsharded(gpu):
+    """1/2/4/8-way range sharding gives byte-identical hit lists: every shard reports global indices and the
+    rank-order concatenation is the listing order (the NCCL all-gatherv moves exactly these lists)."""
+    from fei_b200 import shard
+    from fei_b200.corpus import Corpus
+    n = 4100
+    prog = content_batch_program([Pattern("regex", p, re.IGNORECASE) for p in BATCH32[:8]] + [Pattern("regex", r"kubernetes.*docker", re.IGNORECASE)])
+    whole = Corpus().synth(0xFE1, 0, n).scan_hits(prog, 9)
+    for world in (2, 4, 8):
+        per_rank = []
+        for a, b in shard.shard_ranges(n, world):
+            per_rank.append(Corpus().synth(0xFE1, a, b - a).scan_hits(prog, 9))
+        got = shard.concat_in_rank_order(per_rank)
+        for q in range(9):
+            assert np.array_equal(got[q], whole[q]), (world, q)
