@@ -178,6 +178,26 @@ def make_memdir(scratch: str, import_reference):
         with contextlib.redirect_stdout(buf):
             stats = mgr.process_memories(statuses=statuses, dry_run=True)
         out["filters"].append({"statuses": statuses, "stats": stats})
+    # public signatures of the entry points the drop-in keeps (checked against fei_b200.memdir_tools on every CPU run)
+    import inspect
+    sig = lambda f: [[p.name, int(p.kind), None if p.default is inspect.Parameter.empty else repr(p.default)] for p in inspect.signature(f).parameters.values()]
+    out["signatures"] = {
+        "search.search_memories": sig(rs.search_memories), "search.parse_search_args": sig(rs.parse_search_args),
+        "search.SearchQuery.add_condition": sig(rs.SearchQuery.add_condition), "search.SearchQuery.set_sort": sig(rs.SearchQuery.set_sort),
+        "search.SearchQuery.set_pagination": sig(rs.SearchQuery.set_pagination), "search.SearchQuery.with_content": sig(rs.SearchQuery.with_content),
+        "filter.MemoryFilter.__init__": sig(rf.MemoryFilter.__init__), "filter.MemoryFilter.add_condition": sig(rf.MemoryFilter.add_condition),
+        "filter.MemoryFilter.add_action": sig(rf.MemoryFilter.add_action), "filter.MemoryFilter.matches": sig(rf.MemoryFilter.matches),
+        "filter.MemoryFilter.apply_actions": sig(rf.MemoryFilter.apply_actions), "filter.FilterManager.add_filter": sig(rf.FilterManager.add_filter),
+        "filter.FilterManager.process_memories": sig(rf.FilterManager.process_memories), "filter.create_default_filters": sig(rf.create_default_filters),
+        "filter.run_filters": sig(rf.run_filters),
+        "memorychain.MemoryBlock.__init__": sig(rm.MemoryBlock.__init__), "memorychain.MemoryBlock.calculate_hash": sig(rm.MemoryBlock.calculate_hash),
+        "memorychain.MemoryBlock.mine_block": sig(rm.MemoryBlock.mine_block), "memorychain.MemoryBlock.to_dict": sig(rm.MemoryBlock.to_dict),
+        "memorychain.MemoryBlock.from_dict": sig(rm.MemoryBlock.from_dict), "memorychain.MemoryChain.validate_chain": sig(rm.MemoryChain.validate_chain),
+        "memorychain.MemoryChain.receive_chain_update": sig(rm.MemoryChain.receive_chain_update),
+        "utils.parse_memory_filename": sig(ru.parse_memory_filename), "utils.parse_memory_content": sig(ru.parse_memory_content),
+        "utils.list_memories": sig(ru.list_memories), "utils.move_memory": sig(ru.move_memory), "utils.update_memory_flags": sig(ru.update_memory_flags),
+        "utils.save_memory": sig(ru.save_memory), "utils.get_memdir_folders": sig(ru.get_memdir_folders),
+    }
     with open(os.path.join(HERE, "memdir_golden.json"), "w") as f:
         json.dump(out, f, indent=0, sort_keys=True, default=str)
     print("wrote memdir_golden.json:", len(out["listing"]), "memories listed,", len(out["queries"]), "queries,", len(out["filters"]), "filter runs")

@@ -84,3 +84,44 @@ def test_parse_search_args_matches_reference():
         assert q.conditions == case["conditions"], case["input"]
         assert (q.sort_by, q.sort_reverse, q.limit, q.offset, q.include_content) == \
                (case["sort_by"], case["sort_reverse"], case["limit"], case["offset"], case["include_content"]), case["input"]
+
+
+def test_public_signatures_match_reference():
+    """Drop-in contract: same parameter names, kinds, order and defaults as the reference's entry points."""
+    import importlib
+    import inspect
+    from tests.conftest import load_golden
+    sigs = load_golden("memdir_golden.json")["signatures"]
+    for name, want in sigs.items():
+        mod, _, attr = name.partition(".")
+        obj = importlib.import_module(f"fei_b200.memdir_tools.{mod}")
+        for part in attr.split("."):
+            obj = getattr(obj, part)
+        got = [[p.name, int(p.kind), None if p.default is inspect.Parameter.empty else repr(p.default)]
+               for p in inspect.signature(obj).parameters.values()]
+        if name == "memorychain.MemoryBlock.mine_block":        # ours appends an optional `max_tries`
+            got = got[:len(want)]
+        assert got == want, (name, got, want)
+
+
+def test_dropin_install_patches_the_reference_package():
+    """Only where the reference tree is mounted (build container): install() rebinds the three entry points of the
+    unmodified package.  (Running them needs a GPU; the patched functions are the ones the gpu suite exercises.)"""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/memdir_tools"):
+        pytest.skip("reference tree not mounted")
+    code = (
+        "import sys, os, tempfile; d = tempfile.mkdtemp(); os.chdir(d); os.environ['HOME'] = d;"
+        "sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r); sys.dont_write_bytecode = True;"
+        "import fei_b200.dropin as D; D.install();"
+        "import memdir_tools.search as S, memdir_tools.filter as F, memdir_tools.memorychain as M;"
+        "assert S.__file__.startswith('/root/reference');"
+        "assert S.search_memories.__module__ == 'fei_b200.dropin' and F.run_filters.__module__ == 'fei_b200.dropin';"
+        "assert F.FilterManager.process_memories.__module__ == 'fei_b200.dropin' and hasattr(F, 'apply_filters');"
+        "assert M.MemoryChain.validate_chain.__module__ == 'fei_b200.memdir_tools.memorychain';"
+        "q = S.parse_search_args('#python +F'); assert len(q.conditions) == 2; print('patched')"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "patched" in out.stdout, out.stderr[-2000:]
