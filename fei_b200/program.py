@@ -49,6 +49,9 @@ def _pad16(b: bytearray) -> None:
         b.append(0)
 
 
+_DFA_CACHE: Dict[Tuple, Dfa] = {}
+
+
 class _FieldDfa:
     """Patterns that read the same field, deduplicated -> output bits."""
 
@@ -69,7 +72,17 @@ class _FieldDfa:
         return b
 
     def compile(self, sticky: bool = False) -> Dfa:
-        return compile_patterns(self.patterns, sticky=sticky and len(self.patterns) == 1)
+        """Compiled automata are cached per process: repeated queries / the default filters skip the (host-side,
+        Python) subset construction, which costs 10-900 ms for Unicode-class-heavy patterns."""
+        sticky = sticky and len(self.patterns) == 1
+        key = (tuple((p.kind, p.text, int(p.flags)) for p in self.patterns), sticky)
+        d = _DFA_CACHE.get(key)
+        if d is None:
+            d = compile_patterns(self.patterns, sticky=sticky)
+            if len(_DFA_CACHE) >= 256:
+                _DFA_CACHE.pop(next(iter(_DFA_CACHE)))
+            _DFA_CACHE[key] = d
+        return d
 
 
 def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
