@@ -131,6 +131,7 @@ class FilterManager:
             statuses = ["new"]
         pm = packer.packed()
         ranges = pm.ranges(folders, statuses)
+        pm.report_skipped(folders, statuses)
         masks = self.match_matrix(pm) if self.filters and pm.corpus.n else np.zeros((1, pm.corpus.n), dtype=np.uint32)
         idx = np.concatenate([np.arange(a, b) for a, b in ranges]) if ranges else np.zeros(0, dtype=np.int64)
         stats = {"total_memories": int(idx.size), "filters_applied": 0, "actions_taken": 0, "memories_modified": 0, "details": []}

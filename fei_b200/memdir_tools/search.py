@@ -308,6 +308,7 @@ def search_memories(query: SearchQuery, folders: Optional[List[str]] = None, sta
                     debug: bool = False) -> List[Dict[str, Any]]:
     pm = packer.packed()
     ranges = pm.ranges(folders, statuses)
+    pm.report_skipped(folders, statuses)
     compiled = compile_conditions(query.conditions, query.include_content, pm)
     conds: List[Cond] = []
     for item in compiled:

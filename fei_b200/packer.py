@@ -53,10 +53,12 @@ def read_segment(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
     return out
 
 
-def read_segment_raw(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
+def read_segment_raw(base: str, folder: str, status: str, file_cache: Optional[Dict[Tuple, bytes]] = None) -> List[Dict[str, Any]]:
     """Like read_segment but leaves the file *text* work (decode, newline folding, '---' split, strip) to the
     GPU ingest kernels (fei_corpus_load_raw): files are read as bytes; only the file-name grammar and the
-    listing order are handled here."""
+    listing order are handled here.  `file_cache` maps (inode, size, mtime_ns) to content: a memory file is
+    immutable, and moves / flag changes are renames (utils.py:255-297, :354-388), so an incremental re-pack
+    re-reads only files it has never seen."""
     path = os.path.join(base, folder, status) if folder else os.path.join(base, status)
     if not os.path.exists(path):
         return []
@@ -68,8 +70,17 @@ def read_segment_raw(base: str, folder: str, status: str) -> List[Dict[str, Any]
             m = U.FILENAME_RE.match(name)
             if not m:
                 raise ValueError(f"Invalid memory filename: {name}")
-            with open(os.path.join(path, name), "rb") as f:
-                raw = f.read()
+            full = os.path.join(path, name)
+            raw = None
+            if file_cache is not None:
+                st = os.stat(full)
+                key = (st.st_ino, st.st_size, st.st_mtime_ns)
+                raw = file_cache.get(key)
+            if raw is None:
+                with open(full, "rb") as f:
+                    raw = f.read()
+                if file_cache is not None:
+                    file_cache[key] = raw
             ts = int(m.group(1))
             out.append({"filename": name, "folder": folder, "status": status, "ts": ts, "uid": m.group(2), "host": m.group(3),
                         "flags": m.group(4), "uid_span": (m.start(2), m.end(2)), "host_span": (m.start(3), m.end(3)),
@@ -199,6 +210,10 @@ class PackedMemdir:
         self.arrays: Dict[str, Any] = {}
         self.corpus = None
         self.signature: Tuple = ()
+        self.seg_cache: Dict[Tuple[str, str], Tuple[int, List[Dict[str, Any]]]] = {}   # (folder, status) -> (dir mtime, records)
+        self.file_cache: Dict[Tuple, bytes] = {}
+        self.files_read = 0          # files whose content was read from disk by the last build (incremental-sync telemetry)
+        self.bad: Dict[Tuple[str, str], List[str]] = {}      # undecodable files per directory, reported on every listing
 
     @staticmethod
     def tree_signature(base: str) -> Tuple:
@@ -252,9 +267,21 @@ class PackedMemdir:
             raise NotImplementedError("more than 65535 folders")
         self.folder_ids = {f: i for i, f in enumerate(self.folders)}
         segs: Dict[Tuple[str, str], List[Dict[str, Any]]] = {}
+        self.bad = {}
+        skipped_raw = set()
+        before = len(self.file_cache)
+        new_seg_cache = {}
         for folder in self.folders:
             for st in U.STANDARD_FOLDERS:
-                segs[(folder, st)] = read_segment_raw(self.base, folder, st)
+                path = os.path.join(self.base, folder, st) if folder else os.path.join(self.base, st)
+                mt = os.stat(path).st_mtime_ns if os.path.exists(path) else -1
+                cached = self.seg_cache.get((folder, st))
+                if cached is not None and cached[0] == mt:
+                    segs[(folder, st)] = list(cached[1])                 # directory untouched since the last pack
+                else:
+                    segs[(folder, st)] = read_segment_raw(self.base, folder, st, self.file_cache)
+                new_seg_cache[(folder, st)] = (mt, segs[(folder, st)])
+        self.files_read = len(self.file_cache) - before
         corpus = Corpus()
         while True:
             recs = [r for folder in self.folders for st in U.STANDARD_FOLDERS for r in segs[(folder, st)]]
@@ -269,9 +296,13 @@ class PackedMemdir:
                         msg = "invalid UTF-8"
                     except UnicodeDecodeError as e:
                         msg = str(e)
-                    print(f"Error processing {r['filename']}: {msg}")
+                    self.bad.setdefault((r["folder"], r["status"]), []).append(f"Error processing {r['filename']}: {msg}")
+                    skipped_raw.add(id(r["raw"]))
                     segs[(r["folder"], r["status"])].remove(r)
         self.recs = recs
+        self.seg_cache = {k: (mt, list(segs[k])) for k, (mt, _r) in new_seg_cache.items()}
+        live = {id(r["raw"]) for r in recs} | skipped_raw
+        self.file_cache = {k: v for k, v in self.file_cache.items() if id(v) in live}   # forget deleted files
         self.segments = {}
         pos = 0
         for folder in self.folders:
@@ -284,6 +315,13 @@ class PackedMemdir:
         arrays["any_lower_inexact"] = bool(((fsb >> 24) & REC_LOWER_INEXACT).any())
         self.arrays = arrays
         return self
+
+    def report_skipped(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> None:
+        """The reference prints `Error processing <file>: <error>` each time a directory is listed (utils.py:247-248)."""
+        for f in (self.folders if folders is None else folders):
+            for st in (U.STANDARD_FOLDERS if statuses is None else statuses):
+                for msg in self.bad.get((f, st), []):
+                    print(msg)
 
     def ranges(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> List[Tuple[int, int]]:
         """Index ranges of the requested (folder, status) pairs in the caller's order (search.py:361-363)."""
@@ -309,9 +347,14 @@ def packed(base: Optional[str] = None) -> PackedMemdir:
     """The packed corpus for a tree, rebuilt when any cur/new/tmp directory changed."""
     base = base or U.MEMDIR_BASE
     pm = _cache.get(base)
-    if pm is None or pm.signature != PackedMemdir.tree_signature(base):
-        if pm is not None and pm.corpus is not None:
-            pm.corpus.close()
+    if pm is None:
         pm = PackedMemdir(base).build()
         _cache[base] = pm
+    elif pm.signature != PackedMemdir.tree_signature(base):
+        # incremental sync: unchanged directories and already-seen files come from the host cache; the packed
+        # arrays are rebuilt and re-uploaded (H2D + tiling are cheap next to file I/O)
+        old = pm.corpus
+        pm.build()
+        if old is not None and old is not pm.corpus:
+            old.close()
     return pm

@@ -142,3 +142,45 @@ def test_real_filter_actions_move_and_flag(gpu, tmp_path):
             assert os.path.exists(os.path.join(d, name)), name
     finally:
         U.set_memdir_base(old)
+
+
+def test_incremental_sync_after_flag_and_move(gpu, tmp_path, capsys):
+    """Renames (flag updates, moves) and new files invalidate only the touched directories; file contents already
+    seen are not read again; results stay identical to the oracle's fresh listing; skipped files are reported on
+    every listing like the reference does."""
+    import os
+    from fei_b200 import packer, synth
+    from fei_b200.memdir_tools import utils as U
+    from fei_b200.memdir_tools.search import search_memories
+    base = str(tmp_path / "Memdir")
+    recs = [synth.record(21, i) for i in range(200)]
+    synth.write_memdir(base, recs)
+    with open(os.path.join(base, "cur", "1700009999.badbad01.host:2,"), "wb") as f:
+        f.write(b"Subject: x\n---\n\xff\xfe")
+    old = U.MEMDIR_BASE
+    U.set_memdir_base(base)
+    try:
+        q = _query([("Tags", "has_tag", "python")], False)
+        r1 = search_memories(q)
+        pm = packer.packed()
+        assert pm.files_read == 201
+        assert "Error processing 1700009999.badbad01.host:2,:" in capsys.readouterr().out
+        # flag update (rename inside one directory) + a move across folders + one brand-new memory
+        m = r1[0]
+        assert U.update_memory_flags(m["filename"], m["folder"], m["status"], "FRS")
+        m2 = r1[1]
+        assert U.move_memory(m2["filename"], m2["folder"], ".Archive", m2["status"], "cur")
+        U.save_memory(".Projects/AI", "fresh body about python", {"Tags": "python,new", "Subject": "fresh"}, "P")
+        r2 = search_memories(q)
+        pm2 = packer.packed()
+        assert pm2 is pm and pm.files_read == 1                      # only the new file's content was read
+        assert "Error processing 1700009999.badbad01.host:2,:" in capsys.readouterr().out
+        mems = mo.listing(base, None, None, False)
+        capsys.readouterr()
+        want = [mems[i] for i in mo.run_search(mems, [{"field": "Tags", "operator": "has_tag", "value": "python"}])]
+        assert [key_of(x) for x in r2] == [key_of(x) for x in want]
+        assert len(r2) == len(r1) + 1
+        got_flags = [x for x in r2 if x["metadata"]["unique_id"] == m["metadata"]["unique_id"]][0]["metadata"]["flags"]
+        assert got_flags == list("FRS")
+    finally:
+        U.set_memdir_base(old)
