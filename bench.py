@@ -104,6 +104,22 @@ def _oracle_batch_worker(args):
     return time.perf_counter() - t0, total
 
 
+def usable_cores() -> int:
+    """Cores this process may really use: scheduler affinity capped by the cgroup CPU quota (os.cpu_count() reports the
+    whole machine inside a container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_scan_rate(sample: int, cores: int):
     """memories/s of the 32-pattern batch on `cores` host processes (match-only, records already parsed)."""
     if cores <= 1:
@@ -132,7 +148,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     use = max(1, min(cores, 64))
     per_step = 1500 * use                               # bounded sample: 1500 records x 32 passes per worker per step
     times = []
@@ -305,7 +321,7 @@ def main():
         rate, dt = cpu_scan_rate(args.cpu_sample, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "memories/s", "cores": 1, "kind": "port",
                                 "sample": f"{args.cpu_sample} synthetic records x 32 single-pattern passes (oracle port of search.py:244-335, match-only), {dt:.1f} s",
-                                "host_cores_available": os.cpu_count()}
+                                "host_cores_available": usable_cores(), "host_cores_reported": os.cpu_count()}
         if not args.no_extra:
             line["extra"] = run_extra(args, corpus, st, peak, lib, _abi)
     if dist:
