@@ -75,13 +75,13 @@ def test_message_length_edges(gpu):
     assert (fb.value, kind.value) == (3, 1)          # block 4's link to "weird-hash" is fine, block 3's hash is not
 
 
-def test_synthetic_chain_100k_properties(gpu):
+def test_synthetic_chain_1m_properties(gpu):
     """Full-size style run on device-resident data: valid chain -> True; one corruption -> same index;
     digests equal hashlib on the fetched texts (sampled)."""
     from fei_b200 import _abi
     import ctypes as C
-    n = 100_000
-    for corrupt in (-1, 77_777):
+    n = 1_000_000                                     # BASELINE configs[3] size
+    for corrupt in (-1, 777_777):
         ch = C.c_void_p()
         _abi.check(_abi.lib().fei_chain_create(C.byref(ch)))
         try:
@@ -96,7 +96,7 @@ def test_synthetic_chain_100k_properties(gpu):
             k = 2000
             buf = np.zeros(k * 400, dtype=np.uint8); off = np.zeros(k + 1, dtype=np.uint64)
             hh = np.zeros(k * 64, dtype=np.uint8)
-            first = 50_000
+            first = 500_000
             _abi.check(_abi.lib().fei_chain_fetch(ch, first, k, _abi.ptr(buf), buf.size, _abi.ptr(off), _abi.ptr(hh), None))
             for i in range(k):
                 text = bytes(buf[int(off[i]):int(off[i + 1])])

@@ -384,3 +384,36 @@ def test_sharded_scan_equals_unsharded(gpu):
         got = shard.concat_in_rank_order(per_rank)
         for q in range(9):
             assert np.array_equal(got[q], whole[q]), (world, q)
+
+
+def test_full_size_corpus_sampled_windows_and_invariants(gpu):
+    """BASELINE-scale run (2M entries generated and tiled on the GPU): sampled windows must equal the oracle on the same
+    records from the host generator; size-independent invariants hold on the whole result (ordering, counts = popcounts,
+    hits ⊆ range, union/intersection consistency between a batch and its single-pattern scans)."""
+    from fei_b200.corpus import Corpus
+    n = 2_000_000
+    c = Corpus().synth(0xFE1, 0, n)
+    pats = BATCH32[:6] + [r"kubernetes.*docker|docker.*kubernetes", r"quagga"]
+    prog = content_batch_program([Pattern("regex", p, re.IGNORECASE) for p in pats])
+    masks = c.scan_masks(prog)
+    counts = c.scan_count(prog, len(pats))
+    for q in range(len(pats)):
+        assert int(counts[q]) == int(((masks >> np.uint32(q)) & np.uint32(1)).sum())
+    assert int(counts[len(pats) - 1]) == 0
+    hits = c.scan_hits(prog, len(pats))
+    for q in range(len(pats)):
+        h = hits[q]
+        assert h.size == int(counts[q]) and (h.size == 0 or (int(h[0]) >= 0 and int(h[-1]) < n and bool(np.all(h[1:] > h[:-1]))))
+        assert np.array_equal(np.nonzero((masks >> np.uint32(q)) & np.uint32(1))[0].astype(np.uint64), h)
+    # single-pattern (sticky kernel variant) == its bit in the batch (multi-output variant)
+    for q in (0, 6):
+        pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", pats[q], re.IGNORECASE))])
+        assert np.array_equal(c.scan_hits(pb.build(), 1)[0], hits[q])
+    for first in (0, 777_777, n - 1500):
+        k = 1500
+        recs = [synth.record(0xFE1, first + i) for i in range(k)]
+        mems = memories_of(recs)
+        for q, p in enumerate(pats):
+            want = mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}])
+            got = np.nonzero((masks[first:first + k] >> np.uint32(q)) & np.uint32(1))[0].tolist()
+            assert got == want, (first, p)
