@@ -92,6 +92,7 @@ __global__ void k_tile_copy(const uint8_t* __restrict__ body, const uint64_t* __
       uint4 v = load16_unaligned(src + (uint64_t)k * 16);
       int rem = (int)len - (int)(k * 16);
       if (rem < 16) { v.x = mask_bytes(v.x, rem); v.y = mask_bytes(v.y, rem - 4); v.z = mask_bytes(v.z, rem - 8); v.w = mask_bytes(v.w, rem - 12); }
+      v.x = tile_byte_perm4(v.x); v.y = tile_byte_perm4(v.y); v.z = tile_byte_perm4(v.z); v.w = tile_byte_perm4(v.w);
       *reinterpret_cast<uint4*>(row + lane * 16) = v;
     }
     row += (uint64_t)m * 16;
@@ -115,7 +116,7 @@ __global__ void k_untile(const uint8_t* __restrict__ tiles, const uint64_t* __re
     for (int l = 0; l < 32; ++l) { uint32_t u = (gl[l] + 15) >> 4; before += u < k ? u : k; }
     const uint8_t* p = gb + before * 16 + lane * 16;
     uint32_t cnt = len - k * 16 < 16 ? len - k * 16 : 16;
-    for (uint32_t b = 0; b < cnt; ++b) dst[k * 16 + b] = p[b];
+    for (uint32_t b = 0; b < cnt; ++b) { uint8_t t = p[b]; dst[k * 16 + b] = (uint8_t)(t ^ ((t >> 1) & 0x20)); }   // undo the tile byte permutation
   }
 }
 

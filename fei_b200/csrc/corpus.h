@@ -19,6 +19,15 @@
 #include <mutex>
 
 namespace fei {
+// Body tiles store every byte b as  b ^ ((b >> 1) & 0x20)  (an involution: bit 5 ^= bit 6).  The scan tables are
+// indexed by the stored value (program.py permutes their columns), so nothing changes for the result; what changes
+// is which shared-memory bank a byte selects: plain ASCII puts lower-case letters (0x60-0x7F) and space / digits /
+// punctuation (0x20-0x3F) on the SAME 16 banks (bank = (row + byte/2) mod 32), so lanes sitting in the same automaton
+// state collided whenever one read a letter and another a space; after the swap letters use banks 0-15 and
+// space / punctuation banks 16-31 (measured: 2.0 -> see DESIGN.md wavefronts per lookup on single-pattern scans).
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ uint32_t tile_byte_perm4(uint32_t w) { return w ^ ((w >> 1) & 0x20202020u); }
+#endif
 constexpr int kWindow = 1024;
 constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
 }

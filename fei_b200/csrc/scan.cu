@@ -453,6 +453,174 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
   if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
 }
 
+// ---------------------------------------------------------------- single-pattern content scan, small automaton
+// k_body_sticky: the kAcc == 3 case of k_body when the whole byte-indexed table sits below shared address 64 Ki.
+// The transition entries are rewritten in place, after staging, from "state index" to "shared address of that
+// state's row", so one step is PRMT (byte extract) + IMAD (byte * 2 + row address) + LDS.U16: 3 issue slots per
+// byte instead of 4, no second multiply on the dependent chain.  Rows that are full for all 32 lanes (all but the
+// ragged tail of a group: the records of a group are length-sorted neighbours) run in a predicate-free loop, two
+// rows per iteration with the loads for the next two already in flight.
+__device__ __forceinline__ uint32_t sticky_step(uint32_t e, uint32_t b) {
+  uint32_t addr;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(b), "r"(e));
+  uint16_t nxt;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(nxt) : "r"(addr));
+  return nxt;
+}
+__device__ __forceinline__ uint32_t sticky_word(uint32_t e, uint32_t w) {
+  e = sticky_step(e, __byte_perm(w, 0, 0x4440)); e = sticky_step(e, __byte_perm(w, 0, 0x4441));
+  e = sticky_step(e, __byte_perm(w, 0, 0x4442)); return sticky_step(e, __byte_perm(w, 0, 0x4443));
+}
+__device__ __forceinline__ uint32_t sticky_row(uint32_t e, const uint4& v) {
+  return sticky_word(sticky_word(sticky_word(sticky_word(e, v.x), v.y), v.z), v.w);
+}
+__device__ __forceinline__ uint32_t sticky_partial(uint32_t e, uint32_t w, int nbytes) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) if (j < nbytes) e = sticky_step(e, (w >> (8 * j)) & 0xFFu);
+  return e;
+}
+
+constexpr int kStages = 4, kChunkRows = 2;        // per warp: 4 bulk copies of 2 rows (1 KiB) in flight
+constexpr uint32_t kChunkBytes = kChunkRows * 512u;
+constexpr uint32_t kWarpRingBytes = kStages * kChunkBytes;
+constexpr uint32_t kStickyRingBytes = (kWarpRingBytes + kStages * 8u) * (kBodyThreads / 32);
+__device__ __forceinline__ uint4 lds128(uint32_t addr_s) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr_s));
+  return r;
+}
+constexpr uint32_t kStickyAddrLimit = 65535u;
+constexpr uint32_t kStickyAddrSlack = 4096u;     // head-room the host leaves for the shared-memory window base
+
+__global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const fei_prog_dfa* dd = reinterpret_cast<const fei_prog_dfa*>(a.prog + ph->off_body_dfa);
+  const uint32_t table_bytes = dd->table_bytes;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, table_bytes);
+    const uint8_t* src = a.prog + dd->off_trans;
+    for (uint32_t o = 0; o < table_bytes; o += 32768u) {
+      uint32_t nb = table_bytes - o < 32768u ? table_bytes - o : 32768u;
+      bulk_g2s(smem + o, src + o, nb, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+  const uint32_t trans_s = smem_u32(smem), stride2 = dd->row_stride * 2u, n_entries = dd->n_states * dd->row_stride;
+  // per-warp ring + its mbarriers, behind the table
+  const uint32_t warp = threadIdx.x >> 5;
+  uint8_t* ring = smem + ((table_bytes + 127u) & ~127u) + warp * kWarpRingBytes;
+  const uint32_t ring_s = smem_u32(ring);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ((table_bytes + 127u) & ~127u) + (kBodyThreads / 32) * kWarpRingBytes) + warp * kStages;
+  if ((threadIdx.x & 31) < kStages) mbar_init(&bars[threadIdx.x & 31], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  uint32_t prod = 0, cons = 0;                       // chunks issued / consumed by this warp since kernel start (stage = count % kStages)
+  if (trans_s + dd->n_states * stride2 > kStickyAddrLimit) __trap();      // host-side eligibility test left 4 KiB of slack
+  {
+    uint16_t* t = reinterpret_cast<uint16_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < n_entries; i += kBodyThreads) t[i] = (uint16_t)(trans_s + (uint32_t)t[i] * stride2);
+  }
+  __syncthreads();
+  const uint32_t* endout = reinterpret_cast<const uint32_t*>(smem + (dd->off_endout - dd->off_trans));
+  const uint32_t start_e = trans_s + dd->start * stride2;
+  const uint32_t sticky_e = dd->sticky != 0xFFFFFFFFu ? trans_s + (dd->sticky - 1u) * stride2 : 0xFFFFFFFFu;
+  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
+  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
+  const uint32_t nq = ph->n_queries;
+  const uint32_t all_q = nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1u);
+  const int lane = threadIdx.x & 31;
+  unsigned long long touched = 0;
+
+  for (;;) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(a.counter, 1ull);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= a.n_groups) break;
+    const uint32_t rec = a.grp_rec[g * 32 + lane];
+    const uint32_t len = a.grp_len[g * 32 + lane];
+    const uint32_t units = (len + 15) >> 4;
+    uint32_t alive = 0;
+    if (rec != kInvalidRec) alive = a.has_alive ? a.hits[rec] : all_q;
+    const bool live = alive != 0;
+    const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+    if (live_mask == 0) continue;
+    const uint8_t* row = a.tiles + a.grp_base[g] * 16;
+    const uint32_t maxu = __shfl_sync(0xffffffffu, units, 0);
+    if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
+    uint32_t e = start_e;
+    uint32_t k = 0;
+    // ---- rows that are 16 full bytes for all 32 lanes are one contiguous run of 512-byte rows: stream it through the
+    // warp's ring with TMA bulk copies, kChunkRows rows per copy, kStages copies in flight.  A stage is refilled as soon
+    // as its rows sit in registers, so the automaton always runs with the next kStages chunks on their way.
+    const uint32_t full = live_mask == 0xffffffffu ? __reduce_min_sync(0xffffffffu, len >> 4) : 0u;
+    const uint32_t n_chunks = full / kChunkRows;
+    if (n_chunks) {
+      uint32_t issued = 0;
+      for (; issued < n_chunks && issued < (uint32_t)kStages; ++issued, ++prod)
+        if (lane == 0) { mbar_expect_tx(&bars[prod % kStages], kChunkBytes); bulk_g2s(ring + (prod % kStages) * kChunkBytes, row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[prod % kStages]); }
+      uint32_t c = 0;
+      bool stop = false;
+      for (; c < n_chunks && !stop; ++c) {
+        const uint32_t st = cons % kStages;
+        mbar_wait(&bars[st], (cons / kStages) & 1u);
+        ++cons;
+        uint4 v[kChunkRows];
+#pragma unroll
+        for (int r = 0; r < kChunkRows; ++r) v[r] = lds128(ring_s + st * kChunkBytes + r * 512u + lane * 16u);
+        __syncwarp();                                  // every lane holds its rows: the stage may be overwritten
+        if (issued < n_chunks) {
+          if (lane == 0) { mbar_expect_tx(&bars[st], kChunkBytes); bulk_g2s(ring + st * kChunkBytes, row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[st]); }
+          ++issued; ++prod;
+        }
+#pragma unroll
+        for (int r = 0; r < kChunkRows; ++r) e = sticky_row(e, v[r]);
+        stop = __ballot_sync(0xffffffffu, e != sticky_e) == 0;      // every lane has matched
+      }
+      for (; cons < prod; ++cons) mbar_wait(&bars[cons % kStages], (cons / kStages) & 1u);   // early stop: let the copies in flight land
+      k = stop ? maxu : c * kChunkRows;
+      row += (uint64_t)c * kChunkBytes;
+    }
+    // ---- ragged remainder (and groups with dead lanes): per-row lane count from a ballot, next row's load in flight
+    if (k < maxu) {
+      uint4 cur = make_uint4(0, 0, 0, 0);
+      if (k < units && live) cur = ldg_stream16(row + lane * 16);
+      for (; k < maxu; ++k) {
+        const uint32_t m = __popc(__ballot_sync(0xffffffffu, k < units));
+        const uint8_t* next_row = row + (uint64_t)m * 16;
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (k + 1 < units && live) nxt = ldg_stream16(next_row + lane * 16);
+        if (k < units && live) {
+          int nb = (int)len - (int)(k * 16);
+          if (nb >= 16) e = sticky_row(e, cur);
+          else { e = sticky_partial(e, cur.x, nb); e = sticky_partial(e, cur.y, nb - 4); e = sticky_partial(e, cur.z, nb - 8); e = sticky_partial(e, cur.w, nb - 12); }
+        }
+        cur = nxt; row = next_row;
+        if (__ballot_sync(0xffffffffu, live && k + 1 < units && e != sticky_e) == 0) break;
+      }
+    }
+    if (live) {
+      const uint32_t acc = endout[(e - trans_s) / stride2];
+      uint32_t hit = 0;
+      for (uint32_t q = 0; q < nq; ++q) {
+        if (!(alive >> q & 1)) continue;
+        bool ok = true;
+        for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
+          const fei_prog_cond& cd = conds[c];
+          if (cd.kind == FEI_C_BODY) ok = ((acc >> cd.bit) & 1u) != cd.negate;
+        }
+        if (ok) hit |= 1u << q;
+      }
+      a.hits[rec] = hit;
+    } else if (rec != kInvalidRec && !a.has_alive) {
+      a.hits[rec] = 0;
+    }
+  }
+  if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
+}
+
 template <bool kDirect, int kAcc>
 static int launch_body(const BodyArgs& a, unsigned grid, size_t smem, cudaStream_t s) {
   FEI_CUDA(cudaFuncSetAttribute(k_body<kDirect, kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -637,7 +805,12 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
     int acc_mode = d.sticky ? 3 : n_acc <= 32 ? 1 : n_acc <= 64 ? 2 : 0;
     bool direct = d.n_cols == 256;
     int rc;
-    if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
+    if (direct && acc_mode == 3 && (uint64_t)d.n_states * d.row_stride * 2 + kStickyAddrSlack <= kStickyAddrLimit) {
+      const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
+      FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
+      k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);
+      rc = FEI_OK;
+    } else if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
     else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
     FEI_TRY(rc);
     ++launches;

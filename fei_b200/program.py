@@ -85,7 +85,13 @@ class _FieldDfa:
         return d
 
 
-def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
+def tile_byte_perm(b: np.ndarray) -> np.ndarray:
+    """Byte substitution applied to the body tiles at pack time (fei_b200/csrc/corpus.h): bit 5 ^= bit 6."""
+    b = b.astype(np.int64)
+    return b ^ ((b >> 1) & 0x20)
+
+
+def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0, tile_bytes: bool = False) -> int:
     """Append descriptor + tables; returns the descriptor offset.  States are renumbered so that
     states with a non-empty `out` come first (the kernels test `state < n_acc`, and the body kernel
     records accepting state k as bit k without a table lookup)."""
@@ -98,12 +104,17 @@ def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
     new_id[order] = np.arange(n)
     n_acc = int(accepting.sum())
     direct = direct_limit and n * 516 + n * 8 + 256 <= direct_limit
+    cls = d.cls.astype(np.uint8)
     if direct:
         trans = new_id[d.trans[order]].astype(np.uint16)              # [n, 256]
         ncols = 256
+        if tile_bytes:                                                # columns addressed by the stored (permuted) byte
+            trans = trans[:, tile_byte_perm(np.arange(256))]
     else:
         trans = new_id[d.ctrans[order]].astype(np.uint16)             # [n, ncls]
         ncols = trans.shape[1]
+        if tile_bytes:
+            cls = cls[tile_byte_perm(np.arange(256))]
     # pad rows so that (row_stride / 2) is odd: state s starts at bank (s * stride/2) % 32, which walks
     # all 32 banks instead of piling every row onto the same ones (bank-conflict spreading)
     stride = ncols + (ncols & 1)
@@ -124,7 +135,7 @@ def serialize_dfa(d: Dfa, blob: bytearray, direct_limit: int = 0) -> int:
     trans_bytes = len(blob) - off_trans
     off_out = len(blob); blob.extend(out.tobytes()); _pad16(blob)
     off_endout = len(blob); blob.extend(endout.tobytes()); _pad16(blob)
-    off_cls = len(blob); blob.extend(d.cls.astype(np.uint8).tobytes()); _pad16(blob)
+    off_cls = len(blob); blob.extend(cls.tobytes()); _pad16(blob)
     table_bytes = len(blob) - off_trans
     empty_acc = int(out[start]) | int(endout[start])
     sticky = 0
@@ -203,7 +214,7 @@ class ProgramBuilder:
             for si, (f, mode, empty) in enumerate(slots):
                 off_val = serialize_dfa(slot_dfas[si].compile(), blob)
                 struct.pack_into("<4I", blob, off_slots + 16 * si, mode, off_val, 1 if empty else 0, 0)
-        off_body = serialize_dfa(body.compile(sticky=True), blob, SMEM_TABLE_LIMIT) if body.patterns else 0
+        off_body = serialize_dfa(body.compile(sticky=True), blob, SMEM_TABLE_LIMIT, tile_bytes=True) if body.patterns else 0
         if off_body:
             tb = struct.unpack_from("<I", blob, off_body + 44)[0]
             if tb > 220 * 1024:
