@@ -14,47 +14,48 @@ __global__ void k_units(const uint64_t* __restrict__ off, uint64_t n, uint32_t* 
   if (i < n) len[i] = (uint32_t)(off[i + 1] - off[i]);
 }
 
-// One block per window of kWindow records: bitonic sort by (units desc, index asc).
-__global__ void __launch_bounds__(kWindow)
+// One block per window of kWindow records: bitonic sort by (units desc, index asc), kWindow / kSortThreads keys per thread.
+constexpr int kSortThreads = 1024;
+__global__ void __launch_bounds__(kSortThreads)
 k_window_sort(const uint32_t* __restrict__ len, uint64_t n, uint32_t* __restrict__ grp_rec, uint32_t* __restrict__ grp_len,
               uint32_t* __restrict__ grp_units, uint32_t* __restrict__ rec_pos) {
-  __shared__ uint32_t key[kWindow];
-  __shared__ uint32_t gsum[kWindow / 32];
-  uint64_t base = (uint64_t)blockIdx.x * kWindow;
-  uint32_t t = threadIdx.x;
-  uint64_t i = base + t;
-  uint32_t l = i < n ? len[i] : 0;
-  uint32_t units = (l + 15) >> 4;
-  // key: bit 31 = real record, bits 30..10 = units (bodies are limited to 32 MiB by fei_corpus_load),
-  // bits 9..0 = kWindow-1-index.  Larger key sorts first: real records, longer bodies, lower index.
-  key[t] = (i < n ? 0x80000000u : 0u) | ((units & 0x1FFFFFu) << 10) | (uint32_t)(kWindow - 1 - t);
+  __shared__ uint64_t key[kWindow];
+  const uint64_t base = (uint64_t)blockIdx.x * kWindow;
+  // key: bit 63 = real record, bits 62..32 = units, bits 31..0 = kWindow-1-index.
+  // Larger key sorts first: real records, longer bodies, lower index.
+  for (uint32_t t = threadIdx.x; t < kWindow; t += kSortThreads) {
+    const uint64_t i = base + t;
+    const uint32_t l = i < n ? len[i] : 0;
+    key[t] = (i < n ? 1ull << 63 : 0ull) | ((uint64_t)((l + 15) >> 4) << 32) | (uint64_t)(kWindow - 1 - t);
+  }
   __syncthreads();
   for (uint32_t k = 2; k <= kWindow; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      uint32_t p = t ^ j;
-      if (p > t) {
-        uint32_t a = key[t], b = key[p];
-        bool desc = (t & k) == 0;                             // overall descending order
-        if (desc ? a < b : a > b) { key[t] = b; key[p] = a; }
+      for (uint32_t t = threadIdx.x; t < kWindow; t += kSortThreads) {
+        const uint32_t p = t ^ j;
+        if (p > t) {
+          const uint64_t a = key[t], b = key[p];
+          const bool desc = (t & k) == 0;                       // overall descending order
+          if (desc ? a < b : a > b) { key[t] = b; key[p] = a; }
+        }
       }
       __syncthreads();
     }
   }
-  uint32_t kk = key[t];
-  uint32_t idx = kWindow - 1 - (kk & (kWindow - 1));
-  uint64_t rec = base + idx;
-  bool real = (kk & 0x80000000u) != 0;
-  uint32_t rl = real ? len[rec] : 0;
-  uint32_t ru = (rl + 15) >> 4;
-  uint64_t pos = base + t;
-  grp_rec[pos] = real ? (uint32_t)rec : kInvalidRec;
-  grp_len[pos] = rl;
-  if (real) rec_pos[rec] = (uint32_t)pos;
-  uint32_t s = ru;
-  for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((t & 31) == 0) gsum[t >> 5] = s;
-  __syncthreads();
-  if (t < kWindow / 32) grp_units[(base >> 5) + t] = gsum[t];
+  for (uint32_t t = threadIdx.x; t < kWindow; t += kSortThreads) {       // t, t + 1024, ... keep warps on whole groups
+    const uint64_t kk = key[t];
+    const uint32_t idx = kWindow - 1 - (uint32_t)(kk & 0xFFFFFFFFu);
+    const uint64_t rec = base + idx;
+    const bool real = (kk >> 63) != 0;
+    const uint32_t rl = real ? len[rec] : 0;
+    const uint64_t pos = base + t;
+    grp_rec[pos] = real ? (uint32_t)rec : kInvalidRec;
+    grp_len[pos] = rl;
+    if (real) rec_pos[rec] = (uint32_t)pos;
+    uint32_t s = (rl + 15) >> 4;
+    for (int o = 16; o; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((t & 31) == 0) grp_units[pos >> 5] = s;
+  }
 }
 
 __device__ __forceinline__ uint4 load16_unaligned(const uint8_t* s) {
@@ -135,7 +136,7 @@ int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off
   FEI_TRY(c->grp_base.ensure((n_groups + 1) * sizeof(uint64_t)));
   if (n == 0) { FEI_CUDA(cudaMemsetAsync(c->grp_base.p, 0, sizeof(uint64_t), s)); c->tile_bytes = 0; return FEI_OK; }
   k_units<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_body_off, n, len.as<uint32_t>());
-  k_window_sort<<<(unsigned)n_windows, kWindow, 0, s>>>(len.as<uint32_t>(), n, c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
+  k_window_sort<<<(unsigned)n_windows, kSortThreads, 0, s>>>(len.as<uint32_t>(), n, c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
                                                        gunits.as<uint32_t>(), c->rec_pos.as<uint32_t>());
   FEI_TRY(exclusive_scan_u32_u64(gunits.as<uint32_t>(), n_groups, c->grp_base.as<uint64_t>(), c->scan_tmp, s));
   uint64_t total_units = 0;

@@ -28,7 +28,7 @@ namespace fei {
 #ifdef __CUDACC__
 __host__ __device__ __forceinline__ uint32_t tile_byte_perm4(uint32_t w) { return w ^ ((w >> 1) & 0x20202020u); }
 #endif
-constexpr int kWindow = 1024;
+constexpr int kWindow = 4096;
 constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
 }
 

@@ -480,9 +480,10 @@ __device__ __forceinline__ uint32_t sticky_partial(uint32_t e, uint32_t w, int n
   return e;
 }
 
-constexpr int kStages = 4, kChunkRows = 2;        // per warp: 4 bulk copies of 2 rows (1 KiB) in flight
+constexpr int kStages = 2, kChunkRows = 2;        // per warp: 2 stages, each 2 rows (1 KiB) of each of two groups
 constexpr uint32_t kChunkBytes = kChunkRows * 512u;
-constexpr uint32_t kWarpRingBytes = kStages * kChunkBytes;
+constexpr uint32_t kStageBytes = 2 * kChunkBytes;
+constexpr uint32_t kWarpRingBytes = kStages * kStageBytes;
 constexpr uint32_t kStickyRingBytes = (kWarpRingBytes + kStages * 8u) * (kBodyThreads / 32);
 __device__ __forceinline__ uint4 lds128(uint32_t addr_s) {
   uint4 r;
@@ -534,78 +535,166 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
   const int lane = threadIdx.x & 31;
   unsigned long long touched = 0;
 
-  for (;;) {
-    unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(a.counter, 1ull);
-    g = __shfl_sync(0xffffffffu, g, 0);
-    if (g >= a.n_groups) break;
-    const uint32_t rec = a.grp_rec[g * 32 + lane];
-    const uint32_t len = a.grp_len[g * 32 + lane];
-    const uint32_t units = (len + 15) >> 4;
-    uint32_t alive = 0;
-    if (rec != kInvalidRec) alive = a.has_alive ? a.hits[rec] : all_q;
-    const bool live = alive != 0;
-    const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
-    if (live_mask == 0) continue;
-    const uint8_t* row = a.tiles + a.grp_base[g] * 16;
-    const uint32_t maxu = __shfl_sync(0xffffffffu, units, 0);
+  // One group of 32 records as this warp sees it.
+  struct Grp {
+    uint32_t rec, len, alive, maxu, full, k, e;
+    bool live;
+    const uint8_t* row;          // next unread row
+  };
+  auto open_group = [&](unsigned long long g, Grp& G) {
+    G.rec = kInvalidRec; G.len = 0; G.alive = 0; G.maxu = 0; G.full = 0; G.k = 0; G.e = start_e; G.live = false; G.row = a.tiles;
+    if (g >= a.n_groups) return;
+    G.rec = a.grp_rec[g * 32 + lane];
+    G.len = a.grp_len[g * 32 + lane];
+    if (G.rec != kInvalidRec) G.alive = a.has_alive ? a.hits[G.rec] : all_q;
+    G.live = G.alive != 0;
+    const uint32_t live_mask = __ballot_sync(0xffffffffu, G.live);
+    if (live_mask == 0) return;                                     // nobody in this group can still match: skip its bytes
+    G.row = a.tiles + a.grp_base[g] * 16;
+    G.maxu = __shfl_sync(0xffffffffu, (G.len + 15) >> 4, 0);
+    // rows that are 16 full bytes for all 32 lanes form one contiguous run of 512-byte rows
+    G.full = live_mask == 0xffffffffu ? __reduce_min_sync(0xffffffffu, G.len >> 4) : 0u;
     if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
-    uint32_t e = start_e;
-    uint32_t k = 0;
-    // ---- rows that are 16 full bytes for all 32 lanes are one contiguous run of 512-byte rows: stream it through the
-    // warp's ring with TMA bulk copies, kChunkRows rows per copy, kStages copies in flight.  A stage is refilled as soon
-    // as its rows sit in registers, so the automaton always runs with the next kStages chunks on their way.
-    const uint32_t full = live_mask == 0xffffffffu ? __reduce_min_sync(0xffffffffu, len >> 4) : 0u;
-    const uint32_t n_chunks = full / kChunkRows;
-    if (n_chunks) {
-      uint32_t issued = 0;
-      for (; issued < n_chunks && issued < (uint32_t)kStages; ++issued, ++prod)
-        if (lane == 0) { mbar_expect_tx(&bars[prod % kStages], kChunkBytes); bulk_g2s(ring + (prod % kStages) * kChunkBytes, row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[prod % kStages]); }
-      uint32_t c = 0;
-      bool stop = false;
-      for (; c < n_chunks && !stop; ++c) {
-        const uint32_t st = cons % kStages;
-        mbar_wait(&bars[st], (cons / kStages) & 1u);
-        ++cons;
-        uint4 v[kChunkRows];
+  };
+  // Full rows of ONE group through the ring: kChunkRows rows per bulk copy, kStages copies in flight; a stage is refilled
+  // as soon as its rows sit in registers.
+  auto stream_single = [&](Grp& G) {
+    if (G.k >= G.full) return;
+    const uint32_t n_chunks = (G.full - G.k) / kChunkRows;
+    if (!n_chunks) return;
+    uint32_t issued = 0, c = 0;
+    for (; issued < n_chunks && issued < (uint32_t)kStages; ++issued, ++prod)
+      if (lane == 0) { mbar_expect_tx(&bars[prod % kStages], kChunkBytes); bulk_g2s(ring + (prod % kStages) * kStageBytes, G.row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[prod % kStages]); }
+    bool stop = false;
+    for (; c < n_chunks && !stop; ++c) {
+      const uint32_t st = cons % kStages;
+      mbar_wait(&bars[st], (cons / kStages) & 1u);
+      ++cons;
+      uint4 v[kChunkRows];
 #pragma unroll
-        for (int r = 0; r < kChunkRows; ++r) v[r] = lds128(ring_s + st * kChunkBytes + r * 512u + lane * 16u);
-        __syncwarp();                                  // every lane holds its rows: the stage may be overwritten
-        if (issued < n_chunks) {
-          if (lane == 0) { mbar_expect_tx(&bars[st], kChunkBytes); bulk_g2s(ring + st * kChunkBytes, row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[st]); }
-          ++issued; ++prod;
-        }
+      for (int r = 0; r < kChunkRows; ++r) v[r] = lds128(ring_s + st * kStageBytes + r * 512u + lane * 16u);
+      if (G.e == sticky_e) {                         // matched lanes all look up the same word (a broadcast) from here on
 #pragma unroll
-        for (int r = 0; r < kChunkRows; ++r) e = sticky_row(e, v[r]);
-        stop = __ballot_sync(0xffffffffu, e != sticky_e) == 0;      // every lane has matched
+        for (int r = 0; r < kChunkRows; ++r) v[r] = make_uint4(0, 0, 0, 0);
       }
-      for (; cons < prod; ++cons) mbar_wait(&bars[cons % kStages], (cons / kStages) & 1u);   // early stop: let the copies in flight land
-      k = stop ? maxu : c * kChunkRows;
-      row += (uint64_t)c * kChunkBytes;
+      __syncwarp();                                  // every lane holds its rows: the stage may be overwritten
+      if (issued < n_chunks) {
+        if (lane == 0) { mbar_expect_tx(&bars[st], kChunkBytes); bulk_g2s(ring + st * kStageBytes, G.row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[st]); }
+        ++issued; ++prod;
+      }
+#pragma unroll
+      for (int r = 0; r < kChunkRows; ++r) G.e = sticky_row(G.e, v[r]);
+      stop = __ballot_sync(0xffffffffu, G.e != sticky_e) == 0;      // every lane has matched
     }
-    // ---- ragged remainder (and groups with dead lanes): per-row lane count from a ballot, next row's load in flight
-    if (k < maxu) {
-      uint4 cur = make_uint4(0, 0, 0, 0);
-      if (k < units && live) cur = ldg_stream16(row + lane * 16);
-      for (; k < maxu; ++k) {
-        const uint32_t m = __popc(__ballot_sync(0xffffffffu, k < units));
-        const uint8_t* next_row = row + (uint64_t)m * 16;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (k + 1 < units && live) nxt = ldg_stream16(next_row + lane * 16);
-        if (k < units && live) {
-          int nb = (int)len - (int)(k * 16);
-          if (nb >= 16) e = sticky_row(e, cur);
-          else { e = sticky_partial(e, cur.x, nb); e = sticky_partial(e, cur.y, nb - 4); e = sticky_partial(e, cur.z, nb - 8); e = sticky_partial(e, cur.w, nb - 12); }
+    for (; cons < prod; ++cons) mbar_wait(&bars[cons % kStages], (cons / kStages) & 1u);   // early stop: let the copies in flight land
+    G.row += (uint64_t)c * kChunkBytes;
+    G.k = stop ? G.maxu : G.k + c * kChunkRows;
+  };
+  // The same for TWO groups in lock step: each lane runs two independent automaton chains, so the shared-memory
+  // latency of one lookup is covered by the other chain's (the single chain is LDS-latency bound: 8 warps per scheduler).
+  auto stream_pair = [&](Grp& A, Grp& B) {
+    const uint32_t n_chunks = (A.full < B.full ? A.full : B.full) / kChunkRows;
+    if (!n_chunks) return;
+    uint32_t issued = 0, c = 0;
+    auto issue = [&](uint32_t st) {
+      if (lane == 0) {
+        mbar_expect_tx(&bars[st], 2 * kChunkBytes);
+        bulk_g2s(ring + st * kStageBytes, A.row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[st]);
+        bulk_g2s(ring + st * kStageBytes + kChunkBytes, B.row + (uint64_t)issued * kChunkBytes, kChunkBytes, &bars[st]);
+      }
+      ++issued; ++prod;
+    };
+    while (issued < n_chunks && issued < (uint32_t)kStages) issue(prod % kStages);
+    bool stop_a = false, stop_b = false;
+    for (; c < n_chunks && !stop_a && !stop_b; ++c) {
+      const uint32_t st = cons % kStages;
+      mbar_wait(&bars[st], (cons / kStages) & 1u);
+      ++cons;
+      uint4 va[kChunkRows], vb[kChunkRows];
+#pragma unroll
+      for (int r = 0; r < kChunkRows; ++r) {
+        va[r] = lds128(ring_s + st * kStageBytes + r * 512u + lane * 16u);
+        vb[r] = lds128(ring_s + st * kStageBytes + kChunkBytes + r * 512u + lane * 16u);
+      }
+      uint32_t ea = A.e, eb = B.e;
+      // a lane that has matched stays in the absorbing state whatever it reads: give it zeros, so that all matched
+      // lanes look up one and the same word (a broadcast) instead of spreading over the banks of the absorbing row
+      if (ea == sticky_e) {
+#pragma unroll
+        for (int r = 0; r < kChunkRows; ++r) va[r] = make_uint4(0, 0, 0, 0);
+      }
+      if (eb == sticky_e) {
+#pragma unroll
+        for (int r = 0; r < kChunkRows; ++r) vb[r] = make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      if (issued < n_chunks) issue(st);
+#pragma unroll
+      for (int r = 0; r < kChunkRows; ++r) {
+        const uint32_t wa[4] = {va[r].x, va[r].y, va[r].z, va[r].w}, wb[4] = {vb[r].x, vb[r].y, vb[r].z, vb[r].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ea = sticky_step(ea, __byte_perm(wa[j], 0, 0x4440)); eb = sticky_step(eb, __byte_perm(wb[j], 0, 0x4440));
+          ea = sticky_step(ea, __byte_perm(wa[j], 0, 0x4441)); eb = sticky_step(eb, __byte_perm(wb[j], 0, 0x4441));
+          ea = sticky_step(ea, __byte_perm(wa[j], 0, 0x4442)); eb = sticky_step(eb, __byte_perm(wb[j], 0, 0x4442));
+          ea = sticky_step(ea, __byte_perm(wa[j], 0, 0x4443)); eb = sticky_step(eb, __byte_perm(wb[j], 0, 0x4443));
         }
-        cur = nxt; row = next_row;
-        if (__ballot_sync(0xffffffffu, live && k + 1 < units && e != sticky_e) == 0) break;
       }
+      A.e = ea; B.e = eb;
+      stop_a = __ballot_sync(0xffffffffu, ea != sticky_e) == 0;
+      stop_b = __ballot_sync(0xffffffffu, eb != sticky_e) == 0;
     }
-    if (live) {
-      const uint32_t acc = endout[(e - trans_s) / stride2];
+    for (; cons < prod; ++cons) mbar_wait(&bars[cons % kStages], (cons / kStages) & 1u);
+    A.row += (uint64_t)c * kChunkBytes; B.row += (uint64_t)c * kChunkBytes;
+    A.k = stop_a ? A.maxu : c * kChunkRows;
+    B.k = stop_b ? B.maxu : c * kChunkRows;
+  };
+  // Ragged remainder of both groups (and groups with dead lanes), still two chains per lane: row k of a group holds
+  // only the lanes that have a unit k (lane count from a ballot), every lane steps through all 16 bytes and keeps
+  // the new state only for the bytes its record really has (nb), so there is no divergent branch between the chains.
+  auto ragged_pair = [&](Grp& A, Grp& B) {
+    const uint32_t rem_a = A.maxu - A.k, rem_b = B.maxu - B.k;       // k <= maxu always
+    const uint32_t rounds = rem_a > rem_b ? rem_a : rem_b;
+    if (!rounds) return;
+    const uint32_t units_a = (A.len + 15) >> 4, units_b = (B.len + 15) >> 4;
+    bool act_a = A.live && rem_a, act_b = B.live && rem_b;
+    const uint8_t* row_a = A.row; const uint8_t* row_b = B.row;
+    uint32_t ea = A.e, eb = B.e;
+    uint4 cur_a = make_uint4(0, 0, 0, 0), cur_b = cur_a;
+    if (act_a && A.k < units_a) cur_a = ldg_stream16(row_a + lane * 16);
+    if (act_b && B.k < units_b) cur_b = ldg_stream16(row_b + lane * 16);
+    for (uint32_t i = 0; i < rounds; ++i) {
+      const uint32_t ka = A.k + i, kb = B.k + i;
+      row_a += (uint64_t)__popc(__ballot_sync(0xffffffffu, ka < units_a)) * 16;
+      row_b += (uint64_t)__popc(__ballot_sync(0xffffffffu, kb < units_b)) * 16;
+      uint4 nxt_a = make_uint4(0, 0, 0, 0), nxt_b = nxt_a;
+      if (act_a && ka + 1 < units_a) nxt_a = ldg_stream16(row_a + lane * 16);
+      if (act_b && kb + 1 < units_b) nxt_b = ldg_stream16(row_b + lane * 16);
+      int nba = act_a ? (int)A.len - (int)(ka * 16) : 0, nbb = act_b ? (int)B.len - (int)(kb * 16) : 0;   // <= 0: no byte of this row
+      const uint32_t wa[4] = {cur_a.x, cur_a.y, cur_a.z, cur_a.w}, wb[4] = {cur_b.x, cur_b.y, cur_b.z, cur_b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t ta = sticky_step(ea, __byte_perm(wa[j], 0, 0x4440 + q)), tb = sticky_step(eb, __byte_perm(wb[j], 0, 0x4440 + q));
+          ea = 4 * j + q < nba ? ta : ea;
+          eb = 4 * j + q < nbb ? tb : eb;
+        }
+      }
+      cur_a = nxt_a; cur_b = nxt_b;
+      // a group is finished as soon as every live lane has either matched or ended
+      if (__ballot_sync(0xffffffffu, act_a && ka + 1 < units_a && ea != sticky_e) == 0) act_a = false;
+      if (__ballot_sync(0xffffffffu, act_b && kb + 1 < units_b && eb != sticky_e) == 0) act_b = false;
+      if (__ballot_sync(0xffffffffu, act_a || act_b) == 0) break;
+    }
+    A.e = ea; B.e = eb;
+  };
+  auto close_group = [&](const Grp& G) {
+    if (G.live) {
+      const uint32_t acc = endout[(G.e - trans_s) / stride2];
       uint32_t hit = 0;
       for (uint32_t q = 0; q < nq; ++q) {
-        if (!(alive >> q & 1)) continue;
+        if (!(G.alive >> q & 1)) continue;
         bool ok = true;
         for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
           const fei_prog_cond& cd = conds[c];
@@ -613,10 +702,26 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
         }
         if (ok) hit |= 1u << q;
       }
-      a.hits[rec] = hit;
-    } else if (rec != kInvalidRec && !a.has_alive) {
-      a.hits[rec] = 0;
+      a.hits[G.rec] = hit;
+    } else if (G.rec != kInvalidRec && !a.has_alive) {
+      a.hits[G.rec] = 0;
     }
+  };
+
+  for (;;) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(a.counter, 2ull);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= a.n_groups) break;
+    Grp A, B;
+    open_group(g, A);
+    open_group(g + 1, B);
+    stream_pair(A, B);
+    stream_single(A);
+    stream_single(B);
+    ragged_pair(A, B);
+    close_group(A);
+    close_group(B);
   }
   if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
 }
