@@ -304,7 +304,7 @@ struct BodyArgs {
   uint64_t n_groups;
   uint32_t* hits;              // in: alive masks (when has_alive), out: final hit masks
   int has_alive;
-  unsigned long long* counter; // [0] = next group, [1] = tile bytes touched
+  unsigned long long* counter; // [0] = next group, [1] = tile bytes of the groups entered, [3] = tile bytes requested
 };
 
 constexpr int kBodyThreads = 1024;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
   const uint32_t nq = ph->n_queries;
   const uint32_t all_q = nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1u);
   const int lane = threadIdx.x & 31;
-  unsigned long long touched = 0;
+  unsigned long long touched = 0, bytes_read = 0;
   BodyDfa<kDirect, kAcc> d;
   d.trans_s = smem_u32(smem);
   d.out = reinterpret_cast<const uint32_t*>(smem + (dd->off_out - dd->off_trans));
@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     const uint8_t* row = a.tiles + a.grp_base[g] * 16;
     const uint32_t maxu = __shfl_sync(0xffffffffu, units, 0);
     if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
+    const uint8_t* const row0 = row;
     d.reset(start);
     // software pipeline: the next row's 16 bytes are in flight while this row runs through the DFA
     uint4 cur = make_uint4(0, 0, 0, 0);
@@ -433,6 +434,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
       // sticky automaton: stop reading this group as soon as every live lane has either matched or ended
       if (kAcc == 3 && __ballot_sync(0xffffffffu, live && k + 1 < units && d.s != sticky_state) == 0) break;
     }
+    if (lane == 0) bytes_read += (unsigned long long)(row - row0);
     if (live) {
       const uint32_t acc = d.finish(endout);
       uint32_t hit = 0;
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
       a.hits[rec] = 0;
     }
   }
-  if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
+  if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
 
 // ---------------------------------------------------------------- single-pattern content scan, small automaton
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
   const uint32_t nq = ph->n_queries;
   const uint32_t all_q = nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1u);
   const int lane = threadIdx.x & 31;
-  unsigned long long touched = 0;
+  unsigned long long touched = 0, bytes_read = 0;
 
   // One group of 32 records as this warp sees it.
   struct Grp {
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
       stop = __ballot_sync(0xffffffffu, G.e != sticky_e) == 0;      // every lane has matched
     }
     for (; cons < prod; ++cons) mbar_wait(&bars[cons % kStages], (cons / kStages) & 1u);   // early stop: let the copies in flight land
+    bytes_read += (unsigned long long)issued * kChunkBytes;
     G.row += (uint64_t)c * kChunkBytes;
     G.k = stop ? G.maxu : G.k + c * kChunkRows;
   };
@@ -645,6 +648,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
       stop_b = __ballot_sync(0xffffffffu, eb != sticky_e) == 0;
     }
     for (; cons < prod; ++cons) mbar_wait(&bars[cons % kStages], (cons / kStages) & 1u);
+    bytes_read += 2ull * issued * kChunkBytes;
     A.row += (uint64_t)c * kChunkBytes; B.row += (uint64_t)c * kChunkBytes;
     A.k = stop_a ? A.maxu : c * kChunkRows;
     B.k = stop_b ? B.maxu : c * kChunkRows;
@@ -665,6 +669,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
     if (act_b && B.k < units_b) cur_b = ldg_stream16(row_b + lane * 16);
     for (uint32_t i = 0; i < rounds; ++i) {
       const uint32_t ka = A.k + i, kb = B.k + i;
+      bytes_read += __popc(__ballot_sync(0xffffffffu, act_a && ka < units_a)) * 16 + __popc(__ballot_sync(0xffffffffu, act_b && kb < units_b)) * 16;
       row_a += (uint64_t)__popc(__ballot_sync(0xffffffffu, ka < units_a)) * 16;
       row_b += (uint64_t)__popc(__ballot_sync(0xffffffffu, kb < units_b)) * 16;
       uint4 nxt_a = make_uint4(0, 0, 0, 0), nxt_b = nxt_a;
@@ -723,7 +728,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
     close_group(A);
     close_group(B);
   }
-  if (lane == 0 && touched) atomicAdd(a.counter + 1, touched);
+  if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
 
 template <bool kDirect, int kAcc>
@@ -944,9 +949,10 @@ static int finish_timing(fei_corpus* c, bool compacted) {
   if (compacted) { FEI_CUDA(cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); c->timing.compact_ms = t; }
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[compacted ? 4 : 3], c->ev[5])); c->timing.d2h_ms = t;
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5])); c->timing.total_ms = t;
-  unsigned long long touched = 0;
-  FEI_CUDA(cudaMemcpy(&touched, c->work_counter.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost));
-  c->timing.body_bytes_touched = touched;
+  unsigned long long cnt[4] = {0, 0, 0, 0};
+  FEI_CUDA(cudaMemcpy(cnt, c->work_counter.as<unsigned long long>(), sizeof(cnt), cudaMemcpyDeviceToHost));
+  c->timing.body_bytes_touched = cnt[1];
+  c->timing.body_bytes_read = cnt[3];
   return FEI_OK;
 }
 
