@@ -110,7 +110,7 @@ def test_multi_field_filter_cfg2(corpus3k):
     c, arrays, mems = corpus3k
     import datetime
     median_ts = int(np.median(arrays["ts"]))
-    t = datetime.datetime.utcfromtimestamp(median_ts).strftime("%Y-%m-%d %H:%M:%S")
+    t = datetime.datetime.fromtimestamp(median_ts, datetime.timezone.utc).strftime("%Y-%m-%d %H:%M:%S")
     cases = [
         [("Tags", "has_tag", "python"), ("flags", "has_flag", "F"), ("date", ">", t), ("content", "matches", r"react|angular")],
         [("Tags", "has_tag", "python")],
@@ -417,3 +417,66 @@ def test_full_size_corpus_sampled_windows_and_invariants(gpu):
             want = mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}])
             got = np.nonzero((masks[first:first + k] >> np.uint32(q)) & np.uint32(1))[0].tolist()
             assert got == want, (first, p)
+
+
+def test_single_pattern_kernel_shapes(gpu):
+    """k_body_sticky's code paths: full rows through the TMA ring (pairs of groups, then one group), the joint ragged tail,
+    early stop of one / both groups, window boundary (4096), needles at row and chunk edges, NUL bytes and bytes whose
+    stored form differs (the tile byte substitution), empty bodies."""
+    from fei_b200.corpus import Corpus
+    rng = np.random.default_rng(20260921)
+    words = [b"alpha", b"Beta", b"GAMMA", b"delta", b" ", b"\n", b"_", b"@", b"`", b"{", b"\x00", "é".encode(), "Ω".encode(), b"1234", b"~"]
+
+    def filler(n):
+        out = bytearray()
+        while len(out) < n:
+            out += words[int(rng.integers(len(words)))]
+        return bytes(out[:n]).decode("utf-8", "ignore").encode()     # keep it valid UTF-8 after the cut
+
+    recs = []
+    n = 4096 + 70                                                     # second window: 70 records, 3 groups, padded lanes
+    for i in range(n):
+        r = synth.record(11, i)
+        kind = i % 8
+        if kind == 0:
+            ln = 1024                                                 # equal lengths, multiples of 16: no ragged rows at all
+        elif kind == 1:
+            ln = 0
+        elif kind == 2:
+            ln = int(rng.integers(1, 48))                             # shorter than one chunk: tail loop only
+        else:
+            ln = int(rng.integers(900, 1400))
+        body = bytearray(filler(ln))
+        ln = len(body)
+        where = i % 11
+        needle = b"NeEdLe"
+        pos = None
+        if ln >= 16 and where < 8:                                    # 3 of 11 records carry no needle
+            pos = [0, ln - len(needle), 10, 16 - 3, 512 - 2, 1024 - 6 if ln >= 1024 else ln // 2, ln // 2, ln // 3][where]
+            pos = max(0, min(pos, ln - len(needle)))
+            body[pos:pos + len(needle)] = needle
+        try:
+            body.decode("utf-8")
+        except UnicodeDecodeError:                                    # the needle cut a multi-byte character: repair the neighbours
+            body = bytearray(bytes(body).decode("utf-8", "replace").replace("�", "?").encode())
+        if body and body[:1] in (b" ", b"\n"):                        # bodies are stored stripped (utils.py:120)
+            body[0:1] = b"x"
+        if body and body[-1:] in (b" ", b"\n"):
+            body[-1:] = b"x"
+        r["body"] = bytes(body)
+        recs.append(r)
+    # one group where every record matches in its first row (both groups of a pair stop at once)
+    for i in range(64):
+        recs[2048 + i]["body"] = b"needle " + filler(1100).rstrip() + b"."
+    a = synth.arrays_from_records(recs)
+    c = Corpus().load(a)
+    mems = memories_of(recs)
+    got = c.fetch(0, n)
+    assert bytes(got["body"][:int(a["body_off"][-1])]) == bytes(a["body"][:int(a["body_off"][-1])])
+    for p in ["needle", r"^needle", r"needle\Z", r"alpha.*needle|needle.*delta", "absent-everywhere", r"\x00", "é", r"[`{@~_]needle", "(?s).", r"\Aalpha"]:
+        pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", p, re.IGNORECASE))])
+        want = mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}])
+        assert c.scan_hits(pb.build(), 1)[0].tolist() == want, p
+    pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "NeEdLe", 0))])      # case-sensitive: upper/lower columns differ
+    want = [i for i, m in enumerate(mems) if re.search("NeEdLe", m["content"])]
+    assert c.scan_hits(pb.build(), 1)[0].tolist() == want
