@@ -239,6 +239,7 @@ extern "C" int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h) {
   FEI_TRY(upload(body_off, boff, (n + 1) * 8, 0, s));
   FEI_CUDA(cudaEventRecord(c->ev[1], s));
   FEI_TRY(build_tiles(c, body.as<uint8_t>(), body_off.as<uint64_t>(), s));
+  FEI_TRY(build_header_dir(c, s));
   // the canonical body is only a staging area: keep it for the next batch when it is small (streaming
   // loads of host batches), drop it for big resident corpora so HBM holds one copy of the text
   if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); }
@@ -278,6 +279,7 @@ extern "C" int fei_corpus_synth(fei_corpus* c, uint64_t seed, uint64_t first, ui
                                          c->ts.as<int64_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>());
   FEI_CUDA(cudaGetLastError());
   FEI_TRY(build_tiles(c, body.as<uint8_t>(), body_off.as<uint64_t>(), s));
+  FEI_TRY(build_header_dir(c, s));
   c->loaded = true;
   return FEI_OK;
 }

@@ -44,6 +44,8 @@ struct fei_corpus {
   bool loaded = false;
   fei::DevBuf hdr, hdr_off, name, name_off, name_spans, ts, wall, flags8, fsb;
   fei::DevBuf tiles, grp_base, grp_rec, grp_len, rec_pos;
+  fei::DevBuf hdir, hdir_off;            // header directory (hdir.cu): uint2 entries, u64 offsets [n+1]
+  uint64_t hdir_entries = 0;
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
   // scan scratch (grown on demand, reused across scans)
   fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors;
@@ -58,6 +60,8 @@ struct fei_corpus {
 namespace fei {
 // builds tiles from a canonical body blob already on the device (body has >= 32 bytes of slack)
 int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off, cudaStream_t s);
+// builds the header directory from hdr / hdr_off already on the device (hdir.cu)
+int build_header_dir(fei_corpus* c, cudaStream_t s);
 int exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, DevBuf& tmp, cudaStream_t s);
 int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t global_base, CompactScratch& sc,
                   uint64_t* counts_out, DevBuf* lists, uint64_t* stride_out, uint32_t* launches, cudaStream_t s);

@@ -182,6 +182,7 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
     if (ms[i].body_len > (32u << 20)) { set_error("record %llu: body larger than 32 MiB is not supported", (unsigned long long)i); return FEI_E_UNSUPPORTED; }
   FEI_CUDA(cudaGetLastError());
   FEI_TRY(build_tiles(c, body.as<uint8_t>(), body_off.as<uint64_t>(), s));
+  FEI_TRY(build_header_dir(c, s));
   if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); }
   c->loaded = true;
   return FEI_OK;

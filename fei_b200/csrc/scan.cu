@@ -70,6 +70,7 @@ struct HeadArgs {
   const int64_t* wall; const uint64_t* flags8; const uint32_t* fsb;
   uint64_t n;
   uint32_t* alive;
+  const uint2* hdir; const uint64_t* hdir_off;     // header directory (hdir.cu)
 };
 
 constexpr int kHeadThreads = 256;
@@ -112,6 +113,35 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
     uint32_t have_first = 0;
     DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
     const uint8_t* h = hptr;
+    const uint2* ent = a.hdir + a.hdir_off[rec];
+    const uint32_t n_ent = (uint32_t)(a.hdir_off[rec + 1] - a.hdir_off[rec]);
+    if (!(n_ent == 1 && ent[0].x == 0xFFFFFFFFu)) {
+      // the usual case: walk the record's header directory (one entry per line with a colon, spans already stripped)
+      uint32_t val_span[FEI_MAX_SLOTS];
+      for (uint32_t j = 0; j < n_ent; ++j) {
+        const uint2 e = ent[j];
+        const uint8_t* ka = h + (e.x & 0xFFFFu); const uint32_t klen = e.x >> 16;
+        uint32_t km = dfa_run(keyd, ka, klen);
+        while (km) {
+          int s = __ffs(km) - 1; km &= km - 1;
+          if (slots[s].mode == 0) {                            // first key that lower()-equals the field (search.py:121-122)
+            if (!(have_first >> s & 1)) { have_first |= 1u << s; first_off[s] = e.x & 0xFFFFu; first_len[s] = klen; }
+            else {
+              bool same = first_len[s] == klen;
+              for (uint32_t k = 0; same && k < klen; ++k) same = h[first_off[s] + k] == ka[k];
+              if (!same) continue;                             // a different spelling of the key: not the dict entry we read
+            }
+          }
+          val_span[s] = e.y;                                   // repeated key: last value wins (dict assignment)
+          present |= 1u << s;
+        }
+      }
+      for (uint32_t m = present; m;) {
+        int s = __ffs(m) - 1; m &= m - 1;
+        slot_acc[s] = dfa_run(dfa_view(a.prog, slots[s].off_val_dfa), h + (val_span[s] & 0xFFFFu), val_span[s] >> 16);
+      }
+    } else {
+    // header text longer than a directory span can address: split / strip it here
     const uint8_t* hend = hptr + hlen;
     const uint8_t* p = h;
     while (p < hend) {
@@ -137,6 +167,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
         }
       }
       p = eol + 1;
+    }
     }
   }
   for (uint32_t s = 0; s < nslots; ++s)
@@ -246,21 +277,75 @@ __global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
 // text is never read.
 struct Survivor { uint32_t rec, pre, flags_acc; };
 
+constexpr int kMetaPer = 4;     // records per thread: the (uniform) condition fetch / decode is paid once for four records
+
 __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restrict__ list, unsigned int* __restrict__ count) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
-  uint32_t flags_acc = 0, pre = 0;
-  const bool valid = i < a.n;
-  if (valid) pre = head_meta(a, i, flags_acc);
-  const bool later = valid && (pre & (ph->slot_mask | ph->name_mask)) != 0;
-  if (valid && !later) a.alive[i] = pre;                       // no header / name condition left: pre is the verdict
-  const uint32_t bal = __ballot_sync(0xffffffffu, later);
-  if (bal) {
-    const int lane = threadIdx.x & 31;
-    unsigned int base = 0;
-    if (lane == __ffs(bal) - 1) base = atomicAdd(count, (unsigned int)__popc(bal));   // one atomic per warp
-    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-    if (later) list[base + __popc(bal & ((1u << lane) - 1u))] = Survivor{(uint32_t)i, pre, flags_acc};
+  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
+  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
+  const uint64_t base = blockIdx.x * (uint64_t)(256 * kMetaPer) + threadIdx.x;
+  uint32_t fsb[kMetaPer], flags_acc[kMetaPer], pre[kMetaPer];
+  int64_t wall[kMetaPer];
+  uint64_t f8[kMetaPer];
+  bool valid[kMetaPer];
+#pragma unroll
+  for (int r = 0; r < kMetaPer; ++r) {
+    const uint64_t i = base + (uint64_t)r * 256;
+    valid[r] = i < a.n;
+    fsb[r] = valid[r] ? a.fsb[i] : 0u; wall[r] = valid[r] ? a.wall[i] : 0; f8[r] = valid[r] ? a.flags8[i] : 0ull;
+    flags_acc[r] = 0; pre[r] = 0;
+  }
+  if (ph->off_flags_dfa) {                                     // flags string (search.py:105-106): up to 7 letters in flags8
+    const DfaView fd = dfa_view(a.prog, ph->off_flags_dfa);
+#pragma unroll
+    for (int r = 0; r < kMetaPer; ++r) {
+      uint8_t fb[8];
+      for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f8[r] >> (8 * k));
+      flags_acc[r] = dfa_run(fd, fb, (uint32_t)(f8[r] >> 56));
+    }
+  }
+  for (uint32_t q = 0; q < ph->n_queries; ++q) {
+    bool ok[kMetaPer];
+#pragma unroll
+    for (int r = 0; r < kMetaPer; ++r) ok[r] = true;
+    for (uint32_t c = queries[q].cond_begin; c < queries[q].cond_end; ++c) {
+      const fei_prog_cond cd = conds[c];
+      if (cd.kind == FEI_C_SLOT && cd.if_missing == 2) { ++c; continue; }     // header-or-fallback pair: decided in phase 2
+#pragma unroll
+      for (int r = 0; r < kMetaPer; ++r) ok[r] = ok[r] && eval_meta_cond(cd, flags_acc[r], wall[r], fsb[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kMetaPer; ++r) if (ok[r]) pre[r] |= 1u << q;
+  }
+  const uint32_t later_mask = ph->slot_mask | ph->name_mask;
+  const int lane = threadIdx.x & 31;
+  // survivors: slots are reserved per warp in shared memory and per CTA with ONE global atomic (a global atomic per
+  // warp put 260 k same-address atomics on the L2 for 10 M records: 130 us, more than streaming the columns)
+  __shared__ unsigned int cta_count, cta_base;
+  if (threadIdx.x == 0) cta_count = 0;
+  __syncthreads();
+  bool later[kMetaPer];
+  uint32_t bal[kMetaPer];
+  unsigned int warp_total = 0;
+#pragma unroll
+  for (int r = 0; r < kMetaPer; ++r) {
+    const uint64_t i = base + (uint64_t)r * 256;
+    later[r] = valid[r] && (pre[r] & later_mask) != 0;
+    if (valid[r] && !later[r]) a.alive[i] = pre[r];            // no header / name condition left: pre is the verdict
+    bal[r] = __ballot_sync(0xffffffffu, later[r]);
+    warp_total += __popc(bal[r]);
+  }
+  unsigned int warp_base = 0;
+  if (lane == 0 && warp_total) warp_base = atomicAdd(&cta_count, warp_total);
+  warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+  __syncthreads();
+  if (threadIdx.x == 0 && cta_count) cta_base = atomicAdd(count, cta_count);
+  __syncthreads();
+  unsigned int slot = cta_base + warp_base;
+#pragma unroll
+  for (int r = 0; r < kMetaPer; ++r) {
+    if (later[r]) list[slot + __popc(bal[r] & ((1u << lane) - 1u))] = Survivor{(uint32_t)(base + (uint64_t)r * 256), pre[r], flags_acc[r]};
+    slot += __popc(bal[r]);
   }
 }
 
@@ -884,11 +969,12 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   uint32_t launches = 0;
   if (n && need_head) {
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
-               c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>()};
+               c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>(),
+               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>()};
     // selective meta predicates first: stream the meta columns, collect survivors
     FEI_TRY(c->survivors.ensure((n + 32) * sizeof(Survivor)));
     unsigned int* d_count = reinterpret_cast<unsigned int*>(c->work_counter.as<unsigned long long>() + 2);
-    k_head_meta<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
+    k_head_meta<<<(unsigned)((n + 256 * kMetaPer - 1) / (256 * kMetaPer)), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
     ++launches;
     unsigned int n_surv = 0;
     FEI_CUDA(cudaMemcpyAsync(&n_surv, d_count, sizeof(n_surv), cudaMemcpyDeviceToHost, s));

@@ -162,6 +162,10 @@ def test_adversarial_records_header_parser_and_unicode(gpu):
         hdr_text, sep, rest = text.partition("---")
         r["hdr"] = hdr_text.encode(); r["body"] = rest.strip().encode(); r["raw_text"] = text
         recs.append(r)
+    # a header text longer than 65535 bytes: the header directory (hdir.cu) defers to the in-scan text parser
+    big = "Filler: " + "x" * 70000 + "\nTags: python , huge\nsubject:  Big One \nTags: final,python\nKey:\n"
+    r = synth.record(11, 98); r["hdr"] = big.encode(); r["body"] = b"big header body"; r["raw_text"] = big + "---\nbig header body"
+    recs.append(r)
     # plus one record with no separator at all
     r = synth.record(11, 99); r["hdr"] = b""; r["body"] = "just text: no separator python".encode(); r["raw_text"] = "just text: no separator python"
     r["bits"] = 1
@@ -176,6 +180,7 @@ def test_adversarial_records_header_parser_and_unicode(gpu):
         [("content", "matches", r"caf. r.sum. \S dragon$")], [("content", "matches", r"(?m)^line2")], [("content", "matches", "^$")],
         [("Subject", "contains", "résumé")], [("Subject", "matches", "RÉSUMÉ$")], [("content", "matches", r"docker.*kubernetes")],
         [("Priority", "=", "high")], [("nokey", "=", "")], [("", "contains", "emptykey")],
+        [("Tags", "has_tag", "huge")], [("Subject", "=", "big one")], [("Filler", "startswith", "xxx")], [("filler", "endswith", "xx")],
     ]
     for conds in cases:
         pb = ProgramBuilder(); pb.add_query(_search_prog(conds))
