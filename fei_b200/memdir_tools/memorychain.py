@@ -18,7 +18,7 @@ from __future__ import annotations
 import ctypes as C
 import logging
 import threading
-from operator import attrgetter
+from operator import attrgetter, itemgetter
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -121,23 +121,65 @@ def _column(vals: Sequence[Any], what: str) -> _Col:
 _get_direct = attrgetter("index", "nonce", "previous_hash", "proposer_node", "responsible_node", "timestamp", "memory_data", "hash")
 
 
+_EMPTY: Dict[str, Any] = {}
+
+
 def _memory_id(md: Any) -> Any:
     # self.memory_data.get("metadata", {}).get("unique_id", "")   (reference :120)
     return md.get("metadata", {}).get("unique_id", "")
 
 
+_DIRECT = ("index", "nonce", "previous_hash", "proposer_node", "responsible_node", "timestamp", "memory_data")
+_OPTIONAL = ("task_state", "difficulty", "solver_node")
+_get_dict = attrgetter("__dict__")
+
+
+def _extract(blocks: Sequence[Any]) -> Optional[List[tuple]]:
+    """Fast attribute extraction: when every block is a plain instance of one class whose hashed fields are ordinary
+    instance attributes, read them straight out of the instance dicts (C speed, no descriptor protocol).
+    Returns 11 tuples (7 direct, hash, 3 optional) or None when the generic getattr path must be used."""
+    kinds = set(map(type, blocks))
+    if len(kinds) != 1:
+        return None
+    cls = kinds.pop()
+    hash_key = "hash"
+    if isinstance(getattr(cls, "hash", None), property):
+        if cls is not MemoryBlock:
+            return None
+        hash_key = "_hash"                       # our lazy-hash block keeps the value there (None until first use)
+    elif hasattr(cls, "hash"):
+        return None
+    if any(hasattr(cls, k) for k in _DIRECT + _OPTIONAL) or hasattr(cls, "__getattr__"):
+        return None                              # class-level attributes / descriptors / dynamic lookup: use getattr
+    try:
+        rows = list(map(itemgetter(*_DIRECT, hash_key, *_OPTIONAL), map(_get_dict, blocks)))
+    except (AttributeError, KeyError):           # __slots__ classes, blocks without task fields (getattr(..., None))
+        return None
+    cols = list(zip(*rows))
+    if hash_key == "_hash" and None in cols[7]:
+        cols[7] = tuple(b.hash if h is None else h for b, h in zip(blocks, cols[7]))
+    return cols
+
+
 def chain_columns(blocks: Sequence[Any]) -> Tuple[List[_Col], List[Any]]:
     """Ten hashed columns (sorted key order) + the stored ``hash`` attributes."""
-    rows = list(map(_get_direct, blocks))
-    if rows:
-        index, nonce, prev, proposer, responsible, timestamp, mdata, stored = map(list, zip(*rows))
+    fast = _extract(blocks) if blocks else None
+    if fast is not None:
+        index, nonce, prev, proposer, responsible, timestamp, mdata, stored, task_state, difficulty, solver = fast
     else:
-        index = nonce = prev = proposer = responsible = timestamp = mdata = stored = []
-    memory_id = list(map(_memory_id, mdata))
-    # getattr(self, "task_state", None) etc. (reference :124-126)
-    task_state = [getattr(b, "task_state", None) for b in blocks]
-    difficulty = [getattr(b, "difficulty", None) for b in blocks]
-    solver = [getattr(b, "solver_node", None) for b in blocks]
+        rows = list(map(_get_direct, blocks))
+        if rows:
+            index, nonce, prev, proposer, responsible, timestamp, mdata, stored = map(list, zip(*rows))
+        else:
+            index = nonce = prev = proposer = responsible = timestamp = mdata = stored = []
+        # getattr(self, "task_state", None) etc. (reference :124-126)
+        task_state = [getattr(b, "task_state", None) for b in blocks]
+        difficulty = [getattr(b, "difficulty", None) for b in blocks]
+        solver = [getattr(b, "solver_node", None) for b in blocks]
+    try:                                         # self.memory_data.get("metadata", {}).get("unique_id", "")   (reference :120)
+        memory_id = [md.get("metadata", _EMPTY).get("unique_id", "") for md in mdata]
+    except AttributeError:
+        memory_id = list(map(_memory_id, mdata))
     by_name = {"difficulty": difficulty, "index": index, "memory_id": memory_id, "nonce": nonce,
                "previous_hash": prev, "proposer_node": proposer, "responsible_node": responsible,
                "solver_node": solver, "task_state": task_state, "timestamp": timestamp}
