@@ -42,6 +42,14 @@ BATCH32 = ["python", "docker|kubernetes", "neural networks", "react", "angular",
 METRIC = "memories_per_sec_scanned"
 
 
+def measured_peak_field(key, default):
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get(key, default)
+    except Exception:
+        return default
+
+
 def measured_peak():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -478,6 +486,9 @@ def run_extra(args, corpus, st, peak, lib, _abi):
         ms.append(kms.value)
     t = float(np.mean(ms)) * 1e-3
     nb = args.chain_blocks
+    info = _abi.device_info() if hasattr(_abi, "device_info") else {}
+    sm_mhz_max = float(measured_peak_field("sm_max_mhz", 1965.0))
+    alu_peak = float(info.get("sm_count", 148)) * 64 * sm_mhz_max * 1e6
     cpu_rate, cpu_dt = cpu_chain_rate(min(nb, 50_000))
     out["cfg4_validate_chain"] = {
         "metric": "sha256_chain_blocks_per_sec", "value": (nb - 1) / t, "unit": "chain blocks/s", "blocks": nb, "kernel_ms": t * 1e3,
@@ -485,6 +496,12 @@ def run_extra(args, corpus, st, peak, lib, _abi):
         "roofline": {"bound": "int32-issue (not HBM)", "achieved": 493.0 * (nb - 1) / t / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": 493.0 * (nb - 1) / t / 1e9 / peak, "bytes_per_block": 493,
                      "note": "SHA-256 is integer-ALU bound: ~13k 32-bit ops per chain block (6 compressions); HBM fraction is expected to be low"},
+        # the bound that applies: ALU-pipe issue (IADD3 / LOP3 / SHF / PRMT run at 64 lanes per clock per SM).  1300 = ALU-pipe
+        # instructions per compression in the kernel's SASS (profiles/r1_sass_evidence.txt); ncu reports the pipe 95 % busy.
+        "roofline_alu": {"bound": "int32 ALU pipe", "achieved": (nb - 1) * 6 * 1300 / t / 1e12, "unit": "T lane-ops/s",
+                         "peak": alu_peak / 1e12, "frac": (nb - 1) * 6 * 1300 / t / alu_peak,
+                         "peak_source": "sm_count x 64 lanes x %.0f MHz (max SM clock)" % sm_mhz_max,
+                         "alu_instr_per_compression": 1300, "ncu": "profiles/r1e_k_sha256_validate_1M.txt"},
         "cpu_baseline": {"value": cpu_rate, "unit": "chain blocks/s", "cores": 1, "kind": "port",
                          "sample": f"validate_chain oracle (json.dumps + hashlib, memorychain.py:596-618) over {min(nb, 50_000)} blocks, {cpu_dt:.2f} s"},
     }
