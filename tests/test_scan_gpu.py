@@ -360,6 +360,15 @@ def test_random_headers_differential(gpu):
         want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
         got = np.nonzero(masks >> np.uint32(q) & np.uint32(1))[0].tolist()
         assert got == want, conds
+    # the same corpus with the header directory switched off (FEI_HDIR=0 at load: every record takes the in-scan text
+    # parser that otherwise only > 64 KiB headers reach): both header paths must give the same masks
+    import os
+    os.environ["FEI_HDIR"] = "0"
+    try:
+        c_text = Corpus().load(synth.arrays_from_records(recs))
+    finally:
+        del os.environ["FEI_HDIR"]
+    assert np.array_equal(c_text.scan_masks(pb.build()), masks)
 
 
 def _search_prog2(conds):
