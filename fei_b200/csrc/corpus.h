@@ -29,6 +29,7 @@ namespace fei {
 __host__ __device__ __forceinline__ uint32_t tile_byte_perm4(uint32_t w) { return w ^ ((w >> 1) & 0x20202020u); }
 #endif
 constexpr int kWindow = 4096;
+constexpr uint32_t kKeySlots = 4096;       // header-key dictionary slots (hdir.cu); at most half may fill
 constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
 }
 
@@ -45,6 +46,7 @@ struct fei_corpus {
   fei::DevBuf hdr, hdr_off, name, name_off, name_spans, ts, wall, flags8, fsb;
   fei::DevBuf tiles, grp_base, grp_rec, grp_len, rec_pos;
   fei::DevBuf hdir, hdir_off;            // header directory (hdir.cu): uint2 entries, u64 offsets [n+1]
+  fei::DevBuf key_tag, key_rep, key_len, key_lut;   // dictionary of the corpus' distinct header keys + per-scan key -> slot-mask table
   uint64_t hdir_entries = 0;
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
   // scan scratch (grown on demand, reused across scans)

@@ -6,11 +6,14 @@
 //   FilterManager.process_memories -> MemoryFilter.matches      (memdir_tools/filter.py:229-233, :67-109)
 //   parse_memory_content header parsing                          (memdir_tools/utils.py:113-118)
 //
-// k_head : one thread per record.  Meta predicates (flags / date / folder / status), then the
-//          header text is parsed on the device exactly like the reference: lines split on '\n',
-//          first ':' splits key and value, both .strip()ped with Python's whitespace set,
-//          dict semantics (a repeated key keeps its last value), case-insensitive field lookup
-//          takes the first matching key.  Every string condition is an output bit of a byte DFA.
+// k_head_meta / k_head_parse : meta predicates (flags / date / folder / status) over the 20-byte meta columns, four
+//          records per thread; records that still need a header or name field go to a work list and get one thread
+//          each in k_head_parse, which reads the record's header directory (hdir.cu: interned key + stripped value
+//          span per header line; k_key_lut maps the corpus' distinct keys to the program's fields once per scan)
+//          and applies the reference's dict semantics (a repeated key keeps its last value, a case-insensitive
+//          field lookup takes the first matching spelling).  Headers the directory cannot address are split / stripped
+//          here exactly like utils.py:113-118.  Every string condition is an output bit of a byte DFA; the program
+//          head (conditions + small automata) is staged into shared memory by a TMA bulk copy per CTA.
 //          Writes alive[i] = bitmask of queries whose non-content conditions all hold.
 // k_body : one warp per group of 32 records in the warp-transposed body tiles (corpus.h): each
 //          row is one contiguous coalesced request (ld.global.nc 16 B per lane); each lane walks
@@ -47,19 +50,20 @@ __device__ __forceinline__ DfaView dfa_view(const uint8_t* blob, uint32_t off) {
   return v;
 }
 
-// generic (global-memory tables) run over a byte span; used by the head kernel on short fields
+// generic run over a byte span (tables in global memory or, for the head kernels, in the shared-memory copy of the
+// program head: plain loads, the address space is resolved at run time); used on short fields
 __device__ uint32_t dfa_run(const DfaView& d, const uint8_t* p, uint32_t len) {
   if (len == 0) return d.empty_acc;
   uint32_t s = d.start;
-  uint32_t acc = s < d.n_acc ? __ldg(d.out + s) : 0u;
+  uint32_t acc = s < d.n_acc ? d.out[s] : 0u;
   const bool direct = d.n_cols == 256;
   for (uint32_t i = 0; i < len; ++i) {
     uint32_t b = p[i];
-    uint32_t col = direct ? b : __ldg(d.cls + b);
-    s = __ldg(d.trans + s * d.stride + col);
-    if (s < d.n_acc) acc |= __ldg(d.out + s);
+    uint32_t col = direct ? b : d.cls[b];
+    s = d.trans[s * d.stride + col];
+    if (s < d.n_acc) acc |= d.out[s];
   }
-  return acc | __ldg(d.endout + s);
+  return acc | d.endout[s];
 }
 
 // ---------------------------------------------------------------- head kernel
@@ -71,10 +75,10 @@ struct HeadArgs {
   uint64_t n;
   uint32_t* alive;
   const uint2* hdir; const uint64_t* hdir_off;     // header directory (hdir.cu)
+  const uint32_t* key_lut;                         // dictionary slot of a header key -> mask of the program's slots it names (k_key_lut)
 };
 
 constexpr int kHeadThreads = 256;
-constexpr uint32_t kHeadStageBytes = 56 * 1024;    // shared-memory window for one CTA's contiguous header span
 
 __device__ __forceinline__ bool eval_meta_cond(const fei_prog_cond& cd, uint32_t flags_acc, int64_t wall, uint32_t fsb) {
   switch (cd.kind) {
@@ -116,29 +120,25 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
     const uint2* ent = a.hdir + a.hdir_off[rec];
     const uint32_t n_ent = (uint32_t)(a.hdir_off[rec + 1] - a.hdir_off[rec]);
     if (!(n_ent == 1 && ent[0].x == 0xFFFFFFFFu)) {
-      // the usual case: walk the record's header directory (one entry per line with a colon, spans already stripped)
-      uint32_t val_span[FEI_MAX_SLOTS];
+      // the usual case: walk the record's header directory (one entry per line with a colon: interned key, stripped value span)
+      uint32_t first_key[FEI_MAX_SLOTS], val_off[FEI_MAX_SLOTS], val_len[FEI_MAX_SLOTS];
       for (uint32_t j = 0; j < n_ent; ++j) {
         const uint2 e = ent[j];
-        const uint8_t* ka = h + (e.x & 0xFFFFu); const uint32_t klen = e.x >> 16;
-        uint32_t km = dfa_run(keyd, ka, klen);
+        const uint32_t kid = e.x & 0xFFFFu;
+        uint32_t km = a.key_lut[kid];
         while (km) {
           int s = __ffs(km) - 1; km &= km - 1;
           if (slots[s].mode == 0) {                            // first key that lower()-equals the field (search.py:121-122)
-            if (!(have_first >> s & 1)) { have_first |= 1u << s; first_off[s] = e.x & 0xFFFFu; first_len[s] = klen; }
-            else {
-              bool same = first_len[s] == klen;
-              for (uint32_t k = 0; same && k < klen; ++k) same = h[first_off[s] + k] == ka[k];
-              if (!same) continue;                             // a different spelling of the key: not the dict entry we read
-            }
+            if (!(have_first >> s & 1)) { have_first |= 1u << s; first_key[s] = kid; }
+            else if (first_key[s] != kid) continue;            // a different spelling of the key: not the dict entry we read
           }
-          val_span[s] = e.y;                                   // repeated key: last value wins (dict assignment)
+          val_off[s] = e.y; val_len[s] = e.x >> 16;            // repeated key: last value wins (dict assignment)
           present |= 1u << s;
         }
       }
       for (uint32_t m = present; m;) {
         int s = __ffs(m) - 1; m &= m - 1;
-        slot_acc[s] = dfa_run(dfa_view(a.prog, slots[s].off_val_dfa), h + (val_span[s] & 0xFFFFu), val_span[s] >> 16);
+        slot_acc[s] = dfa_run(dfa_view(a.prog, slots[s].off_val_dfa), h + val_off[s], val_len[s]);
       }
     } else {
     // header text longer than a directory span can address: split / strip it here
@@ -237,49 +237,40 @@ __device__ __forceinline__ uint32_t head_meta(const HeadArgs& a, uint64_t i, uin
   return pre;
 }
 
-// Dense variant (many records survive the meta predicates): one CTA = 256 consecutive records whose
-// contiguous header span is staged into shared memory by a single TMA bulk copy; every thread then
-// parses its own record from shared memory.
-__global__ void __launch_bounds__(kHeadThreads) k_head(HeadArgs a) {
-  extern __shared__ __align__(128) uint8_t stage[];
-  __shared__ uint64_t bar;
-  const uint64_t i0 = blockIdx.x * (uint64_t)kHeadThreads;
-  const uint64_t i = i0 + threadIdx.x;
-  const bool valid = i < a.n;
-  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
-  uint32_t flags_acc = 0, pre = 0;
-  if (valid) pre = head_meta(a, i, flags_acc);
-  const bool need_hdr = ph->n_slots && (pre & ph->slot_mask);
-  bool staged = false;
-  uint64_t lo = 0;
-  if (__syncthreads_or(need_hdr)) {
-    const uint64_t last = i0 + kHeadThreads < a.n ? i0 + kHeadThreads : a.n;
-    lo = a.hdr_off[i0] & ~15ull;
-    const uint64_t bytes = (a.hdr_off[last] - lo + 15) & ~15ull;
-    staged = bytes && bytes <= kHeadStageBytes;
-    if (staged) {
-      if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-      __syncthreads();
-      if (threadIdx.x == 0) { mbar_expect_tx(&bar, (uint32_t)bytes); bulk_g2s(stage, a.hdr + lo, (uint32_t)bytes, &bar); }
-      mbar_wait(&bar, 0);
-    }
-  }
-  if (!valid) return;
-  if (pre == 0) { a.alive[i] = 0; return; }
-  const uint64_t off = a.hdr_off[i];
-  head_finish(a, i, pre, flags_acc, staged ? stage + (off - lo) : a.hdr + off, (uint32_t)(a.hdr_off[i + 1] - off), need_hdr);
+// Per scan: run the key automaton over the corpus' distinct header keys (hdir.cu), one thread per dictionary slot.
+__global__ void k_key_lut(const uint8_t* __restrict__ prog, const uint8_t* __restrict__ hdr, const unsigned long long* __restrict__ tag,
+                          const unsigned long long* __restrict__ rep, const uint32_t* __restrict__ len, uint32_t* __restrict__ lut) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= kKeySlots) return;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(prog);
+  lut[s] = tag[s] ? dfa_run(dfa_view(prog, ph->off_key_dfa), hdr + rep[s], len[s]) : 0u;
 }
 
-// Sparse variant, used when the meta predicates are selective: k_head_meta streams the 20-byte meta
-// columns, finalises every record that needs no header text and appends the few survivors to a work
-// list; k_head_parse then gives each survivor its own thread at full occupancy (a survivor's serial
-// header parse no longer pins a CTA full of already-finished threads), and the dead records' header
-// text is never read.
+// Every CTA of the head kernels first copies the "head" of the program (header, conditions, queries, slots and all
+// automata except the big content one: fei_prog_hdr.head_bytes, a few KB) into shared memory with one TMA bulk copy,
+// so that the interpretive condition loops and the short automaton runs read LDS instead of chasing global pointers.
+constexpr uint32_t kHeadProgSmem = 32 * 1024;
+__device__ __forceinline__ const uint8_t* stage_prog_head(const uint8_t* gprog, uint8_t* sprog, uint64_t* bar) {
+  const uint32_t head_bytes = reinterpret_cast<const fei_prog_hdr*>(gprog)->head_bytes;
+  if (head_bytes == 0 || head_bytes > kHeadProgSmem) return gprog;           // uniform for the whole grid
+  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x == 0) { mbar_expect_tx(bar, head_bytes); bulk_g2s(sprog, gprog, head_bytes, bar); }
+  mbar_wait(bar, 0);
+  return sprog;
+}
+
+// k_head_meta streams the 20-byte meta columns, finalises every record that needs no header text and appends
+// the others to a work list; k_head_parse then gives each survivor its own thread at full occupancy (a survivor's
+// serial header walk does not pin a CTA full of already-finished threads), and the dead records' headers are never read.
 struct Survivor { uint32_t rec, pre, flags_acc; };
 
 constexpr int kMetaPer = 4;     // records per thread: the (uniform) condition fetch / decode is paid once for four records
 
 __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restrict__ list, unsigned int* __restrict__ count) {
+  __shared__ __align__(128) uint8_t sprog[kHeadProgSmem];
+  __shared__ uint64_t bar;
+  a.prog = stage_prog_head(a.prog, sprog, &bar);
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
   const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
@@ -349,9 +340,14 @@ __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restr
   }
 }
 
-__global__ void __launch_bounds__(128) k_head_parse(HeadArgs a, const Survivor* __restrict__ list, unsigned int n_list) {
+__global__ void __launch_bounds__(256) k_head_parse(HeadArgs a, const Survivor* __restrict__ list, const unsigned int* __restrict__ n_list) {
+  __shared__ __align__(128) uint8_t sprog[kHeadProgSmem];
+  __shared__ uint64_t bar;
+  const unsigned int n_surv = *n_list;                         // written by k_head_meta earlier on this stream: no host round trip
+  if (blockIdx.x * blockDim.x >= n_surv) return;               // the grid is sized for "every record survives"
+  a.prog = stage_prog_head(a.prog, sprog, &bar);
   const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_list) return;
+  if (t >= n_surv) return;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const Survivor sv = list[t];
   const uint64_t off = a.hdr_off[sv.rec];
@@ -939,6 +935,7 @@ static int check_prog(const uint8_t* prog, uint64_t len) {
   const fei_prog_slot* sl = reinterpret_cast<const fei_prog_slot*>(prog + h.off_slots);
   for (uint32_t s = 0; s < h.n_slots; ++s) if (!sl[s].off_val_dfa || !dfa_ok(sl[s].off_val_dfa)) { set_error("bad slot DFA"); return FEI_E_BADARG; }
   if (h.n_slots && !h.off_key_dfa) { set_error("slots without a key DFA"); return FEI_E_BADARG; }
+  if (h.head_bytes > h.total_bytes || (h.head_bytes & 15u)) { set_error("bad head_bytes in program"); return FEI_E_BADARG; }
   const fei_prog_query* qs = reinterpret_cast<const fei_prog_query*>(prog + h.off_queries);
   for (uint32_t q = 0; q < h.n_queries; ++q) if (qs[q].cond_begin > qs[q].cond_end || qs[q].cond_end > h.n_conds) { set_error("bad query range"); return FEI_E_BADARG; }
   return FEI_OK;
@@ -970,22 +967,21 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   if (n && need_head) {
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
                c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>(),
-               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>()};
+               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>()};
+    if (h.n_slots) {                                           // which of the program's fields does each distinct header key of the corpus name?
+      FEI_TRY(c->key_lut.ensure(kKeySlots * sizeof(uint32_t)));
+      a.key_lut = c->key_lut.as<uint32_t>();
+      k_key_lut<<<kKeySlots / 128, 128, 0, s>>>(c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->key_tag.as<unsigned long long>(),
+                                                c->key_rep.as<unsigned long long>(), c->key_len.as<uint32_t>(), c->key_lut.as<uint32_t>());
+      ++launches;
+    }
     // selective meta predicates first: stream the meta columns, collect survivors
     FEI_TRY(c->survivors.ensure((n + 32) * sizeof(Survivor)));
     unsigned int* d_count = reinterpret_cast<unsigned int*>(c->work_counter.as<unsigned long long>() + 2);
     k_head_meta<<<(unsigned)((n + 256 * kMetaPer - 1) / (256 * kMetaPer)), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
     ++launches;
-    unsigned int n_surv = 0;
-    FEI_CUDA(cudaMemcpyAsync(&n_surv, d_count, sizeof(n_surv), cudaMemcpyDeviceToHost, s));
-    FEI_CUDA(cudaStreamSynchronize(s));
-    if ((uint64_t)n_surv * 4 > n) {
-      // most records need their header anyway: the span-staging kernel redoes the (cheap) meta phase for everybody
-      FEI_CUDA(cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadStageBytes));
-      k_head<<<(unsigned)((n + kHeadThreads - 1) / kHeadThreads), kHeadThreads, kHeadStageBytes, s>>>(a);
-      ++launches;
-    } else if (n_surv) {
-      k_head_parse<<<(n_surv + 127) / 128, 128, 0, s>>>(a, c->survivors.as<Survivor>(), n_surv);
+    if (h.slot_mask | h.name_mask) {                           // somebody may need header text or name fields
+      k_head_parse<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
       ++launches;
     }
   }

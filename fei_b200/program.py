@@ -214,17 +214,19 @@ class ProgramBuilder:
             for si, (f, mode, empty) in enumerate(slots):
                 off_val = serialize_dfa(slot_dfas[si].compile(), blob)
                 struct.pack_into("<4I", blob, off_slots + 16 * si, mode, off_val, 1 if empty else 0, 0)
+        off_flags = serialize_dfa(flags.compile(), blob) if flags.patterns else 0
+        off_names = [serialize_dfa(nf.compile(), blob) if nf.patterns else 0 for nf in names]
+        _pad16(blob)
+        head_bytes = len(blob)               # the content automaton goes last: [0, head_bytes) is what the head kernels stage
         off_body = serialize_dfa(body.compile(sticky=True), blob, SMEM_TABLE_LIMIT, tile_bytes=True) if body.patterns else 0
         if off_body:
             tb = struct.unpack_from("<I", blob, off_body + 44)[0]
             if tb > 220 * 1024:
                 raise NotImplementedError(f"content automaton needs {tb} bytes of shared memory (limit 220 KiB)")
-        off_flags = serialize_dfa(flags.compile(), blob) if flags.patterns else 0
-        off_names = [serialize_dfa(nf.compile(), blob) if nf.patterns else 0 for nf in names]
         _pad16(blob)
-        struct.pack_into("<19I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
+        struct.pack_into("<20I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
                          len(slots), off_slots, off_key, off_body, off_flags, off_names[0], off_names[1], off_names[2],
-                         head_mask, body_mask, slot_mask, name_mask)
+                         head_mask, body_mask, slot_mask, name_mask, head_bytes)
         return bytes(blob)
 
 

@@ -48,7 +48,9 @@ typedef struct fei_prog_hdr {            /* 96 bytes */
   uint32_t body_mask;                    /* queries that have at least one body condition            */
   uint32_t slot_mask;                    /* queries that read at least one header slot                */
   uint32_t name_mask;                    /* queries that read filename / id / hostname                */
-  uint32_t reserved[5];
+  uint32_t head_bytes;                   /* everything before the content automaton (which is serialised last): the part the
+                                            head kernels copy into shared memory; 0 = unknown (do not stage)              */
+  uint32_t reserved[4];
 } fei_prog_hdr;
 
 typedef struct fei_prog_dfa {            /* 64 bytes; tables follow at the given offsets            */

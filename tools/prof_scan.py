@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Tiny driver for ncu captures of one scan kernel: tools/prof_scan.py [batch32|single|nomatch|cfg2] [entries]"""
+"""Tiny driver for ncu captures of one scan kernel: tools/prof_scan.py [batch32|single|nomatch|cfg2|hdr|hdr3] [entries]"""
 import os, re, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("TZ", "UTC")
@@ -16,6 +16,16 @@ if what == "batch32":
 elif what in ("single", "nomatch"):
     pat = r"kubernetes.*docker|docker.*kubernetes" if what == "single" else r"quagga.*zebra|zebra.*quagga"
     pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", pat, re.IGNORECASE))]); prog, nq = pb.build(), 1
+elif what == "hdr":
+    pb = ProgramBuilder()
+    pb.add_query([Cond(C_SLOT, pattern=Pattern("has_tag", "python"), field="Tags", mode=0)])
+    prog, nq = pb.build(), 1
+elif what == "hdr3":
+    pb = ProgramBuilder()
+    pb.add_query([Cond(C_SLOT, pattern=Pattern("has_tag", "python"), field="Tags", mode=0)])
+    pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", "learning"), field="Subject", mode=0)])
+    pb.add_query([Cond(C_SLOT, pattern=Pattern("equals", "high"), field="Priority", mode=0), Cond(C_FLAGS, pattern=Pattern("exact_contains", "F"))])
+    prog, nq = pb.build(), 3
 else:
     pb = ProgramBuilder()
     pb.add_query([Cond(C_FLAGS, pattern=Pattern("exact_contains", "F")), Cond(C_DATE_CMP, op=CMP[">"], i64=(1700000000 + n // 8) * 1000000),
