@@ -66,6 +66,54 @@ __device__ uint32_t dfa_run(const DfaView& d, const uint8_t* p, uint32_t len) {
   return acc | d.endout[s];
 }
 
+// The same run with the tables in the shared-memory copy of the program head (stage_prog_head): 32-bit shared
+// addresses and ld.shared instead of generic 64-bit pointer arithmetic (the generic loop costs 29 instructions per
+// byte in SASS, this one about 8).
+struct DfaViewS { uint32_t trans, out, endout, cls, n_cols, stride2, start, n_acc, empty_acc; };
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t r; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t r; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ DfaViewS dfa_view_s(const uint8_t* sblob, uint32_t off) {
+  const fei_prog_dfa* d = reinterpret_cast<const fei_prog_dfa*>(sblob + off);
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sblob);
+  return DfaViewS{base + d->off_trans, base + d->off_out, base + d->off_endout, base + d->off_cls, d->n_cols, d->row_stride * 2u, d->start, d->n_acc, d->empty_acc};
+}
+// One automaton over a byte span in global memory.  out[] has an entry (0) for non-accepting states too, so there is no
+// branch around the lookup and the byte loads of an unrolled group issue ahead of the table walk.  (Fetching the span as
+// aligned 4- or 16-byte words was measured slower on the header workloads: per-lane skip / tail predicates diverge.)
+struct DfaStepS {
+  const DfaViewS& d; uint32_t s, acc; bool direct;
+  __device__ __forceinline__ void step(uint32_t b) {
+    const uint32_t col = direct ? b : lds_u8(d.cls + b);
+    s = lds_u16(d.trans + s * d.stride2 + col * 2u);
+    acc |= lds_u32(d.out + 4u * s);
+  }
+};
+__device__ __forceinline__ uint32_t dfa_run_s(const DfaViewS& d, const uint8_t* p, uint32_t len) {
+  if (len == 0) return d.empty_acc;
+  DfaStepS r{d, d.start, lds_u32(d.out + 4u * d.start), d.n_cols == 256};
+  uint32_t i = 0;
+  for (; i + 4 <= len; i += 4) {
+    const uint32_t b0 = p[i], b1 = p[i + 1], b2 = p[i + 2], b3 = p[i + 3];
+    r.step(b0); r.step(b1); r.step(b2); r.step(b3);
+  }
+  for (; i < len; ++i) r.step(p[i]);
+  return r.acc | lds_u32(d.endout + 4u * r.s);
+}
+// the same over up to 8 bytes held in a register (the flags string of a record: flags8)
+__device__ __forceinline__ uint32_t dfa_run_s_u64(const DfaViewS& d, unsigned long long bytes, uint32_t len) {
+  if (len == 0) return d.empty_acc;
+  DfaStepS r{d, d.start, lds_u32(d.out + 4u * d.start), d.n_cols == 256};
+#pragma unroll
+  for (uint32_t k = 0; k < 8; ++k) if (k < len) r.step((uint32_t)(bytes >> (8 * k)) & 0xFFu);
+  return r.acc | lds_u32(d.endout + 4u * r.s);
+}
+// dispatch: `in_smem` is uniform for the grid (stage_prog_head either staged the head for every CTA or for none)
+__device__ __forceinline__ uint32_t dfa_run_at(const uint8_t* blob, uint32_t off, bool in_smem, const uint8_t* p, uint32_t len) {
+  if (in_smem) return dfa_run_s(dfa_view_s(blob, off), p, len);
+  return dfa_run(dfa_view(blob, off), p, len);
+}
+
 // ---------------------------------------------------------------- head kernel
 struct HeadArgs {
   const uint8_t* prog;         // device copy of the program blob
@@ -76,6 +124,7 @@ struct HeadArgs {
   uint32_t* alive;
   const uint2* hdir; const uint64_t* hdir_off;     // header directory (hdir.cu)
   const uint32_t* key_lut;                         // dictionary slot of a header key -> mask of the program's slots it names (k_key_lut)
+  bool prog_in_smem;                               // set by the kernels after stage_prog_head
 };
 
 constexpr int kHeadThreads = 256;
@@ -115,7 +164,6 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
   if (parse) {
     uint32_t first_off[FEI_MAX_SLOTS], first_len[FEI_MAX_SLOTS];
     uint32_t have_first = 0;
-    DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
     const uint8_t* h = hptr;
     const uint2* ent = a.hdir + a.hdir_off[rec];
     const uint32_t n_ent = (uint32_t)(a.hdir_off[rec + 1] - a.hdir_off[rec]);
@@ -138,10 +186,11 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       }
       for (uint32_t m = present; m;) {
         int s = __ffs(m) - 1; m &= m - 1;
-        slot_acc[s] = dfa_run(dfa_view(a.prog, slots[s].off_val_dfa), h + val_off[s], val_len[s]);
+        slot_acc[s] = dfa_run_at(a.prog, slots[s].off_val_dfa, a.prog_in_smem, h + val_off[s], val_len[s]);
       }
     } else {
     // header text longer than a directory span can address: split / strip it here
+    DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
     const uint8_t* hend = hptr + hlen;
     const uint8_t* p = h;
     while (p < hend) {
@@ -182,7 +231,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       const uint8_t* nb = a.name + a.name_off[rec];
       uint32_t nl = (uint32_t)(a.name_off[rec + 1] - a.name_off[rec]);
       if (k > 0) { const uint16_t* sp = a.name_spans + 4 * rec + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
-      name_acc[k] = dfa_run(dfa_view(a.prog, ph->off_name_dfa[k]), nb, nl);
+      name_acc[k] = dfa_run_at(a.prog, ph->off_name_dfa[k], a.prog_in_smem, nb, nl);
     }
   }
   const int64_t wall = a.wall[rec];
@@ -209,32 +258,6 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
     if (ok) alive |= 1u << q;
   }
   a.alive[rec] = alive;
-}
-
-// Phase 1 for one record: meta predicates only (20 bytes per record).  Returns the queries still possible.
-__device__ __forceinline__ uint32_t head_meta(const HeadArgs& a, uint64_t i, uint32_t& flags_acc) {
-  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
-  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
-  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
-  const uint32_t fsb = a.fsb[i]; const int64_t wall = a.wall[i];
-  flags_acc = 0;
-  if (ph->off_flags_dfa) {                                     // flags string (search.py:105-106): up to 7 letters in flags8
-    uint64_t f = a.flags8[i];
-    uint8_t fb[8];
-    for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f >> (8 * k));
-    flags_acc = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, (uint32_t)(f >> 56));
-  }
-  uint32_t pre = 0;
-  for (uint32_t q = 0; q < ph->n_queries; ++q) {
-    bool ok = true;
-    for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
-      const fei_prog_cond& cd = conds[c];
-      if (cd.kind == FEI_C_SLOT && cd.if_missing == 2) { ++c; continue; }     // header-or-fallback pair: decided in phase 2
-      ok = eval_meta_cond(cd, flags_acc, wall, fsb);
-    }
-    if (ok) pre |= 1u << q;
-  }
-  return pre;
 }
 
 // Per scan: run the key automaton over the corpus' distinct header keys (hdir.cu), one thread per dictionary slot.
@@ -271,6 +294,7 @@ __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restr
   __shared__ __align__(128) uint8_t sprog[kHeadProgSmem];
   __shared__ uint64_t bar;
   a.prog = stage_prog_head(a.prog, sprog, &bar);
+  a.prog_in_smem = a.prog == sprog;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
   const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
@@ -287,12 +311,14 @@ __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restr
     flags_acc[r] = 0; pre[r] = 0;
   }
   if (ph->off_flags_dfa) {                                     // flags string (search.py:105-106): up to 7 letters in flags8
-    const DfaView fd = dfa_view(a.prog, ph->off_flags_dfa);
 #pragma unroll
     for (int r = 0; r < kMetaPer; ++r) {
-      uint8_t fb[8];
-      for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f8[r] >> (8 * k));
-      flags_acc[r] = dfa_run(fd, fb, (uint32_t)(f8[r] >> 56));
+      if (a.prog_in_smem) flags_acc[r] = dfa_run_s_u64(dfa_view_s(a.prog, ph->off_flags_dfa), f8[r], (uint32_t)(f8[r] >> 56));
+      else {
+        uint8_t fb[8];
+        for (int k = 0; k < 7; ++k) fb[k] = (uint8_t)(f8[r] >> (8 * k));
+        flags_acc[r] = dfa_run(dfa_view(a.prog, ph->off_flags_dfa), fb, (uint32_t)(f8[r] >> 56));
+      }
     }
   }
   for (uint32_t q = 0; q < ph->n_queries; ++q) {
@@ -346,6 +372,7 @@ __global__ void __launch_bounds__(256) k_head_parse(HeadArgs a, const Survivor* 
   const unsigned int n_surv = *n_list;                         // written by k_head_meta earlier on this stream: no host round trip
   if (blockIdx.x * blockDim.x >= n_surv) return;               // the grid is sized for "every record survives"
   a.prog = stage_prog_head(a.prog, sprog, &bar);
+  a.prog_in_smem = a.prog == sprog;
   const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_surv) return;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
@@ -967,7 +994,7 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   if (n && need_head) {
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
                c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>(),
-               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>()};
+               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(), false};
     if (h.n_slots) {                                           // which of the program's fields does each distinct header key of the corpus name?
       FEI_TRY(c->key_lut.ensure(kKeySlots * sizeof(uint32_t)));
       a.key_lut = c->key_lut.as<uint32_t>();

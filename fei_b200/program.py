@@ -19,6 +19,8 @@ C_CONST, C_BODY, C_SLOT, C_FLAGS, C_NAME, C_DATE_CMP, C_FOLDER_SET, C_STATUS_SET
 CMP = {">": 0, "<": 1, ">=": 2, "<=": 3, "=": 4, "!=": 5}
 NAME_FILENAME, NAME_ID, NAME_HOST = 0, 1, 2
 SMEM_TABLE_LIMIT = 200 * 1024          # body automaton must fit the CTA's shared memory
+HEAD_SMEM_WINDOW = 32 * 1024           # scan.cu kHeadProgSmem: the program head the head kernels stage per CTA
+HEAD_DIRECT_LIMIT = 12 * 1024          # a head automaton up to this size is stored byte-indexed
 
 
 @dataclass(frozen=True)
@@ -195,28 +197,33 @@ class ProgramBuilder:
                 recs.append((c.kind, ref, bit, 1 if c.negate else 0, c.if_missing, c.op, c.i64, c.set64))
             qranges.append((begin, len(recs)))
 
-        blob = bytearray(96)
-        _pad16(blob)
-        off_conds = len(blob)
-        for kind, ref, bit, neg, ifm, op, i64, set64 in recs:
-            blob.extend(struct.pack("<6B2xqQQ", kind, ref, bit, neg, ifm, op, i64, set64 & 0xFFFFFFFFFFFFFFFF, 0))
-        _pad16(blob)
-        off_queries = len(blob)
-        for a, b in qranges:
-            blob.extend(struct.pack("<4I", a, b, 0, 0))
-        _pad16(blob)
-        off_slots = len(blob)
-        blob.extend(b"\0" * (16 * len(slots)))
-        off_key = 0
-        if slots:
-            key_pats = [Pattern("exact_equals", f) if mode == 1 else Pattern("equals", f) for f, mode, _e in slots]
-            off_key = serialize_dfa(compile_patterns(key_pats), blob)
-            for si, (f, mode, empty) in enumerate(slots):
-                off_val = serialize_dfa(slot_dfas[si].compile(), blob)
-                struct.pack_into("<4I", blob, off_slots + 16 * si, mode, off_val, 1 if empty else 0, 0)
-        off_flags = serialize_dfa(flags.compile(), blob) if flags.patterns else 0
-        off_names = [serialize_dfa(nf.compile(), blob) if nf.patterns else 0 for nf in names]
-        _pad16(blob)
+        # small head automata are stored byte-indexed (one lookup per byte in the head kernels) as long as the whole
+        # program head still fits the kernels' shared-memory window; otherwise class-indexed (two lookups, smaller)
+        for head_direct in (HEAD_DIRECT_LIMIT, 0):
+            blob = bytearray(96)
+            _pad16(blob)
+            off_conds = len(blob)
+            for kind, ref, bit, neg, ifm, op, i64, set64 in recs:
+                blob.extend(struct.pack("<6B2xqQQ", kind, ref, bit, neg, ifm, op, i64, set64 & 0xFFFFFFFFFFFFFFFF, 0))
+            _pad16(blob)
+            off_queries = len(blob)
+            for a, b in qranges:
+                blob.extend(struct.pack("<4I", a, b, 0, 0))
+            _pad16(blob)
+            off_slots = len(blob)
+            blob.extend(b"\0" * (16 * len(slots)))
+            off_key = 0
+            if slots:
+                key_pats = [Pattern("exact_equals", f) if mode == 1 else Pattern("equals", f) for f, mode, _e in slots]
+                off_key = serialize_dfa(compile_patterns(key_pats), blob)          # only run over the key dictionary (k_key_lut)
+                for si, (f, mode, empty) in enumerate(slots):
+                    off_val = serialize_dfa(slot_dfas[si].compile(), blob, head_direct)
+                    struct.pack_into("<4I", blob, off_slots + 16 * si, mode, off_val, 1 if empty else 0, 0)
+            off_flags = serialize_dfa(flags.compile(), blob, head_direct) if flags.patterns else 0
+            off_names = [serialize_dfa(nf.compile(), blob, head_direct) if nf.patterns else 0 for nf in names]
+            _pad16(blob)
+            if len(blob) <= HEAD_SMEM_WINDOW:
+                break
         head_bytes = len(blob)               # the content automaton goes last: [0, head_bytes) is what the head kernels stage
         off_body = serialize_dfa(body.compile(sticky=True), blob, SMEM_TABLE_LIMIT, tile_bytes=True) if body.patterns else 0
         if off_body:
