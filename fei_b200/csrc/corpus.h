@@ -30,6 +30,9 @@ __host__ __device__ __forceinline__ uint32_t tile_byte_perm4(uint32_t w) { retur
 #endif
 constexpr int kWindow = 4096;
 constexpr uint32_t kKeySlots = 4096;       // header-key dictionary slots (hdir.cu); at most half may fill
+constexpr uint32_t kMaxCols = 8;           // header value columns kept per corpus
+constexpr uint32_t kColUnits = 4;          // 16-byte units per column value (longer values: directory walk)
+constexpr uint16_t kColAbsent = 0xFFFF, kColWalk = 0xFFFE;
 constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
 }
 
@@ -48,6 +51,12 @@ struct fei_corpus {
   fei::DevBuf hdir, hdir_off;            // header directory (hdir.cu): uint2 entries, u64 offsets [n+1]
   fei::DevBuf key_tag, key_rep, key_len, key_lut;   // dictionary of the corpus' distinct header keys + per-scan key -> slot-mask table
   uint64_t hdir_entries = 0;
+  // header value columns (hdir.cu): for the few keys almost every record carries, the stripped value of the record's LAST
+  // line with that exact key, as 16-byte units in unit-major planes (unit k of record i at plane k, offset 16 * i): a
+  // thread-per-record scan reads them fully coalesced.  col_len[c * n + i]: 0xFFFF absent, 0xFFFE walk the directory.
+  fei::DevBuf col_len, col_planes, kid_col, slot_col;
+  uint32_t n_cols = 0;
+  bool has_text_records = false;         // some record's header is parsed from its text (keys not in the dictionary)
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
   // scan scratch (grown on demand, reused across scans)
   fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors;

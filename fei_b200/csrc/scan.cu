@@ -108,6 +108,30 @@ __device__ __forceinline__ uint32_t dfa_run_s_u64(const DfaViewS& d, unsigned lo
   for (uint32_t k = 0; k < 8; ++k) if (k < len) r.step((uint32_t)(bytes >> (8 * k)) & 0xFFu);
   return r.acc | lds_u32(d.endout + 4u * r.s);
 }
+// the same over a column value: unit k (16 bytes) of the value at base + k * plane_stride (hdir.cu), LDG.128 per unit
+__device__ __forceinline__ uint32_t dfa_run_units(const DfaViewS& d, const uint8_t* base, uint64_t plane_stride, uint32_t len) {
+  if (len == 0) return d.empty_acc;
+  DfaStepS r{d, d.start, lds_u32(d.out + 4u * d.start), d.n_cols == 256};
+  for (uint32_t k = 0; k * 16 < len; ++k) {
+    const uint4 c = *reinterpret_cast<const uint4*>(base + k * plane_stride);
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    const uint32_t nb = len - k * 16;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) if (j < nb) r.step((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+  }
+  return r.acc | lds_u32(d.endout + 4u * r.s);
+}
+__device__ uint32_t dfa_run_units_g(const DfaView& d, const uint8_t* base, uint64_t plane_stride, uint32_t len) {   // tables in global memory
+  if (len == 0) return d.empty_acc;
+  uint32_t s = d.start, acc = d.out[s];
+  const bool direct = d.n_cols == 256;
+  for (uint32_t i = 0; i < len; ++i) {
+    const uint32_t b = base[(uint64_t)(i >> 4) * plane_stride + (i & 15)];
+    s = d.trans[s * d.stride + (direct ? b : d.cls[b])];
+    acc |= d.out[s];
+  }
+  return acc | d.endout[s];
+}
 // dispatch: `in_smem` is uniform for the grid (stage_prog_head either staged the head for every CTA or for none)
 __device__ __forceinline__ uint32_t dfa_run_at(const uint8_t* blob, uint32_t off, bool in_smem, const uint8_t* p, uint32_t len) {
   if (in_smem) return dfa_run_s(dfa_view_s(blob, off), p, len);
@@ -125,6 +149,8 @@ struct HeadArgs {
   const uint2* hdir; const uint64_t* hdir_off;     // header directory (hdir.cu)
   const uint32_t* key_lut;                         // dictionary slot of a header key -> mask of the program's slots it names (k_key_lut)
   bool prog_in_smem;                               // set by the kernels after stage_prog_head
+  const int8_t* slot_col;                          // per program slot: value column to read (k_slot_cols), -1 walk the directory, -2 no record has the field
+  const uint16_t* col_len; const uint8_t* col_planes;   // header value columns (hdir.cu)
 };
 
 constexpr int kHeadThreads = 256;
@@ -152,8 +178,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
 
-// Phase 2 for one record: header parse (if `hptr`), name fields, evaluation of the queries left in `pre`.
-__device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint32_t flags_acc, const uint8_t* hptr, uint32_t hlen, bool parse) {
+// Phase 2 for one record: header fields (if `parse`), name fields, evaluation of the queries left in `pre`.
+__device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint32_t flags_acc, bool parse) {
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
   const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
@@ -164,7 +190,26 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
   if (parse) {
     uint32_t first_off[FEI_MAX_SLOTS], first_len[FEI_MAX_SLOTS];
     uint32_t have_first = 0;
-    const uint8_t* h = hptr;
+    // fields that have a value column: the record's value sits at plane k, offset 16 * rec -- consecutive threads read
+    // consecutive units, and neither the directory nor the header text of the record is touched
+    bool walk = false;
+    for (uint32_t s = 0; s < nslots; ++s) {
+      const int col = a.slot_col[s];
+      if (col == -2) continue;                                 // no record of this corpus has the field
+      if (col < 0) { walk = true; break; }
+      const uint32_t len = a.col_len[(uint64_t)col * a.n + rec];
+      if (len == kColAbsent) continue;
+      if (len == kColWalk) { walk = true; break; }
+      const uint8_t* unit = a.col_planes + (uint64_t)col * kColUnits * a.n * 16 + rec * 16;
+      slot_acc[s] = a.prog_in_smem ? dfa_run_units(dfa_view_s(a.prog, slots[s].off_val_dfa), unit, a.n * 16, len)
+                                   : dfa_run_units_g(dfa_view(a.prog, slots[s].off_val_dfa), unit, a.n * 16, len);
+      present |= 1u << s;
+    }
+    if (walk) {
+    present = 0;
+    const uint64_t hoff = a.hdr_off[rec];
+    const uint8_t* h = a.hdr + hoff;
+    const uint32_t hlen = (uint32_t)(a.hdr_off[rec + 1] - hoff);
     const uint2* ent = a.hdir + a.hdir_off[rec];
     const uint32_t n_ent = (uint32_t)(a.hdir_off[rec + 1] - a.hdir_off[rec]);
     if (!(n_ent == 1 && ent[0].x == 0xFFFFFFFFu)) {
@@ -191,7 +236,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
     } else {
     // header text longer than a directory span can address: split / strip it here
     DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
-    const uint8_t* hend = hptr + hlen;
+    const uint8_t* hend = h + hlen;
     const uint8_t* p = h;
     while (p < hend) {
       const uint8_t* eol = p; const uint8_t* colon = nullptr;
@@ -218,6 +263,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       p = eol + 1;
     }
     }
+    }
   }
   for (uint32_t s = 0; s < nslots; ++s)
     if (!(present >> s & 1) && slots[s].empty_if_missing) {   // headers.get("Status", "")
@@ -234,12 +280,11 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       name_acc[k] = dfa_run_at(a.prog, ph->off_name_dfa[k], a.prog_in_smem, nb, nl);
     }
   }
-  const int64_t wall = a.wall[rec];
-  const uint32_t fsb = a.fsb[rec];
   uint32_t alive = 0;
   for (uint32_t q = 0; q < ph->n_queries; ++q) {
     if (!(pre >> q & 1)) continue;
     bool ok = true;
+    bool fallback = false;                                      // the condition is the fallback field of an absent header
     for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
       const fei_prog_cond& cd = conds[c];
       bool r;
@@ -247,12 +292,15 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
         case FEI_C_BODY: continue;                              // evaluated by k_body
         case FEI_C_SLOT:
           if (present >> cd.ref & 1) { r = ((slot_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; if (cd.if_missing == 2) ++c; }
-          else if (cd.if_missing == 2) continue;               // header absent: the next condition is the fallback field
+          else if (cd.if_missing == 2) { fallback = true; continue; }   // header absent: the next condition is the fallback field
           else r = cd.if_missing != 0;
           break;
         case FEI_C_NAME: r = ((name_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; break;
-        default: r = eval_meta_cond(cd, flags_acc, wall, fsb);
+        default:
+          // meta predicates of a query in `pre` already held in k_head_meta; only a fallback field (skipped there) is still open
+          r = fallback ? eval_meta_cond(cd, flags_acc, a.wall[rec], a.fsb[rec]) : true;
       }
+      fallback = false;
       ok = r;
     }
     if (ok) alive |= 1u << q;
@@ -267,6 +315,21 @@ __global__ void k_key_lut(const uint8_t* __restrict__ prog, const uint8_t* __res
   if (s >= kKeySlots) return;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(prog);
   lut[s] = tag[s] ? dfa_run(dfa_view(prog, ph->off_key_dfa), hdr + rep[s], len[s]) : 0u;
+}
+
+// One warp, after k_key_lut: a program slot whose field is spelled exactly one way in the whole corpus can be read from that
+// key's value column (if it has one); a field no record carries is absent everywhere; anything else walks the directory.
+__global__ void k_slot_cols(const uint8_t* __restrict__ prog, const uint32_t* __restrict__ lut, const int8_t* __restrict__ kid_col,
+                            uint32_t n_cols, uint32_t any_text, int8_t* __restrict__ slot_col) {
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(prog);
+  const int lane = threadIdx.x & 31;
+  for (uint32_t s = 0; s < ph->n_slots && s < FEI_MAX_SLOTS; ++s) {
+    uint32_t count = 0, kid = 0;
+    for (uint32_t k = lane; k < kKeySlots; k += 32) if (lut[k] >> s & 1u) { ++count; kid = k; }
+    for (int o = 16; o; o >>= 1) { count += __shfl_xor_sync(0xffffffffu, count, o); kid = max(kid, __shfl_xor_sync(0xffffffffu, kid, o)); }
+    // (records whose header is parsed from its text keep their keys out of the dictionary: with any of those, nothing is "absent everywhere")
+    if (lane == 0) slot_col[s] = count == 0 ? (any_text ? (int8_t)-1 : (int8_t)-2) : (count == 1 && n_cols ? kid_col[kid] : (int8_t)-1);
+  }
 }
 
 // Every CTA of the head kernels first copies the "head" of the program (header, conditions, queries, slots and all
@@ -377,8 +440,7 @@ __global__ void __launch_bounds__(256) k_head_parse(HeadArgs a, const Survivor* 
   if (t >= n_surv) return;
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const Survivor sv = list[t];
-  const uint64_t off = a.hdr_off[sv.rec];
-  head_finish(a, sv.rec, sv.pre, sv.flags_acc, a.hdr + off, (uint32_t)(a.hdr_off[sv.rec + 1] - off), (sv.pre & ph->slot_mask) != 0);
+  head_finish(a, sv.rec, sv.pre, sv.flags_acc, (sv.pre & ph->slot_mask) != 0);
 }
 
 // ---------------------------------------------------------------- body kernel
@@ -994,13 +1056,18 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   if (n && need_head) {
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
                c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>(),
-               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(), false};
+               c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(), false,
+               c->slot_col.as<int8_t>(), c->col_len.as<uint16_t>(), c->col_planes.as<uint8_t>()};
     if (h.n_slots) {                                           // which of the program's fields does each distinct header key of the corpus name?
       FEI_TRY(c->key_lut.ensure(kKeySlots * sizeof(uint32_t)));
       a.key_lut = c->key_lut.as<uint32_t>();
       k_key_lut<<<kKeySlots / 128, 128, 0, s>>>(c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->key_tag.as<unsigned long long>(),
                                                 c->key_rep.as<unsigned long long>(), c->key_len.as<uint32_t>(), c->key_lut.as<uint32_t>());
-      ++launches;
+      FEI_TRY(c->slot_col.ensure(FEI_MAX_SLOTS));
+      FEI_TRY(c->kid_col.ensure(kKeySlots));
+      a.slot_col = c->slot_col.as<int8_t>();
+      k_slot_cols<<<1, 32, 0, s>>>(c->prog.as<uint8_t>(), c->key_lut.as<uint32_t>(), c->kid_col.as<int8_t>(), c->n_cols, c->has_text_records ? 1u : 0u, c->slot_col.as<int8_t>());
+      launches += 2;
     }
     // selective meta predicates first: stream the meta columns, collect survivors
     FEI_TRY(c->survivors.ensure((n + 32) * sizeof(Survivor)));

@@ -145,6 +145,7 @@ ADVERSARIAL = [
     ("  Subject  :  spaced out  \n\tTags\t:\tpython , rust\t\n", "Ünïcödé K ſ body\nwith KELVIN \u212a and long s \u017f"),
     ("NoColonLine\nTags: python\n: emptykey\nKey:\n", ""),                               # line without colon, empty key, empty value
     ("Tags:\u00a0python\u2003\n", "nbsp and em-space around the tag"),
+    ("Tags: " + ",".join(f"tag{i}" for i in range(20)) + ",python, lower\nSubject: " + "long subject " * 8 + "beta\n", "values longer than a column slot (64 bytes): directory walk"),
     ("Subject: x\nStatus: done\nStatus: ACTIVE\n", "status twice"),
     ("", "no headers at all but a body mentioning python and docker then kubernetes"),
     ("Tags: Python,\u212aelvin\nPriority: HIGH\n", "kelvin sign tag"),
@@ -363,12 +364,13 @@ def test_random_headers_differential(gpu):
     # the same corpus with the header directory switched off (FEI_HDIR=0 at load: every record takes the in-scan text
     # parser that otherwise only > 64 KiB headers reach): both header paths must give the same masks
     import os
-    os.environ["FEI_HDIR"] = "0"
-    try:
-        c_text = Corpus().load(synth.arrays_from_records(recs))
-    finally:
-        del os.environ["FEI_HDIR"]
-    assert np.array_equal(c_text.scan_masks(pb.build()), masks)
+    for var in ("FEI_HDIR", "FEI_HCOLS"):      # FEI_HCOLS=0: directory walk for every field (no value columns)
+        os.environ[var] = "0"
+        try:
+            c_alt = Corpus().load(synth.arrays_from_records(recs))
+        finally:
+            del os.environ[var]
+        assert np.array_equal(c_alt.scan_masks(pb.build()), masks), var
 
 
 def _search_prog2(conds):
