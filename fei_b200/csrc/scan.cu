@@ -26,6 +26,7 @@
 #include "../../include/feiscan_prog.h"
 #include "pyws.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace fei {
@@ -353,6 +354,7 @@ struct Survivor { uint32_t rec, pre, flags_acc; };
 
 constexpr int kMetaPer = 4;     // records per thread: the (uniform) condition fetch / decode is paid once for four records
 
+template <bool kFused>
 __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restrict__ list, unsigned int* __restrict__ count) {
   __shared__ __align__(128) uint8_t sprog[kHeadProgSmem];
   __shared__ uint64_t bar;
@@ -398,6 +400,17 @@ __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restr
     for (int r = 0; r < kMetaPer; ++r) if (ok[r]) pre[r] |= 1u << q;
   }
   const uint32_t later_mask = ph->slot_mask | ph->name_mask;
+  if (kFused) {
+    // header / name fields right here: with value columns a record's fields are a couple of coalesced loads and short
+    // automaton runs, so there is no long per-record walk that would pin the CTA, and the work list is not needed
+    for (int r = 0; r < kMetaPer; ++r) {
+      const uint64_t i = base + (uint64_t)r * 256;
+      if (!valid[r]) continue;
+      if ((pre[r] & later_mask) == 0) a.alive[i] = pre[r];
+      else head_finish(a, i, pre[r], flags_acc[r], (pre[r] & ph->slot_mask) != 0);
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31;
   // survivors: slots are reserved per warp in shared memory and per CTA with ONE global atomic (a global atomic per
   // warp put 260 k same-address atomics on the L2 for 10 M records: 130 us, more than streaming the columns)
@@ -1072,11 +1085,32 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
     // selective meta predicates first: stream the meta columns, collect survivors
     FEI_TRY(c->survivors.ensure((n + 32) * sizeof(Survivor)));
     unsigned int* d_count = reinterpret_cast<unsigned int*>(c->work_counter.as<unsigned long long>() + 2);
-    k_head_meta<<<(unsigned)((n + 256 * kMetaPer - 1) / (256 * kMetaPer)), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
-    ++launches;
-    if (h.slot_mask | h.name_mask) {                           // somebody may need header text or name fields
-      k_head_parse<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
+    const unsigned meta_grid = (unsigned)((n + 256 * kMetaPer - 1) / (256 * kMetaPer));
+    // One fused kernel when no meta predicate can thin out the records that need header fields (then every one of them is
+    // finished where it was read, no work list); otherwise the meta pass collects the survivors and k_head_parse runs them dense.
+    bool fuse = !(getenv("FEI_HEAD_FUSE") && getenv("FEI_HEAD_FUSE")[0] == '0');
+    {
+      const fei_prog_cond* cds = reinterpret_cast<const fei_prog_cond*>(prog + h.off_conds);
+      const fei_prog_query* qs = reinterpret_cast<const fei_prog_query*>(prog + h.off_queries);
+      for (uint32_t q = 0; q < h.n_queries && fuse; ++q) {
+        if (!((h.slot_mask | h.name_mask) >> q & 1u)) continue;
+        for (uint32_t k = qs[q].cond_begin; k < qs[q].cond_end; ++k) {
+          const uint8_t kind = cds[k].kind;
+          if (kind == FEI_C_SLOT && cds[k].if_missing == 2) { ++k; continue; }      // the fallback field is decided with the header
+          if (kind == FEI_C_FLAGS || kind == FEI_C_DATE_CMP || kind == FEI_C_FOLDER_SET || kind == FEI_C_STATUS_SET) { fuse = false; break; }
+        }
+      }
+    }
+    if (fuse) {
+      k_head_meta<true><<<meta_grid, 256, 0, s>>>(a, nullptr, nullptr);
       ++launches;
+    } else {
+      k_head_meta<false><<<meta_grid, 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
+      ++launches;
+      if (h.slot_mask | h.name_mask) {                         // somebody may need header text or name fields
+        k_head_parse<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, c->survivors.as<Survivor>(), d_count);
+        ++launches;
+      }
     }
   }
   FEI_CUDA(cudaEventRecord(c->ev[2], s));
