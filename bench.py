@@ -536,7 +536,11 @@ def run_extra(args, corpus, st, peak, lib, _abi):
     from fei_b200.memdir_tools import memorychain as mc
     from oracle import chain_oracle as co
     nb_api = min(nb, 100_000)
-    blocks = co.build_chain(synth.chain_specs(CHAIN_SEED, 0, nb_api))      # plain objects with the reference's block attributes
+    blocks = []                                                            # reference-shaped MemoryBlock objects (plain instance attributes)
+    for ob in co.build_chain(synth.chain_specs(CHAIN_SEED, 0, nb_api)):
+        b = mc.MemoryBlock(ob.index, ob.timestamp, ob.memory_data, ob.previous_hash, ob.responsible_node, ob.proposer_node)
+        b.nonce = ob.nonce; b.hash = ob.hash
+        blocks.append(b)
     chain_obj = mc.MemoryChain(blocks=blocks)
     chain_obj.validate_chain()
     ts = []
