@@ -59,7 +59,7 @@ struct fei_corpus {
   bool has_text_records = false;         // some record's header is parsed from its text (keys not in the dictionary)
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
   // scan scratch (grown on demand, reused across scans)
-  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors;
+  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors, live_list;
   fei::CompactScratch compact;
   uint64_t hit_list_stride = 0;          // entries per query in hit_lists (last fei_scan_hits)
   uint32_t last_nq = 0;

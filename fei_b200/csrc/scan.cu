@@ -487,7 +487,8 @@ struct BodyArgs {
   uint64_t n_groups;
   uint32_t* hits;              // in: alive masks (when has_alive), out: final hit masks
   int has_alive;
-  unsigned long long* counter; // [0] = next group, [1] = tile bytes of the groups entered, [3] = tile bytes requested
+  unsigned long long* counter; // [0] = next group, [1] = tile bytes of the groups entered, [3] = tile bytes requested, [4] = live records (gather)
+  unsigned long long gather_max;   // k_body_sticky stands down (and k_body_gather runs) when 0 < counter[4] <= gather_max
 };
 
 constexpr int kBodyThreads = 1024;
@@ -675,12 +676,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr_s) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr_s));
   return r;
 }
+constexpr unsigned long long kGatherDiv = 16;       // k_body_gather takes over when at most 1 record in 16 is still alive
 constexpr uint32_t kStickyAddrLimit = 65535u;
 constexpr uint32_t kStickyAddrSlack = 4096u;     // head-room the host leaves for the shared-memory window base
 
 __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  if (a.gather_max && a.counter[4] <= a.gather_max) return;    // few live records: k_body_gather has them (uniform for the grid)
   const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
   const fei_prog_dfa* dd = reinterpret_cast<const fei_prog_dfa*>(a.prog + ph->off_body_dfa);
   const uint32_t table_bytes = dd->table_bytes;
@@ -914,6 +917,102 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
   if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
 
+// ---------------------------------------------------------------- single-pattern scan of FEW surviving records
+// After selective header predicates a group of 32 has at most a lane or two left alive; k_body_sticky then runs one
+// serial automaton chain per group and the SM idles at 64 chains (measured 0.25 ms for 35 k survivors of 10 M records:
+// the latency floor of that shape).  k_live_list compacts the survivors and k_body_gather gives every one its own
+// thread: a lane walks its record through the tiles of its group (row k of a group starts 16 * sum_{j<k} m_j after the
+// group base, m_j = lanes that still have a unit j, recovered from the group's sorted lengths), so a warp runs 32 chains.
+__global__ void __launch_bounds__(256) k_live_list(const uint32_t* __restrict__ alive, uint64_t n, uint32_t* __restrict__ list,
+                                                  unsigned long long* __restrict__ count, unsigned long long cap) {
+  __shared__ unsigned int cta_count; __shared__ unsigned long long cta_base;
+  if (threadIdx.x == 0) cta_count = 0;
+  __syncthreads();
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const bool live = i < n && alive[i] != 0;
+  const uint32_t bal = __ballot_sync(0xffffffffu, live);
+  const int lane = threadIdx.x & 31;
+  unsigned int wbase = 0;
+  if (lane == 0 && bal) wbase = atomicAdd(&cta_count, (unsigned int)__popc(bal));
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  __syncthreads();
+  if (threadIdx.x == 0 && cta_count) cta_base = atomicAdd(count, (unsigned long long)cta_count);
+  __syncthreads();
+  if (live) { const unsigned long long at = cta_base + wbase + __popc(bal & ((1u << lane) - 1u)); if (at < cap) list[at] = (uint32_t)i; }
+}
+
+__global__ void __launch_bounds__(kBodyThreads, 1) k_body_gather(BodyArgs a, const uint32_t* __restrict__ live, const uint32_t* __restrict__ rec_pos) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  const unsigned long long n_live = a.counter[4];
+  if (n_live == 0 || n_live > a.gather_max) return;            // k_body_sticky takes the dense case (uniform for the grid)
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const fei_prog_dfa* dd = reinterpret_cast<const fei_prog_dfa*>(a.prog + ph->off_body_dfa);
+  const uint32_t table_bytes = dd->table_bytes;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, table_bytes);
+    const uint8_t* src = a.prog + dd->off_trans;
+    for (uint32_t o = 0; o < table_bytes; o += 32768u) {
+      uint32_t nb = table_bytes - o < 32768u ? table_bytes - o : 32768u;
+      bulk_g2s(smem + o, src + o, nb, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+  const uint32_t trans_s = smem_u32(smem), stride2 = dd->row_stride * 2u, n_entries = dd->n_states * dd->row_stride;
+  if (trans_s + dd->n_states * stride2 > kStickyAddrLimit) __trap();
+  {
+    uint16_t* t = reinterpret_cast<uint16_t*>(smem);
+    for (uint32_t i = threadIdx.x; i < n_entries; i += kBodyThreads) t[i] = (uint16_t)(trans_s + (uint32_t)t[i] * stride2);
+  }
+  __syncthreads();
+  const uint32_t* endout = reinterpret_cast<const uint32_t*>(smem + (dd->off_endout - dd->off_trans));
+  const uint32_t start_e = trans_s + dd->start * stride2;
+  const uint32_t sticky_e = dd->sticky != 0xFFFFFFFFu ? trans_s + (dd->sticky - 1u) * stride2 : 0xFFFFFFFFu;
+  const fei_prog_cond* conds = reinterpret_cast<const fei_prog_cond*>(a.prog + ph->off_conds);
+  const fei_prog_query* queries = reinterpret_cast<const fei_prog_query*>(a.prog + ph->off_queries);
+  const uint32_t nq = ph->n_queries;
+  unsigned long long bytes_read = 0;
+  for (unsigned long long t = blockIdx.x * (unsigned long long)kBodyThreads + threadIdx.x; t < n_live; t += (unsigned long long)gridDim.x * kBodyThreads) {
+    const uint32_t rec = live[t];
+    const uint32_t pos = rec_pos[rec];
+    const uint64_t g = pos >> 5; const uint32_t l = pos & 31u;
+    const uint32_t* gl = a.grp_len + g * 32;
+    const uint32_t len = gl[l];
+    const uint32_t units = (len + 15) >> 4;
+    const uint32_t alive = a.hits[rec];
+    uint32_t m = 32;                                             // lanes of the group that have a unit k (lengths are sorted descending)
+    uint32_t drop = (gl[31] + 15) >> 4;                          // the first row lane m-1 is missing from
+    const uint8_t* p = a.tiles + a.grp_base[g] * 16 + l * 16;
+    uint32_t e = start_e;
+    for (uint32_t k = 0; k < units; ++k) {
+      while (k >= drop) { --m; drop = m > l + 1 ? (gl[m - 1] + 15) >> 4 : 0xFFFFFFFFu; }
+      const uint4 v = ldg_stream16(p);
+      p += (uint64_t)m * 16;
+      const int nb = (int)len - (int)(k * 16);
+      if (nb >= 16) e = sticky_row(e, v);
+      else { e = sticky_partial(e, v.x, nb); e = sticky_partial(e, v.y, nb - 4); e = sticky_partial(e, v.z, nb - 8); e = sticky_partial(e, v.w, nb - 12); }
+      bytes_read += 16;
+      if (e == sticky_e) break;                                  // matched: the verdict cannot change any more
+    }
+    const uint32_t acc = endout[(e - trans_s) / stride2];
+    uint32_t hit = 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+      if (!(alive >> q & 1)) continue;
+      bool ok = true;
+      for (uint32_t c = queries[q].cond_begin; ok && c < queries[q].cond_end; ++c) {
+        const fei_prog_cond& cd = conds[c];
+        if (cd.kind == FEI_C_BODY) ok = ((acc >> cd.bit) & 1u) != cd.negate;
+      }
+      if (ok) hit |= 1u << q;
+    }
+    a.hits[rec] = hit;
+  }
+  for (int o = 16; o; o >>= 1) bytes_read += __shfl_down_sync(0xffffffffu, bytes_read, o);
+  if ((threadIdx.x & 31) == 0 && bytes_read) { atomicAdd(a.counter + 3, bytes_read); atomicAdd(a.counter + 1, bytes_read); }
+}
+
 template <bool kDirect, int kAcc>
 static int launch_body(const BodyArgs& a, unsigned grid, size_t smem, cudaStream_t s) {
   FEI_CUDA(cudaFuncSetAttribute(k_body<kDirect, kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1055,10 +1154,10 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   c->last_nq = h.n_queries;
   FEI_TRY(c->prog.ensure(prog_len + 16));
   FEI_TRY(c->hits.ensure((n ? n : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->work_counter.ensure(4 * sizeof(unsigned long long)));
+  FEI_TRY(c->work_counter.ensure(8 * sizeof(unsigned long long)));
   FEI_CUDA(cudaEventRecord(c->ev[0], s));
   FEI_CUDA(cudaMemcpyAsync(c->prog.p, prog, prog_len, cudaMemcpyHostToDevice, s));
-  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, 4 * sizeof(unsigned long long), s));
+  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, 8 * sizeof(unsigned long long), s));
   bool need_head = h.head_mask != 0;
   bool need_body = h.off_body_dfa != 0 && h.body_mask != 0;
   if ((h.off_name_dfa[0] || h.off_name_dfa[1] || h.off_name_dfa[2]) && !c->name.p) {
@@ -1119,13 +1218,23 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
     size_t smem = d.table_bytes;
     if (smem > 220 * 1024) { set_error("content automaton needs %zu bytes of shared memory (limit 220 KiB)", smem); return FEI_E_UNSUPPORTED; }
     BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
-               c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>()};
+               c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>(), 0ull};
     unsigned grid = (unsigned)cx.sm_count;
     uint32_t n_acc = d.n_acc;
     int acc_mode = d.sticky ? 3 : n_acc <= 32 ? 1 : n_acc <= 64 ? 2 : 0;
     bool direct = d.n_cols == 256;
     int rc;
     if (direct && acc_mode == 3 && (uint64_t)d.n_states * d.row_stride * 2 + kStickyAddrSlack <= kStickyAddrLimit) {
+      if (need_head && n >= 65536) {
+        // header predicates ran first: when they left few records alive, scan those record by record (k_body_gather); both
+        // kernels are launched and the live count on the device decides which one works (no host round trip)
+        a.gather_max = n / kGatherDiv;
+        FEI_TRY(c->live_list.ensure((a.gather_max + 1) * sizeof(uint32_t)));
+        k_live_list<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->hits.as<uint32_t>(), n, c->live_list.as<uint32_t>(), a.counter + 4, a.gather_max);
+        FEI_CUDA(cudaFuncSetAttribute(k_body_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_body_gather<<<grid, kBodyThreads, smem, s>>>(a, c->live_list.as<uint32_t>(), c->rec_pos.as<uint32_t>());
+        launches += 2;
+      }
       const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
       FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
       k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);

@@ -425,6 +425,15 @@ def test_full_size_corpus_sampled_windows_and_invariants(gpu):
     for q in (0, 6):
         pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", pats[q], re.IGNORECASE))])
         assert np.array_equal(c.scan_hits(pb.build(), 1)[0], hits[q])
+    # selective header predicates + one content pattern: few records reach the body pass (k_live_list + k_body_gather, one
+    # thread per surviving record); it must equal the intersection of the header-only and the content-only scans (other kernels)
+    head_conds = [("Tags", "has_tag", "python"), ("flags", "has_flag", "F")]
+    body_cond = ("content", "matches", r"react|angular")
+    pb = ProgramBuilder(); pb.add_query(_search_prog(head_conds)); m_head = c.scan_masks(pb.build()) & np.uint32(1)
+    pb = ProgramBuilder(); pb.add_query(_search_prog([body_cond])); m_body = c.scan_masks(pb.build()) & np.uint32(1)
+    pb = ProgramBuilder(); pb.add_query(_search_prog(head_conds + [body_cond])); m_both = c.scan_masks(pb.build()) & np.uint32(1)
+    assert 0 < int(m_head.sum()) < n // 16                              # sparse enough for the gather path
+    assert np.array_equal(m_both, m_head & m_body)
     for first in (0, 777_777, n - 1500):
         k = 1500
         recs = [synth.record(0xFE1, first + i) for i in range(k)]
@@ -433,6 +442,8 @@ def test_full_size_corpus_sampled_windows_and_invariants(gpu):
             want = mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}])
             got = np.nonzero((masks[first:first + k] >> np.uint32(q)) & np.uint32(1))[0].tolist()
             assert got == want, (first, p)
+        want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in head_conds + [body_cond]])
+        assert np.nonzero(m_both[first:first + k])[0].tolist() == want, first
 
 
 def test_single_pattern_kernel_shapes(gpu):
