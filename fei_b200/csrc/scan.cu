@@ -740,8 +740,12 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
     if (live_mask == 0) return;                                     // nobody in this group can still match: skip its bytes
     G.row = a.tiles + a.grp_base[g] * 16;
     G.maxu = __shfl_sync(0xffffffffu, (G.len + 15) >> 4, 0);
-    // rows that are 16 full bytes for all 32 lanes form one contiguous run of 512-byte rows
-    G.full = live_mask == 0xffffffffu ? __reduce_min_sync(0xffffffffu, G.len >> 4) : 0u;
+    // rows that are 16 full bytes for all 32 lanes form one contiguous run of 512-byte rows.  Lanes a header predicate
+    // already rejected ride along in the absorbing state (they read zeros, never hold up the early stop, write nothing):
+    // a half-alive group keeps the streaming path instead of falling back to the row-by-row loop.
+    const uint32_t valid_mask = __ballot_sync(0xffffffffu, G.rec != kInvalidRec);
+    G.full = valid_mask == 0xffffffffu ? __reduce_min_sync(0xffffffffu, G.len >> 4) : 0u;
+    if (!G.live && sticky_e != 0xFFFFFFFFu) G.e = sticky_e;
     if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
   };
   // Full rows of ONE group through the ring: kChunkRows rows per bulk copy, kStages copies in flight; a stage is refilled

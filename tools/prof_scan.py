@@ -16,6 +16,10 @@ if what == "batch32":
 elif what in ("single", "nomatch"):
     pat = r"kubernetes.*docker|docker.*kubernetes" if what == "single" else r"quagga.*zebra|zebra.*quagga"
     pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", pat, re.IGNORECASE))]); prog, nq = pb.build(), 1
+elif what == "half":
+    pb = ProgramBuilder()
+    pb.add_query([Cond(C_FLAGS, pattern=Pattern("exact_contains", "F")), Cond(C_BODY, pattern=Pattern("regex", r"quagga.*zebra|zebra.*quagga", re.IGNORECASE))])
+    prog, nq = pb.build(), 1
 elif what == "hdr":
     pb = ProgramBuilder()
     pb.add_query([Cond(C_SLOT, pattern=Pattern("has_tag", "python"), field="Tags", mode=0)])
