@@ -290,7 +290,8 @@ extern "C" int fei_corpus_stats_get(const fei_corpus* c, fei_corpus_stats* out) 
   out->hdr_bytes = c->hdr_bytes; out->body_bytes = c->body_bytes; out->tile_bytes = c->tile_bytes; out->name_bytes = c->name_bytes;
   out->n_groups = c->n_groups;
   out->device_bytes = c->hdr.bytes + c->hdr_off.bytes + c->name.bytes + c->name_off.bytes + c->ts.bytes + c->wall.bytes + c->flags8.bytes + c->fsb.bytes +
-                      c->tiles.bytes + c->grp_base.bytes + c->grp_rec.bytes + c->grp_len.bytes + c->rec_pos.bytes;
+                      c->tiles.bytes + c->grp_base.bytes + c->grp_rec.bytes + c->grp_len.bytes + c->rec_pos.bytes +
+                      c->hdir.bytes + c->hdir_off.bytes + c->key_tag.bytes + c->key_rep.bytes + c->key_len.bytes + c->col_len.bytes + c->col_planes.bytes + c->kid_col.bytes;
   return FEI_OK;
 }
 
