@@ -16,8 +16,11 @@ library's C++ serialiser and SHA-256 + the two comparisons run in the CUDA kerne
 from __future__ import annotations
 
 import ctypes as C
+import json
 import logging
+import os
 import threading
+import time
 from operator import attrgetter, itemgetter
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -26,6 +29,8 @@ import numpy as np
 from .. import _abi
 
 logger = logging.getLogger("memorychain")     # same logger name as the reference (:43)
+
+CHAIN_FILE = os.path.join(os.path.expanduser("~"), ".memdir", "memorychain.json")     # reference :49
 
 TASK_PROPOSED = "proposed"
 DIFFICULTY_LEVELS = {"easy": 1, "medium": 3, "hard": 5, "very_hard": 10, "extreme": 20}
@@ -353,19 +358,83 @@ class _HashProbe:
 
 
 class MemoryChain:
-    """The slice of the reference's ``MemoryChain`` that validation touches (:501-526, :596-618).
+    """The ledger slice of the reference's ``MemoryChain``: building (genesis, add_memory with GPU proof of work), validating
+    (:596-618), syncing (receive_chain_update) and persisting (serialize / save / load) a chain.
 
-    Consensus, wallet, networking and persistence are out of scope.
+    Consensus voting, wallet and networking are out of scope.  Unlike the reference constructor this one
+    does not touch the disk: pass ``chain_file`` to have add_memory persist after every block as the reference does.
     """
 
-    def __init__(self, node_id: str = "validator", difficulty: int = 2, blocks: Optional[Iterable[Any]] = None):
+    def __init__(self, node_id: str = "validator", difficulty: int = 2, blocks: Optional[Iterable[Any]] = None,
+                 chain_file: Optional[str] = None):
         self.chain: List[Any] = list(blocks) if blocks is not None else []
         self.node_id = node_id
         self.difficulty = difficulty
         self.lock = threading.RLock()
+        self.chain_file = chain_file      # None: nothing is written behind the caller's back; save_chain() then uses CHAIN_FILE
 
     def validate_chain(self) -> bool:
         return validate_chain_blocks(self.chain, lock=self.lock, log=logger)
+
+    # ---- building and persisting the ledger (reference :528-594, :1130-1172); proof of work runs on the GPU (mine_block)
+    def create_genesis_block(self) -> None:
+        """Reference :528-550 (same memory payload; the date object is kept in memory_data exactly as there)."""
+        from datetime import datetime
+        genesis_memory = {
+            "metadata": {"unique_id": "genesis", "timestamp": time.time(), "date": datetime.now(), "flags": []},
+            "headers": {"Subject": "Genesis Block", "Tags": "system,genesis,memorychain", "Status": "system"},
+            "content": "Initial block of the Memory Chain. Created on " + datetime.now().isoformat(),
+        }
+        genesis_block = MemoryBlock(0, time.time(), genesis_memory, "0", self.node_id, self.node_id)
+        genesis_block.mine_block(self.difficulty)
+        with self.lock:
+            self.chain.append(genesis_block)
+
+    def get_latest_block(self) -> "MemoryBlock":
+        with self.lock:
+            return self.chain[-1]
+
+    def add_memory(self, memory_data: Dict[str, Any], responsible_node: Optional[str] = None) -> str:
+        """Reference :562-594: link to the latest block, mine (GPU nonce search), append, persist.  Returns the new hash."""
+        if responsible_node is None:
+            responsible_node = self.node_id
+        previous_block = self.get_latest_block()
+        new_block = MemoryBlock(previous_block.index + 1, time.time(), memory_data, previous_block.hash,
+                                responsible_node, self.node_id)
+        new_block.mine_block(self.difficulty)
+        with self.lock:
+            self.chain.append(new_block)
+            if self.chain_file:
+                self.save_chain()
+        return new_block.hash
+
+    def serialize_chain(self) -> List[Dict[str, Any]]:
+        with self.lock:
+            return [block.to_dict() for block in self.chain]
+
+    def save_chain(self) -> None:
+        """Reference :1140-1149 (`json.dump(chain_data, f, indent=2)`), to `self.chain_file` (default: the reference's CHAIN_FILE)."""
+        with self.lock:
+            chain_data = self.serialize_chain()
+            path = self.chain_file or CHAIN_FILE
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "w") as f:
+                json.dump(chain_data, f, indent=2)
+
+    def load_chain(self) -> bool:
+        """Reference :1151-1172: True when a non-empty chain was read."""
+        path = self.chain_file or CHAIN_FILE
+        try:
+            if not os.path.exists(path):
+                return False
+            with open(path, "r") as f:
+                chain_data = json.load(f)
+            with self.lock:
+                self.chain = [MemoryBlock.from_dict(block_data) for block_data in chain_data]
+            return len(self.chain) > 0
+        except (json.JSONDecodeError, KeyError, FileNotFoundError) as e:
+            logger.error(f"Error loading chain: {e}")
+            return False
 
     def receive_chain_update(self, chain_data: List[Dict[str, Any]]) -> bool:
         """Validation half of the reference's chain sync (:1037-1085): the same two checks as

@@ -157,3 +157,37 @@ def test_mine_block_matches_reference(gpu, chain_golden):
     for n in range(max(0, b.nonce - 3000), b.nonce):          # no smaller nonce in the window before it
         probe.nonce = n
         assert not co.block_hash(probe).startswith("00000")
+
+
+def test_build_persist_and_reload_a_chain(gpu, tmp_path):
+    """create_genesis_block / add_memory (GPU proof of work) / save_chain / load_chain / serialize_chain (reference :528-594, :1130-1172)."""
+    import json
+    from fei_b200 import synth
+    from fei_b200.memdir_tools import memorychain as mc
+    chain = mc.MemoryChain(node_id="node-a", difficulty=3)
+    chain.create_genesis_block()
+    g = chain.get_latest_block()
+    assert g.index == 0 and g.previous_hash == "0" and g.hash.startswith("000") and g.hash == co.block_hash(g)
+    with pytest.raises(TypeError):                       # the genesis payload holds a datetime, json.dump refuses it -- as in the reference
+        mc.MemoryChain(blocks=chain.chain, chain_file=str(tmp_path / "g.json")).save_chain()
+    g.memory_data["metadata"]["date"] = g.memory_data["metadata"]["date"].isoformat()
+    chain.chain_file = str(tmp_path / "sub" / "chain.json")          # add_memory persists after every block from here on
+    hashes = []
+    for i in range(4):
+        h = chain.add_memory(synth.block(0xC4A1, 10 + i)["memory_data"], responsible_node="node-b" if i % 2 else None)
+        hashes.append(h)
+        b = chain.get_latest_block()
+        assert b.hash == h and h.startswith("000") and b.index == i + 1 and b.previous_hash == chain.chain[-2].hash
+        assert b.responsible_node == ("node-b" if i % 2 else "node-a") and b.proposer_node == "node-a"
+        probe = co.Block(b.index, b.timestamp, b.memory_data, b.previous_hash, b.responsible_node, b.proposer_node)
+        co.mine(probe, 3)                                # the oracle's nonce loop starts from 0 like MemoryBlock.mine_block
+        assert (probe.nonce, probe.hash) == (b.nonce, b.hash)
+    assert chain.validate_chain() is True and co.validate(chain.chain) == (True, -1, 0)
+    on_disk = json.load(open(chain.chain_file))
+    assert on_disk == json.loads(json.dumps(chain.serialize_chain())) and len(on_disk) == 5
+    assert open(chain.chain_file).read() == json.dumps(chain.serialize_chain(), indent=2)
+    again = mc.MemoryChain(node_id="node-c", chain_file=chain.chain_file)
+    assert again.load_chain() is True and [b.hash for b in again.chain] == [g.hash] + hashes and again.validate_chain() is True
+    assert mc.MemoryChain(chain_file=str(tmp_path / "missing.json")).load_chain() is False
+    (tmp_path / "bad.json").write_text("{not json")
+    assert mc.MemoryChain(chain_file=str(tmp_path / "bad.json")).load_chain() is False
