@@ -216,12 +216,23 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
     if (!(n_ent == 1 && ent[0].x == 0xFFFFFFFFu)) {
       // the usual case: walk the record's header directory (one entry per line with a colon: interned key, stripped value span)
       uint32_t first_key[FEI_MAX_SLOTS], val_off[FEI_MAX_SLOTS], val_len[FEI_MAX_SLOTS];
+      uint32_t any_mask = 0;                                   // mode-2 slots ("any header value", utils.py:333-336) already accumulated
       for (uint32_t j = 0; j < n_ent; ++j) {
         const uint2 e = ent[j];
         const uint32_t kid = e.x & 0xFFFFu;
         uint32_t km = a.key_lut[kid];
         while (km) {
           int s = __ffs(km) - 1; km &= km - 1;
+          if (slots[s].mode == 2) {
+            // every value of the headers dict: a line counts unless a later line assigns the same key again
+            bool overridden = false;
+            for (uint32_t k = j + 1; k < n_ent && !overridden; ++k) overridden = (ent[k].x & 0xFFFFu) == kid;
+            if (overridden) continue;
+            const uint32_t acc = dfa_run_at(a.prog, slots[s].off_val_dfa, a.prog_in_smem, h + e.y, e.x >> 16);
+            slot_acc[s] = (any_mask >> s & 1u) ? (slot_acc[s] | acc) : acc;
+            any_mask |= 1u << s;
+            continue;
+          }
           if (slots[s].mode == 0) {                            // first key that lower()-equals the field (search.py:121-122)
             if (!(have_first >> s & 1)) { have_first |= 1u << s; first_key[s] = kid; }
             else if (first_key[s] != kid) continue;            // a different spelling of the key: not the dict entry we read
@@ -234,6 +245,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
         int s = __ffs(m) - 1; m &= m - 1;
         slot_acc[s] = dfa_run_at(a.prog, slots[s].off_val_dfa, a.prog_in_smem, h + val_off[s], val_len[s]);
       }
+      present |= any_mask;
     } else {
     // header text longer than a directory span can address: split / strip it here
     DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
@@ -248,6 +260,26 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
         uint32_t km = dfa_run(keyd, ka, (uint32_t)(kb - ka));
         while (km) {
           int s = __ffs(km) - 1; km &= km - 1;
+          if (slots[s].mode == 2) {
+            // every value of the headers dict: this line counts unless a later line assigns the same (stripped) key again
+            bool overridden = false;
+            for (const uint8_t* q = eol + 1; q < hend && !overridden;) {
+              const uint8_t* e2 = q; const uint8_t* c2 = nullptr;
+              while (e2 < hend && *e2 != '\n') { if (!c2 && *e2 == ':') c2 = e2; ++e2; }
+              if (c2) {
+                const uint8_t* k2a = q; const uint8_t* k2b = c2; strip_span(k2a, k2b);
+                bool same = (k2b - k2a) == (kb - ka);
+                for (uint32_t k = 0; same && k < (uint32_t)(kb - ka); ++k) same = k2a[k] == ka[k];
+                overridden = same;
+              }
+              q = e2 + 1;
+            }
+            if (overridden) continue;
+            const uint32_t acc = dfa_run(dfa_view(a.prog, slots[s].off_val_dfa), va, (uint32_t)(vb - va));
+            slot_acc[s] = (present >> s & 1u) ? (slot_acc[s] | acc) : acc;
+            present |= 1u << s;
+            continue;
+          }
           if (slots[s].mode == 0) {                            // first key that lower()-equals the field (search.py:121-122)
             if (!(have_first >> s & 1)) { have_first |= 1u << s; first_off[s] = (uint32_t)(ka - h); first_len[s] = (uint32_t)(kb - ka); }
             else {

@@ -129,3 +129,40 @@ def list_memories(folder: str, status: str = "cur", include_content: bool = Fals
     from .. import packer
     seg = packer.read_segment(MEMDIR_BASE, folder, status)
     return [packer.memory_dict(r, include_content) for r in seg]
+
+
+def search_memories(query: str, folders: List[str] = None, statuses: List[str] = None,
+                    headers_only: bool = False) -> List[Dict[str, Any]]:
+    """The reference's simple substring search (utils.py:299-352): `query.lower()` in any header value (lower-cased),
+    else -- unless `headers_only` -- in the content.  One GPU pass: an "any header value" slot (one automaton run per value
+    of the record's headers dict) and a content condition as two queries, unioned per (folder, status) in listing order.
+    Hits lose `content` for a 100-character `content_preview`, exactly as there."""
+    import numpy as np
+    from .. import packer
+    from ..program import C_BODY, C_SLOT, Cond, ProgramBuilder
+    from ..regexc import Pattern
+    low = query.lower()
+    pm = packer.packed()
+    ranges = pm.ranges(folders, statuses)
+    pm.report_skipped(folders, statuses)
+    if pm.arrays.get("any_lower_inexact"):
+        raise NotImplementedError("corpus holds U+0130 / capital sigma: str.lower() on those records is context dependent; "
+                                  "the substring search is refused rather than answered inexactly")
+    pb = ProgramBuilder()
+    pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", low), field="", mode=2)])
+    if not headers_only:
+        pb.add_query([Cond(C_BODY, pattern=Pattern("contains", low))])
+    nq = 1 if headers_only else 2
+    per_query = [h.astype(np.int64) for h in pm.corpus.scan_hits(pb.build(), nq)]
+    hits = per_query[0] if nq == 1 else np.union1d(per_query[0], per_query[1])       # sorted = listing order inside a segment
+    results = []
+    for a, b in ranges:
+        lo, hi = np.searchsorted(hits, a), np.searchsorted(hits, b)
+        for i in hits[lo:hi].tolist():
+            memory = packer.memory_dict(pm.recs[i], True)
+            if not headers_only:
+                content = memory["content"]
+                memory["content_preview"] = content[:100] + "..." if len(content) > 100 else content
+                del memory["content"]
+            results.append(memory)
+    return results

@@ -32,7 +32,7 @@ class Cond:
     pattern: Optional[Pattern] = None
     negate: bool = False
     field: str = ""              # header field name (slot)
-    mode: int = 0                # slot: 0 = case-insensitive first key, 1 = exact key
+    mode: int = 0                # slot: 0 = case-insensitive first key, 1 = exact key, 2 = any key (OR over all header values)
     empty_if_missing: bool = False
     if_missing: int = 0          # slot: 0/1 result when absent, 2 = next condition is the fallback
     which: int = 0               # name field
@@ -214,7 +214,8 @@ class ProgramBuilder:
             blob.extend(b"\0" * (16 * len(slots)))
             off_key = 0
             if slots:
-                key_pats = [Pattern("exact_equals", f) if mode == 1 else Pattern("equals", f) for f, mode, _e in slots]
+                key_pats = [Pattern("regex", "", 0) if mode == 2 else Pattern("exact_equals", f) if mode == 1 else Pattern("equals", f)
+                            for f, mode, _e in slots]
                 off_key = serialize_dfa(compile_patterns(key_pats), blob)          # only run over the key dictionary (k_key_lut)
                 for si, (f, mode, empty) in enumerate(slots):
                     off_val = serialize_dfa(slot_dfas[si].compile(), blob, head_direct)

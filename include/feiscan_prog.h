@@ -87,7 +87,9 @@ typedef struct fei_prog_query { uint32_t cond_begin, cond_end, reserved0, reserv
 
 typedef struct fei_prog_slot {           /* 16 bytes */
   uint32_t mode;                         /* 0: first key with key.lower()==field.lower(), last value of that exact key (search.py:121-132)
-                                            1: exact key, last value (search.py:117-118 "Status"; filter.py:90-91)                       */
+                                            1: exact key, last value (search.py:117-118 "Status"; filter.py:90-91)
+                                            2: every key: OR over the values of the headers dict (utils.py:333-336, the legacy
+                                               substring search); the key pattern of such a slot matches every key                      */
   uint32_t off_val_dfa;
   uint32_t empty_if_missing;             /* 1: an absent header reads as "" (headers.get("Status", ""), search.py:118)                   */
   uint32_t reserved;

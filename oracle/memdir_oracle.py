@@ -264,3 +264,26 @@ def run_filters(memories: Sequence[Dict[str, Any]], filters: Sequence[Dict[str, 
                                      "subject": mem["headers"].get("Subject", "No subject"), "filters_applied": applied})
     stats["memories_modified"] = len(touched)
     return stats
+
+
+def legacy_search(memories: Sequence[Dict[str, Any]], query: str, headers_only: bool = False) -> List[Dict[str, Any]]:
+    """memdir_tools.utils.search_memories (utils.py:299-352) on an already listed sequence (include_content=True):
+    case-insensitive substring in any header value, else in the content; hits lose `content` for a 100-character preview."""
+    out = []
+    for memory in memories:
+        memory = dict(memory)
+        found = False
+        for _key, value in memory["headers"].items():
+            if query.lower() in value.lower():
+                found = True
+                break
+        if not found and not headers_only and "content" in memory:
+            if query.lower() in memory["content"].lower():
+                found = True
+        if found:
+            if "content" in memory and not headers_only:
+                c = memory["content"]
+                memory["content_preview"] = c[:100] + "..." if len(c) > 100 else c
+                del memory["content"]
+            out.append(memory)
+    return out

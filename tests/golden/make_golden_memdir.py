@@ -102,6 +102,14 @@ FILTERS_EXTRA = [
 ]
 
 
+# memdir_tools.utils.search_memories (the legacy substring search, utils.py:299-352): (query, folders, statuses, headers_only)
+LEGACY = [
+    ("python", None, None, False), ("python", None, None, True), ("", None, None, True), ("KELVIN", None, None, False),
+    ("learning", [""], ["cur", "new"], False), ("beta", None, ["new", "cur"], True), ("no such words anywhere", None, None, False),
+    ("high", [".Projects", ""], None, True), ("caf\u00e9", None, None, False), (":", None, None, True),
+]
+
+
 def build_corpus(base: str):
     sys.path.insert(0, REPO)
     from fei_b200 import synth
@@ -164,6 +172,12 @@ def make_memdir(scratch: str, import_reference):
         q = rs.parse_search_args(s)
         out["parse"].append({"input": s, "conditions": q.conditions, "sort_by": q.sort_by, "sort_reverse": q.sort_reverse,
                              "limit": q.limit, "offset": q.offset, "include_content": q.include_content})
+    out["legacy"] = []
+    for query, folders, statuses, headers_only in LEGACY:
+        res = ru.search_memories(query, folders, statuses, headers_only)
+        out["legacy"].append({"query": query, "folders": folders, "statuses": statuses, "headers_only": headers_only,
+                              "result": [key_of(m) for m in res], "previews": [m.get("content_preview") for m in res][:4],
+                              "has_content_key": ["content" in m for m in res][:4]})
     # filters: default set + extras, dry run, several status selections
     for statuses in (None, ["cur", "new", "tmp"], ["cur"]):
         mgr = rf.create_default_filters()

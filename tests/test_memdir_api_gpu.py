@@ -184,3 +184,20 @@ def test_incremental_sync_after_flag_and_move(gpu, tmp_path, capsys):
         assert got_flags == list("FRS")
     finally:
         U.set_memdir_base(old)
+
+
+def test_legacy_substring_search(api):
+    """memdir_tools.utils.search_memories (utils.py:299-352): any header value / content substring, previews."""
+    from fei_b200.memdir_tools import utils as U
+    base, g = api
+    assert g["legacy"]
+    for case in g["legacy"]:
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = U.search_memories(case["query"], case["folders"], case["statuses"], case["headers_only"])
+            mems = mo.listing(base, case["folders"], case["statuses"], True)
+        want = mo.legacy_search(mems, case["query"], case["headers_only"])
+        assert [key_of(m) for m in res] == [key_of(m) for m in want], case
+        assert same_modulo_ties([key_of(m) for m in res], case["result"]), case
+        for a, b in zip(res, want):
+            assert a.get("content_preview") == b.get("content_preview") and ("content" in a) == ("content" in b) and a["headers"] == b["headers"]
+        assert [("content" in m) for m in res][:4] == case["has_content_key"], case

@@ -188,6 +188,13 @@ def test_adversarial_records_header_parser_and_unicode(gpu):
         got = np.nonzero(c.scan_masks(pb.build()))[0].tolist()
         want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
         assert got == want, conds
+    # "any header value" slots (mode 2: the legacy substring search, utils.py:333-336): OR over the values of the headers
+    # dict -- a repeated key only counts with its last value -- through the directory walk and the in-scan text parser
+    for q in ["python", "a,b", "lower", "final", "big one", "x" * 300, "", "spaced out", "emptykey", "huge"]:
+        pb = ProgramBuilder(); pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", q), field="", mode=2)])
+        got = np.nonzero(c.scan_masks(pb.build()))[0].tolist()
+        want = [i for i, m in enumerate(mems) if any(q in v.lower() for v in m["headers"].values())]
+        assert got == want, q
 
 
 def test_filter_semantics_negate_and_missing(corpus3k):
