@@ -4,16 +4,30 @@ the CLIs) run the hot path on the GPU without any source change:
     import fei_b200.dropin; fei_b200.dropin.install()
 
 replaces  memdir_tools.search.search_memories          (search.py:337)
+          memdir_tools.utils.search_memories           (utils.py:299, the legacy substring search)
           memdir_tools.filter.FilterManager.process_memories / run_filters   (filter.py:188, :311)
           memdir_tools.filter.MemoryFilter.matches     (filter.py:67)
           memdir_tools.memorychain.MemoryChain.validate_chain                (memorychain.py:596)
-and adds  memdir_tools.filter.apply_filters.
+and adds  memdir_tools.filter.apply_filters.  Names other modules already imported (`from memdir_tools.search import
+search_memories` in server.py / cli.py, the package's own re-exports) are rebound too, by identity.
 Everything else of the reference (SearchQuery objects, MemoryFilter objects, block classes, servers) is used as is:
 the GPU layer only reads their public attributes."""
 from __future__ import annotations
 
 import importlib
+import sys
 from typing import Any
+
+
+def _rebind(orig: Any, new: Any) -> None:
+    """Point every module-level name that still holds `orig` (a `from x import f` done before install) at `new`."""
+    for mod in list(sys.modules.values()):
+        d = getattr(mod, "__dict__", None)
+        if not d:
+            continue
+        for name, val in list(d.items()):
+            if val is orig:
+                d[name] = new
 
 
 def install(package: str = "memdir_tools") -> None:
@@ -56,9 +70,17 @@ def install(package: str = "memdir_tools") -> None:
             filters = _gpu_manager(filters)
         return gfilter.apply_filters(filters, folders, statuses, dry_run)
 
+    def legacy_search_memories(query, folders=None, statuses=None, headers_only=False):
+        _sync_base()
+        return gutils.search_memories(query, folders, statuses, headers_only)
+
+    _rebind(ref_search.search_memories, search_memories)
     ref_search.search_memories = search_memories
+    _rebind(ref_utils.search_memories, legacy_search_memories)
+    ref_utils.search_memories = legacy_search_memories
     ref_filter.FilterManager.process_memories = process_memories
     ref_filter.MemoryFilter.matches = matches
+    _rebind(ref_filter.run_filters, run_filters)
     ref_filter.run_filters = run_filters
     ref_filter.apply_filters = apply_filters
     try:

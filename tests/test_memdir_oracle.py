@@ -121,6 +121,8 @@ def test_dropin_install_patches_the_reference_package():
         "assert S.search_memories.__module__ == 'fei_b200.dropin' and F.run_filters.__module__ == 'fei_b200.dropin';"
         "assert F.FilterManager.process_memories.__module__ == 'fei_b200.dropin' and hasattr(F, 'apply_filters');"
         "assert M.MemoryChain.validate_chain.__module__ == 'fei_b200.memdir_tools.memorychain';"
+        "import memdir_tools as P, memdir_tools.utils as U;"
+        "assert P.search_memories is S.search_memories and U.search_memories.__module__ == 'fei_b200.dropin';"   # names imported before install() are rebound
         "q = S.parse_search_args('#python +F'); assert len(q.conditions) == 2; print('patched')"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
