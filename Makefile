@@ -14,8 +14,10 @@ OBJS      := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(CU_SRCS)) $(patsubst $(SRC)/
 HDRS      := $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.cuh) $(wildcard include/*.h)
 LIB       := fei_b200/libfeiscan.so
 ORACLE_LIB := oracle/libchain_oracle.so
+FASTCOLS  := fei_b200/_fastcols.so
+PY_INC    := $(shell python3 -c "import sysconfig; print('-I' + sysconfig.get_paths()['include'])")
 
-all: $(LIB) $(ORACLE_LIB)
+all: $(LIB) $(ORACLE_LIB) $(FASTCOLS)
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -31,7 +33,11 @@ $(LIB): $(OBJS)
 $(ORACLE_LIB): oracle/chain_oracle.c
 	$(CC) -O2 -fPIC -shared -Wall -o $@ $<
 
+# CPython helper for the Python host layer (attribute marshalling of block objects); host glue, no compute
+$(FASTCOLS): fei_b200/_fastcols.c
+	$(CC) -O2 -fPIC -shared -Wall $(PY_INC) -o $@ $<
+
 clean:
-	rm -rf build $(LIB) $(ORACLE_LIB)
+	rm -rf build $(LIB) $(ORACLE_LIB) $(FASTCOLS)
 
 .PHONY: all clean

@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--entries", type=int, default=10_000_000, help="synthetic Memdir entries per GPU")
     ap.add_argument("--e2e-entries", type=int, default=1_000_000)
+    ap.add_argument("--api-files", type=int, default=20_000, help="files of the on-disk Memdir for the Python-API extra")
     ap.add_argument("--chain-blocks", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=60000)
     ap.add_argument("--no-extra", action="store_true")
@@ -399,6 +400,42 @@ def run_e2e(args, corpus, prog, nq, lib, _abi):
             "path": "pinned host arrays -> fei_corpus_load (H2D + tiling kernels) -> fei_scan_hits (k_body + compaction) -> 32 ordered hit lists D2H"}
 
 
+def api_on_disk(n_files: int):
+    import contextlib, io, shutil, tempfile
+    from fei_b200 import packer, synth
+    from fei_b200.memdir_tools import filter as gfilter, search as gsearch, utils as gutils
+    from oracle import memdir_oracle as mo
+    scratch = tempfile.mkdtemp(prefix="feiscan_bench_")
+    try:
+        base = os.path.join(scratch, "Memdir")
+        t0 = time.perf_counter()
+        synth.write_memdir(base, [synth.record(SEED, i) for i in range(n_files)])
+        write_s = time.perf_counter() - t0
+        gutils.set_memdir_base(base)
+        q = gsearch.SearchQuery(); q.add_condition("content", "matches", r"kubernetes.*docker|docker.*kubernetes"); q.add_condition("Tags", "has_tag", "python")
+        q.with_content(True)
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink):
+            t0 = time.perf_counter(); cold = gsearch.search_memories(q); cold_s = time.perf_counter() - t0
+            warm = []
+            for _ in range(5):
+                t0 = time.perf_counter(); res = gsearch.search_memories(q); warm.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); stats = gfilter.apply_filters(dry_run=True); filt_s = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            mems = mo.listing(base, None, None, True)
+            want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in (("content", "matches", r"kubernetes.*docker|docker.*kubernetes"), ("Tags", "has_tag", "python"))])
+            cpu_s = time.perf_counter() - t0
+        assert len(cold) == len(res)
+        return {"files": n_files, "write_tree_s": write_s, "query": "content matches kubernetes.*docker|docker.*kubernetes AND Tags has_tag python",
+                "search_memories_cold_s": cold_s, "search_memories_warm_ms": float(np.median(warm)) * 1e3, "hits": len(res),
+                "apply_filters_default_dry_run_warm_ms": filt_s * 1e3, "apply_filters_matched": stats.get("memories_matched", stats.get("matched")),
+                "cpu_oracle_same_search_s": cpu_s, "cpu_oracle_note": "oracle: lists, reads, parses and matches every file on one host core, as the reference does on every call",
+                "memories_per_s_warm": n_files / float(np.median(warm)), "memories_per_s_cold": n_files / cold_s, "memories_per_s_cpu_oracle": n_files / cpu_s}
+    finally:
+        packer._cache.clear()
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
 def run_extra(args, corpus, st, peak, lib, _abi):
     from fei_b200.program import C_BODY, C_DATE_CMP, C_FLAGS, C_SLOT, CMP, Cond, ProgramBuilder
     from fei_b200.regexc import Pattern
@@ -495,6 +532,13 @@ def run_extra(args, corpus, st, peak, lib, _abi):
                      "frac": body_bytes / b0 / 1e9 / peak, "algorithmic_bytes_per_launch": int(body_bytes)},
         "query": "content matches quagga.*zebra|zebra.*quagga (no record matches: no early exit)",
     }
+    # ---- the drop-in entry points end to end on an on-disk Memdir: search_memories() and apply_filters() of the reference-shaped
+    #      Python API (cold = listing + reading + packing + upload + scan; warm = the packed corpus is reused), next to the oracle
+    #      (the reference's algorithm: list, read, parse and match every file on one host core)
+    try:
+        out["python_api_on_disk"] = api_on_disk(args.api_files)
+    except Exception as e:                                     # a full scratch disk must not cost the headline line
+        out["python_api_on_disk"] = {"error": f"{type(e).__name__}: {e}"}
     # ---- configs[3]: validate_chain over synthetic blocks resident on the device
     ch = C.c_void_p()
     _abi.check(lib.fei_chain_create(C.byref(ch)))

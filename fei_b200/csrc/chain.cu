@@ -18,6 +18,9 @@
 #include "chain_json.h"
 #include <vector>
 #include <string.h>
+#include <mutex>
+#include <chrono>
+#include <stdlib.h>
 #include <stdio.h>
 
 namespace fei {
@@ -345,6 +348,9 @@ static int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s) {
 
 using namespace fei;
 
+static std::mutex g_scratch_mu;
+static fei_chain* g_scratch = nullptr;
+
 extern "C" int fei_chain_create(fei_chain** out) {
   if (!out) { set_error("null out"); return FEI_E_BADARG; }
   FEI_TRY(require_ready());
@@ -420,12 +426,26 @@ extern "C" int fei_chain_validate_msgs(const uint8_t* msgs, const uint64_t* msg_
                                        const uint8_t* prev, const uint64_t* prev_off,
                                        uint64_t n, uint64_t first_index,
                                        int64_t* first_bad, int32_t* bad_kind, uint8_t* digests) {
-  fei_chain* ch = nullptr;
-  FEI_TRY(fei_chain_create(&ch));
-  int rc = fei_chain_load_msgs(ch, msgs, msg_off, hash, hash_off, prev, prev_off, n, first_index);
-  if (rc == FEI_OK) rc = fei_chain_validate(ch, first_bad, bad_kind, digests, nullptr);
-  fei_chain_destroy(ch);
+  // one-shot calls (MemoryChain.validate_chain on Python block objects, receive_chain_update) reuse one scratch chain:
+  // its device buffers only grow, so a validation costs copies and kernels, not a dozen cudaMalloc / cudaFree pairs
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  if (!g_scratch) FEI_TRY(fei_chain_create(&g_scratch));
+  const bool dbg = getenv("FEI_DEBUG_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = fei_chain_load_msgs(g_scratch, msgs, msg_off, hash, hash_off, prev, prev_off, n, first_index);
+  auto t1 = std::chrono::steady_clock::now();
+  if (rc == FEI_OK) rc = fei_chain_validate(g_scratch, first_bad, bad_kind, digests, nullptr);
+  if (dbg) fprintf(stderr, "[feiscan] chain load (H2D + pad + links): %.2f ms, validate: %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+  if (g_scratch->padded.bytes + g_scratch->msgs.bytes > (2ull << 30)) { fei_chain_destroy(g_scratch); g_scratch = nullptr; }   // do not sit on GBs
   return rc;
+}
+
+namespace fei {
+void chain_release_scratch() {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  if (g_scratch) { fei_chain_destroy(g_scratch); g_scratch = nullptr; }
+}
 }
 
 extern "C" int fei_chain_validate_cols(const fei_json_col* cols, const uint8_t* hash, const uint64_t* hash_off,
@@ -435,7 +455,11 @@ extern "C" int fei_chain_validate_cols(const fei_json_col* cols, const uint8_t* 
   FEI_TRY(require_ready());
   if (!cols || !hash_off) { set_error("null argument"); return FEI_E_BADARG; }
   std::vector<uint8_t> msgs; std::vector<uint64_t> off;
+  const bool dbg = getenv("FEI_DEBUG_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   FEI_TRY(serialize_chain_cols(cols, n, msgs, off));
+  if (dbg) fprintf(stderr, "[feiscan] serialize_chain_cols: %.2f ms for %llu blocks, %zu bytes\n",
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), (unsigned long long)n, msgs.size());
   if (msg_off_out) memcpy(msg_off_out, off.data(), (n + 1) * sizeof(uint64_t));
   if (msgs_out) {
     if (msgs.size() > msgs_cap) { set_error("message buffer too small: need %zu bytes", msgs.size()); return FEI_E_CAPACITY; }

@@ -8,6 +8,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 #include <algorithm>
@@ -20,10 +21,11 @@ static const char* const kKeys[FEI_CHAIN_NCOLS] = {
 
 namespace {
 
+// Raw writer: the caller guarantees room (block_bound) before every block, so a byte costs a store, not a capacity check.
 struct Out {
-  std::vector<uint8_t>& v;
-  void put(char c) { v.push_back((uint8_t)c); }
-  void put(const char* s, size_t n) { v.insert(v.end(), (const uint8_t*)s, (const uint8_t*)s + n); }
+  uint8_t* p;
+  void put(char c) { *p++ = (uint8_t)c; }
+  void put(const char* s, size_t n) { memcpy(p, s, n); p += n; }
   void lit(const char* s) { put(s, strlen(s)); }
 };
 
@@ -156,25 +158,48 @@ int put_block(Out& o, const fei_json_col* cols, uint64_t i) {
 
 }  // namespace
 
+// upper bound of one block's text: every string byte can become a 6-byte \\uXXXX escape (a 4-byte character two of them)
+static size_t block_bound(const fei_json_col* cols, uint64_t i) {
+  size_t b = 2 + FEI_CHAIN_NCOLS * 56;                          // braces; per field: ", " + quoted key (<= 18) + ": " + a number / literal (<= 26 chars)
+  for (int k = 0; k < FEI_CHAIN_NCOLS; ++k) {
+    const fei_json_col& c = cols[k];
+    const int tag = c.tag ? c.tag[i] : c.uniform_tag;
+    if (tag == FEI_J_STR || tag == FEI_J_BIGINT) b += 6 * (size_t)(c.str_off[i + 1] - c.str_off[i]) + 2;
+  }
+  return b;
+}
+
 int serialize_chain_cols(const fei_json_col* cols, uint64_t n, std::vector<uint8_t>& msgs, std::vector<uint64_t>& off) {
   for (int k = 0; k < FEI_CHAIN_NCOLS; ++k) {
     const fei_json_col& c = cols[k];
     if (!c.tag && (c.uniform_tag < FEI_J_NULL || c.uniform_tag > FEI_J_BIGINT)) { set_error("column %d (%s): bad uniform tag %d", k, kKeys[k], c.uniform_tag); return FEI_E_BADARG; }
   }
   unsigned hw = std::thread::hardware_concurrency();
-  unsigned nt = (unsigned)std::min<uint64_t>(std::max(1u, hw), std::max<uint64_t>(1, n / 4096));
-  std::vector<std::vector<uint8_t>> parts(nt);
+  unsigned nt = (unsigned)std::min<uint64_t>(std::min(std::max(1u, hw), 32u), std::max<uint64_t>(1, n / 4096));
+  // each worker writes into its own malloc'ed buffer (no zero fill), grown by doubling with the block bound as the guard
+  struct Part { uint8_t* buf = nullptr; size_t len = 0, cap = 0; };
+  std::vector<Part> parts(nt);
   std::vector<int> rc(nt, 0);
   off.assign(n + 1, 0);
   auto work = [&](unsigned t) {
     uint64_t lo = n * t / nt, hi = n * (t + 1) / nt;
-    std::vector<uint8_t>& buf = parts[t];
-    buf.reserve((hi - lo) * 384);
-    Out o{buf};
+    Part& pt = parts[t];
+    pt.cap = (hi - lo) * 400 + 4096;
+    pt.buf = (uint8_t*)malloc(pt.cap);
+    if (!pt.buf) { rc[t] = -2; return; }
     for (uint64_t i = lo; i < hi; ++i) {
-      size_t before = buf.size();
+      const size_t need = block_bound(cols, i);
+      if (pt.len + need > pt.cap) {
+        size_t ncap = std::max(pt.cap * 2, pt.len + need);
+        uint8_t* nb = (uint8_t*)realloc(pt.buf, ncap);
+        if (!nb) { rc[t] = -2; return; }
+        pt.buf = nb; pt.cap = ncap;
+      }
+      Out o{pt.buf + pt.len};
       if (put_block(o, cols, i) != 0) { rc[t] = -1; return; }
-      off[i + 1] = buf.size() - before;   // length for now; prefix-summed below
+      const size_t wrote = (size_t)(o.p - (pt.buf + pt.len));
+      off[i + 1] = wrote;                                       // length for now; prefix-summed below
+      pt.len += wrote;
     }
   };
   if (nt == 1) work(0);
@@ -183,12 +208,18 @@ int serialize_chain_cols(const fei_json_col* cols, uint64_t n, std::vector<uint8
     for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
     for (auto& x : th) x.join();
   }
-  for (unsigned t = 0; t < nt; ++t) if (rc[t]) { set_error("unsupported JSON tag in chain columns"); return FEI_E_BADARG; }
+  int bad = 0;
+  for (unsigned t = 0; t < nt; ++t) if (rc[t]) bad = rc[t];
+  if (bad) {
+    for (auto& pt : parts) free(pt.buf);
+    if (bad == -2) { set_error("out of host memory serialising the chain"); return FEI_E_CAPACITY; }
+    set_error("unsupported JSON tag in chain columns"); return FEI_E_BADARG;
+  }
   for (uint64_t i = 0; i < n; ++i) off[i + 1] += off[i];
   msgs.resize(off[n]);
   {
     std::vector<std::thread> th;
-    auto copy = [&](unsigned t) { uint64_t lo = n * t / nt; if (!parts[t].empty()) memcpy(msgs.data() + off[lo], parts[t].data(), parts[t].size()); };
+    auto copy = [&](unsigned t) { uint64_t lo = n * t / nt; if (parts[t].len) memcpy(msgs.data() + off[lo], parts[t].buf, parts[t].len); free(parts[t].buf); };
     if (nt == 1) copy(0);
     else { for (unsigned t = 0; t < nt; ++t) th.emplace_back(copy, t); for (auto& x : th) x.join(); }
   }

@@ -84,7 +84,10 @@ extern "C" int fei_init(int device) {
   return FEI_OK;
 }
 
+namespace fei { void chain_release_scratch(); }
+
 extern "C" int fei_shutdown(void) {
+  fei::chain_release_scratch();
   Context& c = ctx();
   if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
   if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); c.copy_stream = nullptr; }

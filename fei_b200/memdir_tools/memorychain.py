@@ -28,6 +28,11 @@ import numpy as np
 
 from .. import _abi
 
+try:                                    # CPython helper built by `make` (fei_b200/_fastcols.c); host glue only: without it the
+    from .. import _fastcols            # pure-Python marshalling below does the same job, slower
+except ImportError:                     # pragma: no cover
+    _fastcols = None
+
 logger = logging.getLogger("memorychain")     # same logger name as the reference (:43)
 
 CHAIN_FILE = os.path.join(os.path.expanduser("~"), ".memdir", "memorychain.json")     # reference :49
@@ -166,6 +171,52 @@ def _extract(blocks: Sequence[Any]) -> Optional[List[tuple]]:
     return cols
 
 
+def _col_from_native(t: tuple) -> _Col:
+    col = _Col()
+    kind = t[0]
+    if kind == 1:
+        col.uniform = _abi.J_STR
+        col.blob = np.frombuffer(t[1], dtype=np.uint8) if t[1] else np.zeros(1, dtype=np.uint8)
+        col.off = np.frombuffer(t[2], dtype=np.uint64)
+    elif kind == 2:
+        col.uniform = _abi.J_INT; col.num = np.frombuffer(t[1], dtype=np.uint64)
+    elif kind == 3:
+        col.uniform = _abi.J_FLOAT; col.num = np.frombuffer(t[1], dtype=np.uint64)
+    else:
+        col.uniform = _abi.J_NULL
+    return col
+
+
+_NATIVE_NAMES = {"memory_id": "memory_data"}          # hashed field -> instance attribute it is read from
+
+
+def chain_columns_native(blocks: Sequence[Any]) -> Optional[Tuple[List[_Col], np.ndarray, np.ndarray]]:
+    """The ten hashed columns + the stored-hash blob through the C helper, or None when the blocks are not plain enough
+    for it (then chain_columns decides).  Same class test as _extract: one class, ordinary instance attributes."""
+    if _fastcols is None or not blocks:
+        return None
+    kinds = set(map(type, blocks))
+    if len(kinds) != 1:
+        return None
+    cls = kinds.pop()
+    hash_key = "hash"
+    if isinstance(getattr(cls, "hash", None), property):
+        if cls is not MemoryBlock:
+            return None
+        hash_key = "_hash"
+    elif hasattr(cls, "hash"):
+        return None
+    if any(hasattr(cls, k) for k in _DIRECT + _OPTIONAL) or hasattr(cls, "__getattr__"):
+        return None
+    names = tuple(_NATIVE_NAMES.get(k, k) for k in HASHED_FIELDS) + (hash_key,)
+    out = _fastcols.columns(blocks if isinstance(blocks, list) else list(blocks), names, HASHED_FIELDS.index("memory_id"))
+    if out is None or out[-1][0] != 1:                  # unusual values somewhere / hashes not (all) strings yet
+        return None
+    cols = [_col_from_native(t) for t in out[:-1]]
+    h = out[-1]
+    return cols, (np.frombuffer(h[1], dtype=np.uint8) if h[1] else np.zeros(1, dtype=np.uint8)), np.frombuffer(h[2], dtype=np.uint64)
+
+
 def chain_columns(blocks: Sequence[Any]) -> Tuple[List[_Col], List[Any]]:
     """Ten hashed columns (sorted key order) + the stored ``hash`` attributes."""
     fast = _extract(blocks) if blocks else None
@@ -219,11 +270,15 @@ def hash_and_validate(blocks: Sequence[Any], first_index: int = 0, want_digests:
     """
     _abi.init()
     n = len(blocks)
-    cols, stored = chain_columns(blocks)
-    if not all(isinstance(h, str) for h in stored):
-        # `!=` between arbitrary objects (None == None ...) has no string form
-        raise NotImplementedError("block.hash must be a str for GPU validation")
-    hash_blob, hash_off = _str_blob(stored)
+    native = chain_columns_native(blocks)
+    if native is not None:
+        cols, hash_blob, hash_off = native
+    else:
+        cols, stored = chain_columns(blocks)
+        if not all(isinstance(h, str) for h in stored):
+            # `!=` between arbitrary objects (None == None ...) has no string form
+            raise NotImplementedError("block.hash must be a str for GPU validation")
+        hash_blob, hash_off = _str_blob(stored)
     first_bad, kind = C.c_int64(-1), C.c_int32(0)
     digests = np.zeros((n, 32), dtype=np.uint8) if want_digests else None
     arr = _cols_struct(cols)

@@ -90,3 +90,43 @@ def test_oracle_mining_matches_reference(chain_golden):
         b = co.Block(s["index"], s["timestamp"], s["memory_data"], m["previous_hash"], s["responsible_node"], s["proposer_node"], nonce=m["start_nonce"])
         co.mine(b, m["difficulty"])
         assert (b.nonce, b.hash) == (m["nonce"], m["hash"]), m
+
+
+def test_native_marshalling_equals_python_marshalling(chain_golden):
+    """fei_b200/_fastcols.c (CPython helper) must hand libfeiscan exactly the columns the pure-Python path builds, and step
+    aside (None) for anything unusual."""
+    import numpy as np
+    from fei_b200.memdir_tools import memorychain as mc
+    from tests.chain_util import base_chain
+    if mc._fastcols is None:
+        pytest.skip("_fastcols not built")
+    blocks = base_chain(chain_golden["chains"][0])
+    plain = []
+    for b in blocks:
+        m = mc.MemoryBlock(b.index, b.timestamp, b.memory_data, b.previous_hash, b.responsible_node, b.proposer_node)
+        m.nonce = b.nonce; m.hash = b.hash
+        for k in ("task_state", "difficulty", "solver_node"):
+            setattr(m, k, getattr(b, k, None))
+        plain.append(m)
+    nat = mc.chain_columns_native(plain)
+    assert nat is not None
+    cols, stored = mc.chain_columns(plain)
+    for a, b in zip(nat[0], cols):
+        assert a.uniform == b.uniform
+        for k in ("num", "blob", "off", "tag"):
+            x, y = getattr(a, k), getattr(b, k)
+            assert (x is None) == (y is None) and (x is None or np.array_equal(x, y)), k
+    hb, ho = mc._str_blob(stored)
+    assert np.array_equal(nat[1], hb) and np.array_equal(nat[2], ho)
+    # unusual values: the helper declines, the Python path decides
+    plain[3].nonce = True
+    assert mc.chain_columns_native(plain) is None
+    plain[3].nonce = 1 << 70
+    assert mc.chain_columns_native(plain) is None
+    plain[3].nonce = 0
+    plain[5].previous_hash = "\ud800"
+    assert mc.chain_columns_native(plain) is None
+    plain[5].previous_hash = "0"
+    plain[7].memory_data = {"metadata": None}
+    assert mc.chain_columns_native(plain) is None
+    assert mc.chain_columns_native([co.Block(0, 1.0, {}, "0", "a", "b")]) is None          # __slots__ class: no instance dict
