@@ -592,7 +592,7 @@ def run_extra(args, corpus, st, peak, lib, _abi):
         t0 = time.perf_counter(); ok = chain_obj.validate_chain(); ts.append(time.perf_counter() - t0)
     out["cfg4_validate_chain"]["e2e_python_api"] = {
         "value": (nb_api - 1) / min(ts), "unit": "chain blocks/s", "blocks": nb_api, "valid": bool(ok),
-        "path": "MemoryChain.validate_chain(): attribute marshal in Python -> fei_chain_validate_cols (C++ JSON, H2D, kernel)"}
+        "path": "MemoryChain.validate_chain(): attribute marshal (CPython helper _fastcols) -> fei_chain_validate_cols (C++ JSON, H2D, kernel)"}
     return out
 
 
