@@ -105,13 +105,16 @@ def _ensure_text(rec: Dict[str, Any]) -> None:
 def memory_dict(rec: Dict[str, Any], include_content: bool) -> Dict[str, Any]:
     """The dict list_memories yields (utils.py:234-243); headers parsed on the host for materialisation."""
     _ensure_text(rec)
-    headers: Dict[str, str] = {}
-    if rec["has_sep"]:
-        for line in rec["hdr_text"].strip().split("\n"):
-            k, colon, v = line.partition(":")
-            if colon:
-                headers[k.strip()] = v.strip()
-    mem = {"filename": rec["filename"], "folder": rec["folder"], "status": rec["status"], "headers": headers,
+    headers = rec.get("_headers")                       # parsed once per record; callers get their own copy (they may mutate it)
+    if headers is None:
+        headers = {}
+        if rec["has_sep"]:
+            for line in rec["hdr_text"].strip().split("\n"):
+                k, colon, v = line.partition(":")
+                if colon:
+                    headers[k.strip()] = v.strip()
+        rec["_headers"] = headers
+    mem = {"filename": rec["filename"], "folder": rec["folder"], "status": rec["status"], "headers": dict(headers),
            "metadata": {"timestamp": rec["ts"], "unique_id": rec["uid"], "hostname": rec["host"], "flags": list(rec["flags"]),
                         "date": rec["date"]}}
     if include_content:
