@@ -85,6 +85,7 @@ _SIGS = {
     "fei_scan_hits": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
     "fei_scan_count": (C.c_int, [_P, _P, _U64, _P]),
     "fei_scan_last_timing": (C.c_int, [_P, _P]),
+    "fei_corpus_token_histogram": (C.c_int, [_P, _P, _U64, C.c_uint8, _P, _U64, _P, _P, _P, _U64, _P]),
     "fei_chain_validate_msgs": (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P]),
     "fei_chain_validate_cols": (C.c_int, [_P, _P, _P, _U64, _U64, _P, _P, _P, _P, _U64, _P]),
     "fei_chain_create": (C.c_int, [_P]),

@@ -116,6 +116,17 @@ class Corpus:
         _abi.check(_abi.lib().fei_scan_hits(self._h, prog, len(prog), ptrs, _abi.ptr(cap_arr), _abi.ptr(nh)))
         return [bufs[q][:int(nh[q])] for q in range(nq)]
 
+    def token_histogram(self, prog: bytes, sep: str = ",", cap: int = 32768, blob_cap: int = 1 << 22):
+        """[(token bytes, count, global index of the first record carrying it)] in first-occurrence order
+        (fei_corpus_token_histogram: the tag statistics of folders.py:286-292)."""
+        blob = np.zeros(blob_cap, dtype=np.uint8); off = np.zeros(cap + 1, dtype=np.uint64)
+        cnt = np.zeros(cap, dtype=np.uint64); first = np.zeros(cap, dtype=np.uint64)
+        n = C.c_uint64()
+        _abi.check(_abi.lib().fei_corpus_token_histogram(self._h, prog, len(prog), ord(sep), _abi.ptr(blob), blob_cap, _abi.ptr(off),
+                                                         _abi.ptr(cnt), _abi.ptr(first), cap, C.byref(n)))
+        raw = blob.tobytes()
+        return [(raw[int(off[k]):int(off[k + 1])], int(cnt[k]), int(first[k])) for k in range(n.value)]
+
     def timing(self) -> Dict[str, float]:
         t = _abi.ScanTiming()
         _abi.check(_abi.lib().fei_scan_last_timing(self._h, C.byref(t)))

@@ -28,6 +28,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <algorithm>
 
 namespace fei {
 
@@ -1395,4 +1396,145 @@ extern "C" int fei_scan_last_timing(const fei_corpus* c, fei_scan_timing* out) {
   if (!c || !out) { set_error("null argument"); return FEI_E_BADARG; }
   *out = c->timing;
   return FEI_OK;
+}
+
+// ---------------------------------------------------------------- token histogram of a header field ("next" row 4)
+// MemdirFolderManager.get_folder_stats (memdir_tools/folders.py:286-292):
+//     if "Tags" in memory["headers"]: for tag in [t.strip() for t in headers["Tags"].split(",")]: stats["tags"][tag] += 1
+// One thread per selected record walks the record's header directory for the field (exact key: slot 0 of the program,
+// last line wins), splits the value at `sep`, strips every piece with Python's whitespace set and counts it in a device
+// hash table (64-bit hash, representative spelling = smallest header offset, every piece verified against it in a
+// second pass).  `first` orders the tokens the way the reference's dict does (first record, then position in the value).
+namespace fei {
+constexpr uint32_t kTokSlots = 1u << 16;
+struct TokTable { unsigned long long* tag; unsigned long long* rep; unsigned long long* first; uint32_t* len; uint32_t* count; uint32_t* flag; };
+
+__device__ __forceinline__ unsigned long long tok_hash(const uint8_t* p, uint32_t n) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (uint32_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+  h ^= h >> 31; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+  return h | 1ull;
+}
+
+template <int kPass>
+__global__ void __launch_bounds__(256) k_tok_hist(const uint8_t* __restrict__ hdr, const uint64_t* __restrict__ hdr_off,
+                                                  const uint2* __restrict__ hdir, const uint64_t* __restrict__ hdir_off,
+                                                  const uint32_t* __restrict__ key_lut, const uint32_t* __restrict__ alive, uint64_t n,
+                                                  uint8_t sep, TokTable t) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n || !(alive[i] & 1u)) return;
+  const uint2* ent = hdir + hdir_off[i];
+  const uint32_t n_ent = (uint32_t)(hdir_off[i + 1] - hdir_off[i]);
+  if (n_ent == 1 && ent[0].x == 0xFFFFFFFFu) { atomicOr(t.flag, 4u); return; }      // header parsed from its text: not handled here
+  int last = -1;
+  for (uint32_t j = 0; j < n_ent; ++j) if (key_lut[ent[j].x & 0xFFFFu] & 1u) last = (int)j;      // slot 0, repeated key: last value
+  if (last < 0) return;
+  const uint8_t* v = hdr + hdr_off[i] + ent[last].y;
+  const uint32_t vlen = ent[last].x >> 16;
+  uint32_t pos = 0, idx = 0;
+  for (;;) {                                                     // str.split(sep): k separators -> k + 1 pieces, empty ones included
+    uint32_t end = pos;
+    while (end < vlen && v[end] != sep) ++end;
+    const uint8_t* a = v + pos; const uint8_t* b = v + end;
+    strip_span(a, b);
+    const uint32_t len = (uint32_t)(b - a);
+    const unsigned long long h = tok_hash(a, len);
+    uint32_t s = (uint32_t)(h >> 20) & (kTokSlots - 1);
+    bool placed = false;
+    for (uint32_t probe = 0; probe < kTokSlots / 2 && !placed; ++probe, s = (s + 1) & (kTokSlots - 1)) {
+      unsigned long long cur = t.tag[s];
+      if (cur == 0 && kPass == 0) cur = atomicCAS(t.tag + s, 0ull, h), cur = cur == 0 ? h : cur;
+      if (cur == h) {
+        placed = true;
+        if (kPass == 0) {
+          atomicAdd(t.count + s, 1u);
+          atomicMin(t.rep + s, (unsigned long long)(a - hdr));
+          atomicMin(t.first + s, (unsigned long long)i << 20 | (idx < 0xFFFFFu ? idx : 0xFFFFFu));
+          t.len[s] = len;
+        } else {
+          bool same = t.len[s] == len;
+          const uint8_t* r = hdr + t.rep[s];
+          for (uint32_t k = 0; same && k < len; ++k) same = r[k] == a[k];
+          if (!same) atomicOr(t.flag, 2u);                       // two different pieces with one 64-bit hash
+        }
+      } else if (cur == 0) break;                                // pass 1 only: cannot happen after pass 0
+    }
+    if (!placed) atomicOr(t.flag, 1u);                           // table over-full
+    ++idx;
+    if (end >= vlen) break;
+    pos = end + 1;
+  }
+}
+
+__global__ void k_tok_pack(const uint8_t* __restrict__ hdr, const unsigned long long* __restrict__ rep, const uint32_t* __restrict__ len,
+                           const uint32_t* __restrict__ slots, const uint64_t* __restrict__ out_off, uint32_t n_tok, uint8_t* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_tok) return;
+  const uint32_t s = slots[k];
+  const uint8_t* p = hdr + rep[s];
+  for (uint32_t b = 0; b < len[s]; ++b) out[out_off[k] + b] = p[b];
+}
+}  // namespace fei
+
+extern "C" int fei_corpus_token_histogram(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint8_t sep,
+                                          uint8_t* tok_blob, uint64_t blob_cap, uint64_t* tok_off, uint64_t* tok_count, uint64_t* tok_first,
+                                          uint64_t cap, uint64_t* n_tokens) {
+  if (!c || !n_tokens || !tok_off) { set_error("null argument"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
+  *n_tokens = 0; tok_off[0] = 0;
+  FEI_TRY(run_scan(c, prog, prog_len));
+  fei_prog_hdr h; memcpy(&h, prog, sizeof(h));
+  if (h.n_queries != 1 || h.n_slots < 1) { set_error("token histogram wants one query whose first header field names the column"); return FEI_E_BADARG; }
+  if (c->n == 0) return finish_timing(c, false);
+  if (c->has_text_records || !c->hdir.p) { set_error("corpus holds records whose header is parsed from its text; the token histogram does not handle them"); return FEI_E_UNSUPPORTED; }
+  cudaStream_t s = ctx().stream;
+  DevBuf& tb = c->scan_tmp;
+  const size_t bytes = (size_t)kTokSlots * (8 + 8 + 8 + 4 + 4) + 16;
+  FEI_TRY(tb.ensure(bytes));
+  uint8_t* base = tb.as<uint8_t>();
+  TokTable t{reinterpret_cast<unsigned long long*>(base), reinterpret_cast<unsigned long long*>(base) + kTokSlots, reinterpret_cast<unsigned long long*>(base) + 2 * kTokSlots,
+             reinterpret_cast<uint32_t*>(base + (size_t)kTokSlots * 24), reinterpret_cast<uint32_t*>(base + (size_t)kTokSlots * 28), reinterpret_cast<uint32_t*>(base + (size_t)kTokSlots * 32)};
+  FEI_CUDA(cudaMemsetAsync(base, 0, bytes, s));
+  FEI_CUDA(cudaMemsetAsync(t.rep, 0xFF, (size_t)kTokSlots * 16, s));           // rep and first: ~0 so that atomicMin works
+  const unsigned grid = (unsigned)((c->n + 255) / 256);
+  k_tok_hist<0><<<grid, 256, 0, s>>>(c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(),
+                                     c->hits.as<uint32_t>(), c->n, sep, t);
+  k_tok_hist<1><<<grid, 256, 0, s>>>(c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(),
+                                     c->hits.as<uint32_t>(), c->n, sep, t);
+  std::vector<unsigned long long> tag(kTokSlots), first(kTokSlots);
+  std::vector<uint32_t> len(kTokSlots), count(kTokSlots);
+  uint32_t flag = 0;
+  FEI_CUDA(cudaMemcpyAsync(tag.data(), t.tag, kTokSlots * 8, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaMemcpyAsync(first.data(), t.first, kTokSlots * 8, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaMemcpyAsync(len.data(), t.len, kTokSlots * 4, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaMemcpyAsync(count.data(), t.count, kTokSlots * 4, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaMemcpyAsync(&flag, t.flag, 4, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  FEI_CUDA(cudaGetLastError());
+  if (flag & 4u) { set_error("a selected record's header is parsed from its text; the token histogram does not handle it"); return FEI_E_UNSUPPORTED; }
+  if (flag) { set_error(flag & 1u ? "more than 32768 distinct tokens" : "64-bit hash collision between two tokens"); return FEI_E_UNSUPPORTED; }
+  std::vector<uint32_t> slots;
+  for (uint32_t k = 0; k < kTokSlots; ++k) if (tag[k]) slots.push_back(k);
+  std::sort(slots.begin(), slots.end(), [&](uint32_t a, uint32_t b) { return first[a] < first[b]; });   // the order a dict filled record by record has
+  if (slots.size() > cap) { set_error("token table too small: need %zu entries", slots.size()); return FEI_E_CAPACITY; }
+  std::vector<uint64_t> off(slots.size() + 1, 0);
+  for (size_t k = 0; k < slots.size(); ++k) off[k + 1] = off[k] + len[slots[k]];
+  if (off.back() > blob_cap) { set_error("token buffer too small: need %llu bytes", (unsigned long long)off.back()); return FEI_E_CAPACITY; }
+  if (!slots.empty()) {
+    DevBuf d_slots, d_off, d_out;
+    FEI_TRY(d_slots.ensure(slots.size() * 4)); FEI_TRY(d_off.ensure(off.size() * 8)); FEI_TRY(d_out.ensure(off.back() + 16));
+    FEI_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, s));
+    FEI_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, s));
+    k_tok_pack<<<(unsigned)((slots.size() + 127) / 128), 128, 0, s>>>(c->hdr.as<uint8_t>(), t.rep, t.len, d_slots.as<uint32_t>(), d_off.as<uint64_t>(), (uint32_t)slots.size(), d_out.as<uint8_t>());
+    if (off.back() && tok_blob) FEI_CUDA(cudaMemcpyAsync(tok_blob, d_out.p, off.back(), cudaMemcpyDeviceToHost, s));
+    FEI_CUDA(cudaStreamSynchronize(s));
+    FEI_CUDA(cudaGetLastError());
+  }
+  for (size_t k = 0; k < slots.size(); ++k) {
+    tok_off[k + 1] = off[k + 1];
+    if (tok_count) tok_count[k] = count[slots[k]];
+    if (tok_first) tok_first[k] = (first[slots[k]] >> 20) + c->global_base;
+  }
+  *n_tokens = slots.size();
+  return finish_timing(c, false);
 }

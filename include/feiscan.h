@@ -150,6 +150,19 @@ typedef struct fei_scan_timing {
 } fei_scan_timing;
 int fei_scan_last_timing(const fei_corpus* c, fei_scan_timing* out);
 
+/* Token histogram of one header field over the records a program selects -- the tag statistics of
+ * MemdirFolderManager.get_folder_stats (memdir_tools/folders.py:286-292):
+ *     if "Tags" in memory["headers"]: for tag in [t.strip() for t in memory["headers"]["Tags"].split(",")]: tags[tag] += 1
+ * prog: ONE query; its conditions select the records, its first header field (slot 0; use an exact-key slot with an
+ * always-true pattern) names the column.  sep: the separator byte.  Out, ordered like a dict filled record by record
+ * (first record carrying the token, then position inside the value): token k = tok_blob[tok_off[k] .. tok_off[k+1]),
+ * tok_count[k] occurrences, tok_first[k] = global index of the first record with it.  *n_tokens = entries written.
+ * FEI_E_CAPACITY when cap / blob_cap are too small; FEI_E_UNSUPPORTED for corpora with headers over 64 KiB, more than
+ * 32768 distinct tokens or a 64-bit hash collision (callers then count on the host). */
+int fei_corpus_token_histogram(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint8_t sep,
+                               uint8_t* tok_blob, uint64_t blob_cap, uint64_t* tok_off, uint64_t* tok_count, uint64_t* tok_first,
+                               uint64_t cap, uint64_t* n_tokens);
+
 /* ---- Memorychain validation -----------------------------------------------------
  * Replaces the loop of MemoryChain.validate_chain (memdir_tools/memorychain.py:596-618)
  * and its inline copy in receive_chain_update (:1059-1078):

@@ -287,3 +287,39 @@ def legacy_search(memories: Sequence[Dict[str, Any]], query: str, headers_only: 
                 del memory["content"]
             out.append(memory)
     return out
+
+
+def folder_stats(base: str, folder_path: str, include_subfolders: bool = False) -> Dict[str, Any]:
+    """MemdirFolderManager.get_folder_stats (folders.py:216-318) on the tree at `base`."""
+    folder_path = folder_path.replace("\\", "/").strip("/")
+    all_folders = memdir_folders(base)
+    todo = []
+    if include_subfolders:
+        for folder in all_folders:
+            if folder == folder_path or (folder.startswith(folder_path) and folder != folder_path):
+                todo.append(folder)
+    elif folder_path in all_folders or folder_path == "":
+        todo = [folder_path]
+    stats: Dict[str, Any] = {"folder": folder_path or "Inbox", "total_memories": 0, "memory_counts": {"cur": 0, "new": 0, "tmp": 0},
+                             "flag_counts": {"S": 0, "R": 0, "F": 0, "P": 0}, "tags": {}, "subfolders": [], "newest_memory": None, "oldest_memory": None}
+    for folder in todo:
+        sub = {"folder": folder or "Inbox", "memory_counts": {"cur": 0, "new": 0, "tmp": 0}, "total_memories": 0}
+        for status in ("cur", "new", "tmp"):
+            memories = read_folder(base, folder, status, False)
+            sub["memory_counts"][status] = len(memories); sub["total_memories"] += len(memories)
+            stats["total_memories"] += len(memories); stats["memory_counts"][status] += len(memories)
+            for memory in memories:
+                for flag in memory["metadata"]["flags"]:
+                    if flag in stats["flag_counts"]:
+                        stats["flag_counts"][flag] += 1
+                if "Tags" in memory["headers"]:
+                    for tag in [t.strip() for t in memory["headers"]["Tags"].split(",")]:
+                        stats["tags"][tag] = stats["tags"].get(tag, 0) + 1
+                d = memory["metadata"]["date"]
+                if stats["newest_memory"] is None or d > stats["newest_memory"]["date"]:
+                    stats["newest_memory"] = {"id": memory["metadata"]["unique_id"], "subject": memory["headers"].get("Subject", "No subject"), "date": d}
+                if stats["oldest_memory"] is None or d < stats["oldest_memory"]["date"]:
+                    stats["oldest_memory"] = {"id": memory["metadata"]["unique_id"], "subject": memory["headers"].get("Subject", "No subject"), "date": d}
+        if include_subfolders and folder != folder_path:
+            stats["subfolders"].append(sub)
+    return stats

@@ -110,6 +110,11 @@ LEGACY = [
 ]
 
 
+# MemdirFolderManager.get_folder_stats (folders.py:216-318): (folder_path, include_subfolders)
+FOLDER_STATS = [("", False), ("", True), (".Projects", False), (".Projects", True), (".Archive", True), ("no-such-folder", False), (".Proj", True),
+                ("/.Projects/", False)]
+
+
 def build_corpus(base: str):
     sys.path.insert(0, REPO)
     from fei_b200 import synth
@@ -192,6 +197,14 @@ def make_memdir(scratch: str, import_reference):
         with contextlib.redirect_stdout(buf):
             stats = mgr.process_memories(statuses=statuses, dry_run=True)
         out["filters"].append({"statuses": statuses, "stats": stats})
+    # folder statistics last: the manager's constructor creates the special folders, which changes get_memdir_folders()
+    import memdir_tools.folders as rfo
+    out["folder_stats"] = []
+    for folder_path, include_sub in FOLDER_STATS:
+        st = rfo.MemdirFolderManager().get_folder_stats(folder_path, include_sub)
+        out["folder_stats"].append({"folder_path": folder_path, "include_subfolders": include_sub, "stats": st,
+                                    "tag_order": list(st["tags"].keys())})
+    out["folders_after_manager"] = ru.get_memdir_folders()
     # public signatures of the entry points the drop-in keeps (checked against fei_b200.memdir_tools on every CPU run)
     import inspect
     sig = lambda f: [[p.name, int(p.kind), None if p.default is inspect.Parameter.empty else repr(p.default)] for p in inspect.signature(f).parameters.values()]

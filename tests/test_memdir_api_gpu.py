@@ -201,3 +201,25 @@ def test_legacy_substring_search(api):
         for a, b in zip(res, want):
             assert a.get("content_preview") == b.get("content_preview") and ("content" in a) == ("content" in b) and a["headers"] == b["headers"]
         assert [("content" in m) for m in res][:4] == case["has_content_key"], case
+
+
+def test_folder_stats(api):
+    """MemdirFolderManager.get_folder_stats (folders.py:216-318): counts from the packed segments, flag counts and the tag
+    statistics (fei_corpus_token_histogram) from the GPU, newest / oldest from the packed wall-clock column."""
+    from fei_b200.memdir_tools.folders import MemdirFolderManager
+    base, g = api
+    assert g["folder_stats"]
+    for case in g["folder_stats"]:
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = MemdirFolderManager().get_folder_stats(case["folder_path"], case["include_subfolders"])
+            want = mo.folder_stats(base, case["folder_path"], case["include_subfolders"])
+        assert got == want, case["folder_path"]                                       # same tree: exact, including dict order
+        assert list(got["tags"].keys()) == list(want["tags"].keys()), case["folder_path"]
+        ref = case["stats"]                                                           # the reference on its own copy of the tree
+        for k in ("folder", "total_memories", "memory_counts", "flag_counts"):
+            assert got[k] == ref[k], (case["folder_path"], k)
+        by_name = lambda subs: sorted(subs, key=lambda x: x["folder"])                # folder order = os.walk order: differs between boxes
+        assert by_name(got["subfolders"]) == by_name(ref["subfolders"]), case["folder_path"]
+        assert got["tags"] == ref["tags"]                                             # order may differ on timestamp ties (listdir order)
+        for k in ("newest_memory", "oldest_memory"):
+            assert (got[k] is None) == (ref[k] is None) and (got[k] is None or str(got[k]["date"]) == ref[k]["date"])
