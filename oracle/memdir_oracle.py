@@ -323,3 +323,42 @@ def folder_stats(base: str, folder_path: str, include_subfolders: bool = False) 
         if include_subfolders and folder != folder_path:
             stats["subfolders"].append(sub)
     return stats
+
+
+def matches_criteria(memory: Dict[str, Any], criteria: Dict[str, Any], now=None) -> bool:
+    """MemoryArchiver._memory_matches_criteria (archiver.py:128-181); `now` pins datetime.now() for tests."""
+    from datetime import datetime
+    now = now or datetime.now()
+    for key, pattern in criteria.items():
+        if key in ("age", "min_age", "max_age"):
+            memory_age = (now - memory["metadata"]["date"]).days
+            if key == "age" and memory_age < pattern:
+                return False
+            elif key == "min_age" and memory_age < pattern:
+                return False
+            elif key == "max_age" and memory_age > pattern:
+                return False
+        elif key == "tag" or key == "tags":
+            memory_tags = [tag.strip() for tag in memory["headers"].get("Tags", "").lower().split(",")]
+            if isinstance(pattern, list):
+                if not any(tag in memory_tags for tag in pattern):
+                    return False
+            elif pattern.lower() not in memory_tags:
+                return False
+        elif key in memory["headers"]:
+            value = memory["headers"][key]
+            if isinstance(pattern, str):
+                if not re.search(pattern, value, re.IGNORECASE):
+                    return False
+            elif value != pattern:
+                return False
+        elif key == "flags":
+            memory_flags = "".join(memory["metadata"]["flags"])
+            if isinstance(pattern, str):
+                if not re.search(pattern, memory_flags, re.IGNORECASE):
+                    return False
+            elif memory_flags != pattern:
+                return False
+        else:
+            return False
+    return True

@@ -110,6 +110,15 @@ LEGACY = [
 ]
 
 
+# MemoryArchiver._memory_matches_criteria (archiver.py:128-181) over the whole listing
+CRITERIA = [
+    {"tags": "python"}, {"tag": ["python", "rust"]}, {"tags": ["Python"]}, {"tags": "PYTHON"}, {"tags": [" python"]}, {"tags": []},
+    {"Status": "active|done"}, {"status": "completed|done"}, {"Priority": "^high$", "tags": "python"}, {"Subject": 7},
+    {"flags": "f"}, {"flags": "^FS?$"}, {"flags": ["F"]}, {"age": 100}, {"min_age": 100000}, {"max_age": 100000}, {"max_age": 10},
+    {"age": 100, "tags": ["learning", "ai"], "Status": "."}, {"Nope": "x"}, {},
+]
+
+
 # MemdirFolderManager.get_folder_stats (folders.py:216-318): (folder_path, include_subfolders)
 FOLDER_STATS = [("", False), ("", True), (".Projects", False), (".Projects", True), (".Archive", True), ("no-such-folder", False), (".Proj", True),
                 ("/.Projects/", False)]
@@ -197,6 +206,16 @@ def make_memdir(scratch: str, import_reference):
         with contextlib.redirect_stdout(buf):
             stats = mgr.process_memories(statuses=statuses, dry_run=True)
         out["filters"].append({"statuses": statuses, "stats": stats})
+    import memdir_tools.archiver as ra
+    arch = ra.MemoryArchiver()
+    out["criteria"] = [{"criteria": c, "result": [key_of(m) for m in listing if arch._memory_matches_criteria(m, c)]} for c in CRITERIA]
+    arch2 = ra.MemoryArchiver()
+    arch2.add_cleanup_rule({"tags": "python", "Priority": "high"}, "trash")
+    arch2.add_cleanup_rule({"flags": "P"}, "delete")
+    st = arch2.cleanup_memories(dry_run=True)
+    out["cleanup_dry_run"] = {"trashed": st["trashed"], "deleted": st["deleted"], "details": st["details"]}
+    st = ra.MemoryArchiver().cleanup_memories(dry_run=True)                  # the two default rules
+    out["cleanup_default_dry_run"] = {"trashed": st["trashed"], "deleted": st["deleted"]}
     # folder statistics last: the manager's constructor creates the special folders, which changes get_memdir_folders()
     import memdir_tools.folders as rfo
     out["folder_stats"] = []

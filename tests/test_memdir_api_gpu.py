@@ -223,3 +223,39 @@ def test_folder_stats(api):
         assert got["tags"] == ref["tags"]                                             # order may differ on timestamp ties (listdir order)
         for k in ("newest_memory", "oldest_memory"):
             assert (got[k] is None) == (ref[k] is None) and (got[k] is None or str(got[k]["date"]) == ref[k]["date"])
+
+
+def test_archiver_criteria_and_cleanup(api):
+    """MemoryArchiver._memory_matches_criteria / cleanup_memories (archiver.py:128-181, :306-381) through match_criteria on the GPU."""
+    import numpy as np
+    from fei_b200 import packer
+    from fei_b200.memdir_tools.archiver import MemoryArchiver
+    base, g = api
+    arch = MemoryArchiver()
+    crits = [c["criteria"] for c in g["criteria"]]
+    with contextlib.redirect_stdout(io.StringIO()):
+        rows = arch.match_criteria(crits)
+        pm = packer.packed()
+        mems = mo.listing(base, None, None, True)
+    order = pm.ranges(None, None)
+    idx = np.concatenate([np.arange(a, b) for a, b in order])
+    assert idx.size == len(mems)
+    for c, row in zip(g["criteria"], rows):
+        got = [key_of(mems[k]) for k in np.nonzero(row[idx])[0].tolist()]
+        want = [key_of(m) for m in mems if mo.matches_criteria(m, c["criteria"])]
+        assert got == want, c["criteria"]
+        assert same_modulo_ties(got, c["result"]), c["criteria"]
+        for m in mems[:40]:                                   # the single-record host form agrees too
+            assert arch._memory_matches_criteria(m, c["criteria"]) == mo.matches_criteria(m, c["criteria"]), c["criteria"]
+    a2 = MemoryArchiver()
+    a2.add_cleanup_rule({"tags": "python", "Priority": "high"}, "trash")
+    a2.add_cleanup_rule({"flags": "P"}, "delete")
+    with contextlib.redirect_stdout(io.StringIO()):
+        st = a2.cleanup_memories(dry_run=True)
+    ref = g["cleanup_dry_run"]
+    assert (st["trashed"], st["deleted"]) == (ref["trashed"], ref["deleted"])
+    key = lambda d: (d["action"], d["memory_id"], d["subject"])
+    assert sorted(map(key, st["details"])) == sorted(map(key, ref["details"]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        st = MemoryArchiver().cleanup_memories(dry_run=True)
+    assert (st["trashed"], st["deleted"]) == (g["cleanup_default_dry_run"]["trashed"], g["cleanup_default_dry_run"]["deleted"])
