@@ -388,7 +388,7 @@ struct Survivor { uint32_t rec, pre, flags_acc; };
 constexpr int kMetaPer = 4;     // records per thread: the (uniform) condition fetch / decode is paid once for four records
 
 template <bool kFused>
-__global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restrict__ list, unsigned int* __restrict__ count) {
+__global__ void __launch_bounds__(256, 5) k_head_meta(HeadArgs a, Survivor* __restrict__ list, unsigned int* __restrict__ count) {
   __shared__ __align__(128) uint8_t sprog[kHeadProgSmem];
   __shared__ uint64_t bar;
   a.prog = stage_prog_head(a.prog, sprog, &bar);
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(256) k_head_meta(HeadArgs a, Survivor* __restr
   }
 }
 
-__global__ void __launch_bounds__(256) k_head_parse(HeadArgs a, const Survivor* __restrict__ list, const unsigned int* __restrict__ n_list) {
+__global__ void __launch_bounds__(256, 5) k_head_parse(HeadArgs a, const Survivor* __restrict__ list, const unsigned int* __restrict__ n_list) {
   __shared__ __align__(128) uint8_t sprog[kHeadProgSmem];
   __shared__ uint64_t bar;
   const unsigned int n_surv = *n_list;                         // written by k_head_meta earlier on this stream: no host round trip
