@@ -454,7 +454,7 @@ extern "C" int fei_chain_validate_cols(const fei_json_col* cols, const uint8_t* 
                                        uint8_t* msgs_out, uint64_t msgs_cap, uint64_t* msg_off_out) {
   FEI_TRY(require_ready());
   if (!cols || !hash_off) { set_error("null argument"); return FEI_E_BADARG; }
-  std::vector<uint8_t> msgs; std::vector<uint64_t> off;
+  ByteVec msgs; std::vector<uint64_t> off;
   const bool dbg = getenv("FEI_DEBUG_TIMING") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
   FEI_TRY(serialize_chain_cols(cols, n, msgs, off));

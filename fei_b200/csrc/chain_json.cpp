@@ -169,7 +169,7 @@ static size_t block_bound(const fei_json_col* cols, uint64_t i) {
   return b;
 }
 
-int serialize_chain_cols(const fei_json_col* cols, uint64_t n, std::vector<uint8_t>& msgs, std::vector<uint64_t>& off) {
+int serialize_chain_cols(const fei_json_col* cols, uint64_t n, ByteVec& msgs, std::vector<uint64_t>& off) {
   for (int k = 0; k < FEI_CHAIN_NCOLS; ++k) {
     const fei_json_col& c = cols[k];
     if (!c.tag && (c.uniform_tag < FEI_J_NULL || c.uniform_tag > FEI_J_BIGINT)) { set_error("column %d (%s): bad uniform tag %d", k, kKeys[k], c.uniform_tag); return FEI_E_BADARG; }
@@ -230,7 +230,7 @@ int serialize_chain_cols(const fei_json_col* cols, uint64_t n, std::vector<uint8
 
 extern "C" int fei_chain_serialize_cols(const fei_json_col* cols, uint64_t n, uint8_t* msgs_out, uint64_t msgs_cap, uint64_t* msg_off_out) {
   if (!cols || !msg_off_out) { fei::set_error("null argument"); return FEI_E_BADARG; }
-  std::vector<uint8_t> msgs; std::vector<uint64_t> off;
+  fei::ByteVec msgs; std::vector<uint64_t> off;
   int rc = fei::serialize_chain_cols(cols, n, msgs, off);
   if (rc != FEI_OK) return rc;
   memcpy(msg_off_out, off.data(), (n + 1) * sizeof(uint64_t));

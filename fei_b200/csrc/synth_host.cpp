@@ -99,7 +99,7 @@ extern "C" int fei_chain_synth(fei_chain* ch, uint64_t seed, uint64_t first, uin
   std::vector<uint64_t> moff{0}, hoff{0}, poff{0};
   msgs.reserve((end - keep_from) * 368);
   std::string prev_hash = "0";                       // genesis previous_hash (memorychain.py:546)
-  std::vector<uint8_t> one; std::vector<uint64_t> one_off;
+  fei::ByteVec one; std::vector<uint64_t> one_off;
   static const char hx[] = "0123456789abcdef";
   for (uint64_t i = 0; i < end; ++i) {
     feisynth::ChainBlockSpec b = feisynth::gen_block(seed, i);
