@@ -694,20 +694,46 @@ def _to_bytes(cp_trans, cp_out, cp_end, bounds, cls_of, ncls, npat) -> Dfa:
 
 def _minimize(T: np.ndarray, out: np.ndarray, endout: np.ndarray, start: int):
     n = T.shape[0]
-    # collapse identical columns first (cheaper refinement)
-    _, col_first, col_inv = np.unique(T, axis=1, return_index=True, return_inverse=True)
+    # collapse identical columns first (cheaper refinement): columns are grouped by a 64-bit hash, then checked exactly
+    with np.errstate(over="ignore"):
+        rmult = (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0xD6E8FEB86659FD93)) | np.uint64(1)
+        colh = (T.astype(np.uint64) * rmult[:, None]).sum(axis=0, dtype=np.uint64)
+    _, col_first, col_inv = np.unique(colh, return_index=True, return_inverse=True)
+    if not np.array_equal(T, T[:, col_first[col_inv.reshape(-1)]]):      # two different columns with one hash: compare columns themselves
+        _, col_first, col_inv = np.unique(T, axis=1, return_index=True, return_inverse=True)
     Tc = T[:, np.sort(col_first)]
     key = out.astype(np.int64) << 32 | endout.astype(np.int64)
     _, block = np.unique(key, return_inverse=True)
+    block = block.reshape(-1)
     nblocks = int(block.max()) + 1
-    while True:
-        sig = np.concatenate([block[:, None], block[Tc]], axis=1)
-        _, newblock = np.unique(sig, axis=0, return_inverse=True)
-        nb = int(newblock.max()) + 1
-        block = newblock.reshape(-1)
-        if nb == nblocks:
-            break
-        nblocks = nb
+    # Moore refinement on 64-bit hashes of the signature rows (a 1-D unique per round instead of a row-wise one); a hash
+    # collision could only merge two different signatures, which the exact check below would expose
+    mult = (np.arange(1, Tc.shape[1] + 2, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(1)
+    with np.errstate(over="ignore"):
+        while True:
+            h = block.astype(np.uint64) * mult[0] + (block[Tc].astype(np.uint64) * mult[None, 1:]).sum(axis=1, dtype=np.uint64)
+            _, newblock = np.unique(h, return_inverse=True)
+            newblock = newblock.reshape(-1)
+            nb = int(newblock.max()) + 1
+            block = newblock
+            if nb == nblocks:
+                break
+            nblocks = nb
+    rep0 = np.full(nblocks, n, dtype=np.int64)
+    np.minimum.at(rep0, block, np.arange(n))
+    sig = np.concatenate([key[:, None], block[Tc]], axis=1)
+    if not np.array_equal(sig, sig[rep0[block]]):            # never seen; exact row-wise refinement from scratch
+        _, block = np.unique(key, return_inverse=True)
+        block = block.reshape(-1)
+        nblocks = int(block.max()) + 1
+        while True:
+            sig = np.concatenate([block[:, None], block[Tc]], axis=1)
+            _, newblock = np.unique(sig, axis=0, return_inverse=True)
+            nb = int(newblock.max()) + 1
+            block = newblock.reshape(-1)
+            if nb == nblocks:
+                break
+            nblocks = nb
     # representative per block, block of start first
     # stable numbering by first occurrence, with the start state's block as 0
     first_idx = np.full(nblocks, n, dtype=np.int64)
