@@ -127,3 +127,33 @@ def test_dropin_install_patches_the_reference_package():
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "patched" in out.stdout, out.stderr[-2000:]
+
+
+def test_oracle_next_rows_match_reference(tree):
+    """The oracle's restatements of the "next" rows (legacy substring search, folder statistics, archiver criteria) against
+    the reference-generated goldens; the archiver's single-record host form against the oracle."""
+    import contextlib, io
+    base, g = tree
+    with contextlib.redirect_stdout(io.StringIO()):
+        for case in g["legacy"]:
+            mems = mo.listing(base, case["folders"], case["statuses"], True)
+            res = mo.legacy_search(mems, case["query"], case["headers_only"])
+            assert same_modulo_ties([key_of(m) for m in res], case["result"]), case
+            assert [("content" in m) for m in res][:4] == case["has_content_key"]
+        listing = mo.listing(base, None, None, True)
+        from fei_b200.memdir_tools.archiver import MemoryArchiver
+        arch = MemoryArchiver()
+        for c in g["criteria"]:
+            got = [key_of(m) for m in listing if mo.matches_criteria(m, c["criteria"])]
+            assert same_modulo_ties(got, c["result"]), c["criteria"]
+            assert [arch._memory_matches_criteria(m, c["criteria"]) for m in listing] == [mo.matches_criteria(m, c["criteria"]) for m in listing]
+        # folder statistics need the special folders the reference manager creates before it counts (ensure_memdir_structure)
+        from fei_b200.memdir_tools import utils as U
+        U.set_memdir_base(base); U.ensure_memdir_structure()
+        for case in g["folder_stats"]:
+            st = mo.folder_stats(base, case["folder_path"], case["include_subfolders"])
+            ref = case["stats"]
+            for k in ("folder", "total_memories", "memory_counts", "flag_counts"):
+                assert st[k] == ref[k], (case["folder_path"], k)
+            assert st["tags"] == ref["tags"]
+            assert sorted(st["subfolders"], key=lambda x: x["folder"]) == sorted(ref["subfolders"], key=lambda x: x["folder"])
