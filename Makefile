@@ -35,7 +35,7 @@ $(ORACLE_LIB): oracle/chain_oracle.c
 
 # CPython helper for the Python host layer (attribute marshalling of block objects); host glue, no compute
 $(FASTCOLS): fei_b200/_fastcols.c
-	$(CC) -O2 -fPIC -shared -Wall $(PY_INC) -o $@ $<
+	$(CC) -O2 -fPIC -shared -Wall $(PY_INC) -o $@ $< || echo "warning: _fastcols not built (no Python headers?): the pure-Python marshalling path will be used"
 
 clean:
 	rm -rf build $(LIB) $(ORACLE_LIB) $(FASTCOLS)
