@@ -15,6 +15,9 @@ Each function follows /root/reference/memdir_tools:
   run_search         <- search.search_memories                     (search.py:337-390)
   filter_accepts     <- filter.MemoryFilter.matches                (filter.py:67-109)
   run_filters        <- filter.FilterManager.process_memories, dry run   (filter.py:188-261)
+  legacy_search      <- utils.search_memories (substring search)   (utils.py:299-352)
+  folder_stats       <- folders.MemdirFolderManager.get_folder_stats   (folders.py:216-318)
+  matches_criteria   <- archiver.MemoryArchiver._memory_matches_criteria   (archiver.py:128-181)
 `re`, `datetime` are CPython stdlib; `dateutil` (unpinned third-party, 2.9.0.post0 here) is what the
 reference imports (search.py:12).  Pinned by tests/golden/memdir_golden.json, produced by running the
 unmodified reference on the same inputs (tests/golden/make_golden_memdir.py).
@@ -326,39 +329,29 @@ def folder_stats(base: str, folder_path: str, include_subfolders: bool = False) 
 
 
 def matches_criteria(memory: Dict[str, Any], criteria: Dict[str, Any], now=None) -> bool:
-    """MemoryArchiver._memory_matches_criteria (archiver.py:128-181); `now` pins datetime.now() for tests."""
+    """MemoryArchiver._memory_matches_criteria (archiver.py:128-181), restated: every criterion must hold.
+    Order of interpretation per key: age family, tag family, a header of exactly that name, the file-name flags, else fail.
+    `now` pins datetime.now() for tests."""
     from datetime import datetime
     now = now or datetime.now()
+    headers, meta = memory["headers"], memory["metadata"]
+
+    def text_rule(value: str, pattern: Any) -> bool:
+        return bool(re.search(pattern, value, re.IGNORECASE)) if isinstance(pattern, str) else value == pattern
+
     for key, pattern in criteria.items():
         if key in ("age", "min_age", "max_age"):
-            memory_age = (now - memory["metadata"]["date"]).days
-            if key == "age" and memory_age < pattern:
-                return False
-            elif key == "min_age" and memory_age < pattern:
-                return False
-            elif key == "max_age" and memory_age > pattern:
-                return False
-        elif key == "tag" or key == "tags":
-            memory_tags = [tag.strip() for tag in memory["headers"].get("Tags", "").lower().split(",")]
-            if isinstance(pattern, list):
-                if not any(tag in memory_tags for tag in pattern):
-                    return False
-            elif pattern.lower() not in memory_tags:
-                return False
-        elif key in memory["headers"]:
-            value = memory["headers"][key]
-            if isinstance(pattern, str):
-                if not re.search(pattern, value, re.IGNORECASE):
-                    return False
-            elif value != pattern:
-                return False
+            days = (now - meta["date"]).days
+            ok = days <= pattern if key == "max_age" else days >= pattern
+        elif key in ("tag", "tags"):
+            have = [piece.strip() for piece in headers.get("Tags", "").lower().split(",")]
+            ok = any(t in have for t in pattern) if isinstance(pattern, list) else pattern.lower() in have
+        elif key in headers:
+            ok = text_rule(headers[key], pattern)
         elif key == "flags":
-            memory_flags = "".join(memory["metadata"]["flags"])
-            if isinstance(pattern, str):
-                if not re.search(pattern, memory_flags, re.IGNORECASE):
-                    return False
-            elif memory_flags != pattern:
-                return False
+            ok = text_rule("".join(meta["flags"]), pattern)
         else:
+            ok = False
+        if not ok:
             return False
     return True
