@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(256) k_hdir(const uint8_t* __restrict__ hdr, c
         const uint32_t s = key_slot(kd, kh, true);
         if (s == 0xFFFFFFFFu) atomicOr(kd.flag, 1u);
         else {
-          atomicMin(kd.rep + s, (unsigned long long)(ka - hdr)); kd.len[s] = klen;   // same hash => same length unless colliding (checked in pass 1)
+          const unsigned long long at = (unsigned long long)(ka - hdr);
+          if (at < kd.rep[s]) atomicMin(kd.rep + s, at);                 // representative = smallest offset; the plain read skips almost every atomic
+          kd.len[s] = klen;                                              // same hash => same length unless colliding (checked in pass 1)
           if ((i & 63) == 0) atomicAdd(kd.cnt + s, 1u);                             // sampled frequency: which keys deserve a value column
         }
       } else {
