@@ -207,9 +207,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--entries", type=int, default=10_000_000, help="synthetic Memdir entries per GPU")
-    ap.add_argument("--e2e-entries", type=int, default=1_000_000)
-    ap.add_argument("--api-files", type=int, default=20_000, help="files of the on-disk Memdir for the Python-API extra")
+    ap.add_argument("--entries", type=int, default=0, help="synthetic Memdir entries per GPU (default: 10 M; 12.5 M on 8 GPUs = the 100 M-entry cfg5)")
+    ap.add_argument("--e2e-entries", type=int, default=1_000_000, help="records per streamed batch of the end-to-end leg")
+    ap.add_argument("--e2e-batches", type=int, default=10, help="batches per end-to-end step (10 x 1 M = the 10 M-entry configuration)")
+    ap.add_argument("--parity-entries", type=int, default=500_000, help="records per rank of the sharded-vs-unsharded parity run")
+    ap.add_argument("--api-files", type=int, default=200_000, help="files of the on-disk Memdir for the Python-API extra")
     ap.add_argument("--chain-blocks", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=60000)
     ap.add_argument("--no-extra", action="store_true")
@@ -222,6 +224,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not args.entries:
+        args.entries = 12_500_000 if world >= 8 else 10_000_000
     dist = None
     if world > 1:
         import torch
@@ -258,7 +262,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    if dist:                                           # library-level NCCL communicator for the hit all-gatherv
+    if dist:                                           # library-level NCCL communicator (bootstrap; totals; fallback of the mask exchange)
         import torch
         idbuf = np.zeros(_abi.NCCL_ID_BYTES, dtype=np.uint8)
         if rank == 0:
@@ -275,14 +279,16 @@ def main():
     st = corpus.stats()
     prog = content_batch_program([Pattern("regex", p, re.IGNORECASE) for p in BATCH32])
     nq = 32
+    if dist:
+        _abi.check(lib.fei_comm_bind_corpus(corpus.handle))
+    p2p = bool(lib.fei_comm_is_p2p()) if dist else False
 
     def step():
-        counts = corpus.scan_count(prog, nq)           # k_body + ordered compaction; lists stay on the device
-        if dist:
+        if dist:                                       # the same scan, the mask all-gather of each finished chunk under the next chunk's scan
             tot = np.zeros(32, dtype=np.uint64)
-            _abi.check(lib.fei_comm_allgather_hits(corpus.handle, nq, None, None, _abi.ptr(tot), None))
+            _abi.check(lib.fei_comm_scan_gather(corpus.handle, prog, len(prog), _abi.ptr(tot)))
             return tot[:nq]
-        return counts
+        return corpus.scan_count(prog, nq)             # k_body in chunks + ordered compaction on the side stream; lists stay on the device
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -303,31 +309,46 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = allmax(wall * 1e3 / args.steps)         # wall between barriers, max over ranks (includes the all-gatherv)
+    step_ms = allmax(wall * 1e3 / args.steps)         # wall between barriers, max over ranks (includes the exchange)
     dev_step_ms = allmax(dev_ms / args.steps)         # CUDA-event time of the scan calls
     total_entries = allsum(float(args.entries))
     value = total_entries / (step_ms * 1e-3)
+    local_hits = corpus.scan_count(prog, nq) if dist else totals
+    hits_sum_ok = True
+    if dist:                                           # the gathered totals are the sum of the shards' own counts
+        import torch
+        t = torch.from_numpy(local_hits.astype(np.int64)).cuda()
+        dist.all_reduce(t)
+        hits_sum_ok = bool((t.cpu().numpy().astype(np.uint64) == totals).all())
 
     peak, peak_src = measured_peak()
     body_ms_avg = body_ms / args.steps
     algo_bytes = st["body_bytes"] + 8 * st["n"] + 4 * st["n"]       # body text + (record id, length) + hit mask written
     achieved = algo_bytes / (body_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_body<direct>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    traffic = ncu_traffic_per_entry()
+    roofline = {"bound": "hbm", "kernel": "k_body<direct,acc64>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": body_ms_avg,
+                "kernel_ms_note": "CUDA events around all chunk launches of the kernel within one step (the compaction of finished chunks runs "
+                                  "concurrently on a second stream); kernel launches per step: %d" % (launches // max(1, args.steps)),
                 "bytes_per_memory": algo_bytes / max(1, st["n"]),
-                # dram__bytes_read+write of this kernel from the ncu --set full capture at 1 M entries
-                # (profiles/r1b_k_body_bankspread_acceptbits.txt: 3.490 GB read + 0.008 GB written), scaled to this launch
-                "traffic": int(3.498e9 * st["n"] / 1e6), "traffic_source": "ncu capture at 1e6 entries, scaled linearly with entries",
+                "traffic": int(traffic["bytes_per_entry"] * st["n"]) if traffic else None,
+                "traffic_source": (traffic["source"] + ", scaled linearly with entries") if traffic else "no capture",
                 "note": "body-only batch: header bytes are not needed by this query and are not read; "
                         "SURVEY 8(d)'s 3626 B/memory figure includes ~152 B of header text"}
 
+    workload = "memdir-32pattern-batch (BASELINE configs[2]): 32 `content matches` regexes, one pass; per step: hit masks + ordered per-query hit lists on the device"
+    if world > 1:
+        workload = ("memdir-32pattern-batch over %d range shards (BASELINE configs[4] / cfg5 batch leg): every rank scans its shard (masks + ordered local lists, the "
+                    "single-GPU work) and the step ENDS when every rank holds the hit masks of all shards (rank-major = global listing order) and the global "
+                    "per-query totals; masks are the wire format because 97-100 %% of the records hit (8 B/hit lists would be 16x larger); the exchange of a "
+                    "finished chunk (%s) runs under the next chunk's scan" % (world, "peer-memory copies over NVLink, CUDA IPC" if p2p else "grouped ncclBroadcast"))
     line = {
         "metric": METRIC, "value": value, "unit": "memories/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "memdir-32pattern-batch (BASELINE configs[2]): 32 `content matches` regexes, one pass, ordered hit lists"
-                               + (" + NCCL all-gatherv of hits" if world > 1 else ""),
+        "config": {"workload": workload,
                    "entries_per_gpu": args.entries, "entries_total": int(total_entries), "patterns": 32,
                    "corpus_bytes_per_gpu": int(st["body_bytes"] + st["hdr_bytes"]), "parallelism": f"range-shard x{world}",
+                   "per_gpu_work_note": "10 M entries per GPU up to 4 GPUs, 12.5 M on 8 (= the 100 M-entry cfg5); memories/s per GPU does not depend on the shard size",
                    "l2": "inputs (tens of GB per GPU) are far larger than the 126 MB L2; no flush needed"},
         "device_ms_per_step": dev_step_ms, "roofline": roofline, "gpu_launches": int(launches),
         "sm_count": info["sm_count"], "corpus_gen_s": gen_s,
@@ -336,14 +357,22 @@ def main():
     if clocks is not None:
         line["clocks"] = clocks
 
-    # end-to-end through the C ABI from pinned host buffers, every rank on its own batch (own PCIe link)
+    # ---- parity: what the timed steps computed, held against independent computations
+    parity = {"gathered_totals_equal_sum_of_shard_counts": hits_sum_ok} if dist else {}
+    parity.update(run_parity(args, rank, world, dist, corpus, prog, nq, lib, _abi))
+    line["parity"] = parity
+    if dist:
+        line["multi_gpu"] = run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, allmax, step_ms)
+
+    # end-to-end through the C ABI from pinned host buffers, every rank on its own batches (own PCIe link)
     barrier()
-    e2e = run_e2e(args, corpus, prog, nq, lib, _abi)
+    e2e = run_e2e(args, corpus, prog, nq, lib, _abi, barrier)
     barrier()
     e2e_ms = allmax(e2e["ms_per_step"])
     e2e_entries = allsum(float(e2e["entries_per_step"]))
     e2e.update({"value": e2e_entries / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "entries_per_step": int(e2e_entries),
-                "h2d_bytes_per_step": int(allsum(float(e2e["h2d_bytes_per_step"]))), "d2h_bytes_per_step": int(allsum(float(e2e["d2h_bytes_per_step"])))})
+                "h2d_bytes_per_step": int(allsum(float(e2e["h2d_bytes_per_step"]))), "d2h_bytes_per_step": int(allsum(float(e2e["d2h_bytes_per_step"]))),
+                "h2d_gbs_measured_min_over_ranks": -allmax(-e2e["h2d_gbs_measured"])})
     line["e2e"] = e2e
     if rank == 0 and world == 1:
         rate, dt = cpu_scan_rate(args.cpu_sample, 1)
@@ -360,20 +389,164 @@ def main():
     return 0
 
 
-def run_e2e(args, corpus, prog, nq, lib, _abi):
-    """Host buffers -> fei_corpus_load (H2D + tiling) -> scan -> ordered hit lists back to the host, every step."""
+def ncu_traffic_per_entry():
+    """dram__bytes_read + dram__bytes_write per entry of the headline kernel, from the latest `ncu --set full` capture summarised
+    under profiles/ (profiles/traffic.json, written by tools/ncu_summary.py --traffic)."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return {"bytes_per_entry": float(t["k_body"]["dram_bytes"]) / float(t["k_body"]["entries"]), "source": t["k_body"]["source"]}
+    except Exception:
+        return None
+
+
+def batch_cfg2_program(n_total: int):
+    """The cfg-2 multi-field query: Tags has_tag python AND flags has_flag F AND date > median AND content matches react|angular."""
+    from fei_b200.program import C_BODY, C_DATE_CMP, C_FLAGS, C_SLOT, CMP, Cond, ProgramBuilder
+    from fei_b200.regexc import Pattern
+    median_ts = 1700000000 + (n_total // 2) // 4
+    pb = ProgramBuilder()
+    pb.add_query([
+        Cond(C_FLAGS, pattern=Pattern("exact_contains", "F")),
+        Cond(C_DATE_CMP, op=CMP[">"], i64=median_ts * 1000000),
+        Cond(C_SLOT, pattern=Pattern("has_tag", "python"), field="Tags", mode=0),
+        Cond(C_BODY, pattern=Pattern("regex", r"react|angular", re.IGNORECASE)),
+    ])
+    return pb.build()
+
+
+def run_parity(args, rank, world, dist, corpus, prog, nq, lib, _abi):
+    """(1) one GPU: the chunked scan against a single-launch scan of the same corpus (order-sensitive checksums of all 32 lists) and
+    three 300-record windows of the bench corpus against the oracle (the CPU restatement of the reference, used as the checker);
+    (2) N GPUs: a sharded scan + gather of P x N records against an UNSHARDED scan of the same global range on rank 0: per-query totals
+    and order-sensitive checksums of the global ordered lists, for the 32-pattern batch (dense wire format) and the cfg-2 query
+    (sparse: grouped-broadcast all-gatherv of the lists)."""
+    from fei_b200.corpus import Corpus
+    out = {}
+    if world == 1:
+        corpus.scan_count(prog, nq)
+        a1, s1 = corpus.list_checksums(nq)
+        os.environ["FEI_SCAN_CHUNKS"] = "1"
+        c1 = corpus.scan_count(prog, nq)
+        a2, s2 = corpus.list_checksums(nq)
+        os.environ.pop("FEI_SCAN_CHUNKS")
+        out["chunked_scan_equals_single_launch"] = bool((a1 == a2).all() and (s1 == s2).all())
+        try:
+            from fei_b200 import synth
+            from oracle import memdir_oracle as mo
+            masks = corpus.scan_masks(prog)
+            ok, checked = True, 0
+            for start in (0, corpus.n // 3, max(0, corpus.n - 300)):
+                recs = [synth.record(SEED, corpus.global_base + start + k) for k in range(min(300, corpus.n - start))]
+                mems = [mo.make_memory(r["filename"], r["folder"], r["status"], synth.file_text(r), True) for r in recs]
+                for q, p in enumerate(BATCH32):
+                    want = set(mo.run_search(mems, [{"field": "content", "operator": "matches", "value": p}]))
+                    got = {k for k in range(len(recs)) if (int(masks[start + k]) >> q) & 1}
+                    ok = ok and want == got
+                checked += len(recs)
+            out["sampled_windows_vs_oracle"] = {"records": checked, "patterns": 32, "equal": bool(ok)}
+        except Exception as e:                                     # the oracle is test infrastructure; its absence must not cost the line
+            out["sampled_windows_vs_oracle"] = {"error": f"{type(e).__name__}: {e}"}
+        return out
+    P = args.parity_entries
+    pc = Corpus().synth(SEED, rank * P, P)
+    full = Corpus().synth(SEED, 0, P * world) if rank == 0 else None
+    _abi.check(lib.fei_comm_bind_corpus(pc.handle))
+    res = {}
+    for name, pr, q_n in (("batch32_dense", prog, nq), ("cfg2_query_sparse", batch_cfg2_program(P * world), 1)):
+        gt = np.zeros(32, dtype=np.uint64); ga = np.zeros(32, dtype=np.uint64); gs = np.zeros(32, dtype=np.uint64)
+        if name == "batch32_dense":
+            tot = np.zeros(32, dtype=np.uint64)
+            _abi.check(lib.fei_comm_scan_gather(pc.handle, pr, len(pr), _abi.ptr(tot)))
+        else:
+            pc.scan_count(pr, q_n)
+            tot = np.zeros(32, dtype=np.uint64)
+            _abi.check(lib.fei_comm_allgather_hits(pc.handle, q_n, None, None, _abi.ptr(tot), None))
+        _abi.check(lib.fei_comm_gathered_checksum(q_n, _abi.ptr(gt), _abi.ptr(ga), _abi.ptr(gs)))
+        if rank == 0:
+            cnt = full.scan_count(pr, q_n)
+            fa, fs = full.list_checksums(q_n)
+            res[name] = {"entries_total": P * world, "queries": q_n,
+                         "totals_equal": bool((cnt == tot[:q_n]).all() and (cnt == gt[:q_n]).all()),
+                         "ordered_list_checksums_equal": bool((fa == ga[:q_n]).all() and (fs == gs[:q_n]).all()),
+                         "hits": [int(cnt.min()), int(cnt.max())]}
+        dist.barrier()
+    pc.close()
+    if full is not None:
+        full.close()
+    _abi.check(lib.fei_comm_bind_corpus(corpus.handle))
+    out["sharded_vs_unsharded"] = res
+    return out
+
+
+def run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, allmax, step_ms):
+    """cfg5's other leg and the list form of the result: (a) the cfg-2 query on the full shards, exchanged with the sparse grouped-
+    broadcast all-gatherv of the compacted lists; (b) the GLOBAL ordered lists of the 32-pattern batch materialised on every rank
+    from the gathered masks (what a caller that wants indices rather than masks pays on top of a step)."""
+    out = {}
+    n_total = args.entries * world
+    pr = batch_cfg2_program(n_total)
+    tot = np.zeros(32, dtype=np.uint64)
+
+    def sparse_step():
+        corpus.scan_count(pr, 1)
+        _abi.check(lib.fei_comm_allgather_hits(corpus.handle, 1, None, None, _abi.ptr(tot), None))
+    for _ in range(3):
+        sparse_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        sparse_step()
+    barrier()
+    ms = allmax((time.perf_counter() - t0) * 1e3 / 10)
+    out["cfg2_query_sparse_allgatherv"] = {"ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "memories/s", "hits_total": int(tot[0]),
+                                           "wire": "counts all-gather + one grouped ncclBroadcast per (rank, query) list segment",
+                                           "query": "Tags has_tag python AND flags has_flag F AND date > median AND content matches react|angular"}
+    gl = np.zeros(32, dtype=np.uint64); lms = C.c_float()
+    vals = []
+    for _ in range(3):
+        _abi.check(lib.fei_comm_global_lists(32, _abi.ptr(gl), C.byref(lms)))
+        vals.append(lms.value)
+    lists_ms = allmax(float(np.mean(vals[1:])))
+    out["global_ordered_lists"] = {"build_ms": lists_ms, "ms_per_step_including_lists": step_ms + lists_ms,
+                                   "value_including_lists": n_total / ((step_ms + lists_ms) * 1e-3), "unit": "memories/s",
+                                   "list_bytes_per_rank": int(gl.sum()) * 8,
+                                   "note": "32 global ordered index lists built on every rank's device from the gathered masks (k_count / k_scan_blocks / k_emit over the rank segments)"}
+    return out
+
+
+def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
+    """Streaming end to end: `batches` batches of raw records (file contents: header text + '---' + body, as read from disk) go from
+    pinned host memory through fei_corpus_load_raw (H2D on the copy stream, then UTF-8 validation / newline folding / split / strip /
+    tiling / header directory kernels) and fei_scan_hits (k_body + compaction + 32 ordered hit lists D2H).  Two corpus handles
+    alternate: batch k+1 is uploaded and packed while batch k is scanned and its hits travel back."""
+    from concurrent.futures import ThreadPoolExecutor
     from fei_b200.corpus import Corpus
     n = min(args.e2e_entries, corpus.n)
+    nb = max(1, args.e2e_batches)
     host = corpus.fetch(0, n)                           # canonical host arrays of the first n records
-    arrays = {"n": n, "global_base": 0, "hdr": host["hdr"], "hdr_off": host["hdr_off"], "body": host["body"], "body_off": host["body_off"],
-              "ts": host["ts"], "wall": host["wall"], "flags8": host["flags8"], "fsb": host["fsb"]}
+    hdr, ho, body, bo = host["hdr"].tobytes(), host["hdr_off"], host["body"].tobytes(), host["body_off"]
+    parts = []
+    for i in range(n):                                  # the file as create_memory_content writes it (utils.py:129-132)
+        parts.append(hdr[int(ho[i]):int(ho[i + 1])]); parts.append(b"---\n"); parts.append(body[int(bo[i]):int(bo[i + 1])])
+    raw = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    raw_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((ho[1:] - ho[:-1]) + 4 + (bo[1:] - bo[:-1]), out=raw_off[1:])
+    del parts, hdr, body
+    arrays = {"n": n, "global_base": 0, "raw": raw, "raw_off": raw_off, "ts": host["ts"], "wall": host["wall"], "flags8": host["flags8"],
+              "fsb": (host["fsb"] & np.uint32(0x00FFFFFF))}
     pinned = []
-    for k in ("hdr", "body", "hdr_off", "body_off", "ts", "wall", "flags8", "fsb"):
+    keys = ("raw", "raw_off", "ts", "wall", "flags8", "fsb")
+    for k in keys:
         a = arrays[k]
         if lib.fei_host_register(a.ctypes.data, a.nbytes) == 0:
             pinned.append(a)
-    h2d = sum(arrays[k].nbytes for k in ("hdr", "body", "hdr_off", "body_off", "ts", "wall", "flags8", "fsb"))
-    c2 = Corpus()
+    h2d = sum(arrays[k].nbytes for k in keys)
+    bw_h2d, bw_d2h = C.c_float(), C.c_float()
+    barrier()                                           # every rank measures its link while the others use theirs
+    _abi.check(lib.fei_host_copy_bench(raw.ctypes.data, min(raw.nbytes, 1 << 30), 3, C.byref(bw_h2d), C.byref(bw_d2h)))
+    barrier()
+    cs = [Corpus(), Corpus()]
     bufs = [np.zeros(n, dtype=np.uint64) for _ in range(nq)]
     for b in bufs:
         if lib.fei_host_register(b.ctypes.data, b.nbytes) == 0:
@@ -381,23 +554,42 @@ def run_e2e(args, corpus, prog, nq, lib, _abi):
     ptrs = (C.c_void_p * 32)(*[b.ctypes.data for b in bufs])
     cap = np.zeros(32, dtype=np.uint64); cap[:nq] = n
     nh = np.zeros(32, dtype=np.uint64)
+    pool = ThreadPoolExecutor(1)
+
+    def load(c):
+        assert c.load_raw(arrays).all()
+
+    def one_step():
+        d2h = 0
+        fut = pool.submit(load, cs[0])
+        for k in range(nb):
+            fut.result()
+            if k + 1 < nb:
+                fut = pool.submit(load, cs[(k + 1) % 2])
+            _abi.check(lib.fei_scan_hits(cs[k % 2].handle, prog, len(prog), ptrs, _abi.ptr(cap), _abi.ptr(nh)))
+            d2h += int(nh[:nq].sum()) * 8
+        return d2h
+    one_step()                                          # warm-up: allocations, first-touch
     times = []
     d2h = 0
-    for it in range(2 + 3):
+    for _ in range(2):
+        barrier()
         t0 = time.perf_counter()
-        c2.load(arrays)
-        _abi.check(lib.fei_scan_hits(c2.handle, prog, len(prog), ptrs, _abi.ptr(cap), _abi.ptr(nh)))
-        dt = time.perf_counter() - t0
-        d2h = int(nh[:nq].sum()) * 8
-        if it >= 2:
-            times.append(dt)
+        d2h = one_step()
+        times.append(time.perf_counter() - t0)
+    pool.shutdown()
     for a in pinned:
         lib.fei_host_unregister(a.ctypes.data)
-    c2.close()
+    for c in cs:
+        c.close()
     dt = float(np.mean(times))
-    return {"value": n / dt, "unit": "memories/s", "entries_per_step": n, "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "path": "pinned host arrays -> fei_corpus_load (H2D + tiling kernels) -> fei_scan_hits (k_body + compaction) -> 32 ordered hit lists D2H"}
+    return {"value": n * nb / dt, "unit": "memories/s", "entries_per_step": n * nb, "batches_per_step": nb, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(h2d) * nb, "d2h_bytes_per_step": int(d2h),
+            "h2d_gbs_achieved": h2d * nb / dt / 1e9, "h2d_gbs_measured": float(bw_h2d.value), "d2h_gbs_measured": float(bw_d2h.value),
+            "frac_of_measured_h2d": (h2d * nb / dt / 1e9) / float(bw_h2d.value) if bw_h2d.value else None,
+            "path": "pinned host buffers of raw file contents -> fei_corpus_load_raw (H2D + ingest + tiling + header directory, copy stream) "
+                    "|| fei_scan_hits of the previous batch (k_body + compaction + 32 ordered hit lists D2H, compute stream); "
+                    "%d batches of %d records per step (the same pinned batch is re-sent: every batch is copied, packed and scanned anew)" % (nb, n)}
 
 
 def api_on_disk(n_files: int):
@@ -558,7 +750,10 @@ def run_extra(args, corpus, st, peak, lib, _abi):
     nb = args.chain_blocks
     info = _abi.device_info() if hasattr(_abi, "device_info") else {}
     sm_mhz_max = float(measured_peak_field("sm_max_mhz", 1965.0))
-    alu_peak = float(info.get("sm_count", 148)) * 64 * sm_mhz_max * 1e6
+    alu_nominal = float(info.get("sm_count", 148)) * 64 * sm_mhz_max * 1e6
+    tops, mb_ms = C.c_float(), C.c_float()
+    _abi.check(lib.fei_microbench_alu(5, C.byref(tops), C.byref(mb_ms)))       # LOP3 / SHF issue rate of this chip, measured now
+    alu_peak = float(tops.value) * 1e12
     cpu_rate, cpu_dt = cpu_chain_rate(min(nb, 50_000))
     out["cfg4_validate_chain"] = {
         "metric": "sha256_chain_blocks_per_sec", "value": (nb - 1) / t, "unit": "chain blocks/s", "blocks": nb, "kernel_ms": t * 1e3,
@@ -570,7 +765,8 @@ def run_extra(args, corpus, st, peak, lib, _abi):
         # instructions per compression in the kernel's SASS (profiles/r1_sass_evidence.txt); ncu reports the pipe 95 % busy.
         "roofline_alu": {"bound": "int32 ALU pipe", "achieved": (nb - 1) * 6 * 1300 / t / 1e12, "unit": "T lane-ops/s",
                          "peak": alu_peak / 1e12, "frac": (nb - 1) * 6 * 1300 / t / alu_peak,
-                         "peak_source": "sm_count x 64 lanes x %.0f MHz (max SM clock)" % sm_mhz_max,
+                         "peak_source": "measured: fei_microbench_alu (8 independent LOP3 + SHF chains per thread, %d SMs x 8 CTAs x 256 threads, best of 5, %.3f ms)" % (info.get("sm_count", 148), mb_ms.value),
+                         "peak_nominal": alu_nominal / 1e12, "peak_nominal_source": "sm_count x 64 lanes x %.0f MHz (max SM clock)" % sm_mhz_max,
                          "alu_instr_per_compression": 1300, "ncu": "profiles/r1e_k_sha256_validate_1M.txt"},
         "cpu_baseline": {"value": cpu_rate, "unit": "chain blocks/s", "cores": 1, "kind": "port",
                          "sample": f"validate_chain oracle (json.dumps + hashlib, memorychain.py:596-618) over {min(nb, 50_000)} blocks, {cpu_dt:.2f} s"},

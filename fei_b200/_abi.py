@@ -74,6 +74,8 @@ _SIGS = {
     "fei_device_info": (C.c_int, [_P, _P, _P, _P]),
     "fei_host_register": (C.c_int, [_P, _U64]),
     "fei_host_unregister": (C.c_int, [_P]),
+    "fei_microbench_alu": (C.c_int, [C.c_int, _P, _P]),
+    "fei_host_copy_bench": (C.c_int, [_P, _U64, C.c_int, _P, _P]),
     "fei_corpus_create": (C.c_int, [_P]),
     "fei_corpus_destroy": (C.c_int, [_P]),
     "fei_corpus_load": (C.c_int, [_P, _P]),
@@ -103,6 +105,13 @@ _SIGS = {
     "fei_comm_destroy": (C.c_int, []),
     "fei_comm_allgather_hits": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "fei_comm_allreduce_first_bad": (C.c_int, [_P, _P]),
+    "fei_comm_bind_corpus": (C.c_int, [_P]),
+    "fei_comm_is_p2p": (C.c_int, []),
+    "fei_comm_scan_gather": (C.c_int, [_P, _P, _U64, _P]),
+    "fei_comm_gathered_checksum": (C.c_int, [C.c_uint32, _P, _P, _P]),
+    "fei_comm_global_lists": (C.c_int, [C.c_uint32, _P, _P]),
+    "fei_scan_list_checksum": (C.c_int, [_P, C.c_uint32, _P, _P]),
+    "fei_scan_fetch_hits": (C.c_int, [_P, C.c_uint32, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

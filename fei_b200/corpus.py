@@ -104,11 +104,14 @@ class Corpus:
 
     def scan_hits(self, prog: bytes, nq: int, cap: Optional[int] = None) -> List[np.ndarray]:
         """Ordered global record indices per query."""
-        if cap is None:
+        if cap is None:                                  # one scan: counts first, then exactly-sized copies of the resident lists
             counts = self.scan_count(prog, nq)
-            caps = [int(c) for c in counts]
-        else:
-            caps = [cap] * nq
+            bufs = [np.empty(max(1, int(c)), dtype=np.uint64) for c in counts]
+            ptrs = (C.c_void_p * 32)(*[_abi.ptr(b) for b in bufs])
+            cap_arr = np.zeros(32, dtype=np.uint64); cap_arr[:nq] = counts
+            _abi.check(_abi.lib().fei_scan_fetch_hits(self._h, nq, ptrs, _abi.ptr(cap_arr)))
+            return [bufs[q][:int(counts[q])] for q in range(nq)]
+        caps = [cap] * nq
         bufs = [np.zeros(max(1, c), dtype=np.uint64) for c in caps]
         ptrs = (C.c_void_p * 32)(*[_abi.ptr(b) for b in bufs])
         cap_arr = np.zeros(32, dtype=np.uint64); cap_arr[:nq] = caps
@@ -126,6 +129,12 @@ class Corpus:
                                                          _abi.ptr(cnt), _abi.ptr(first), cap, C.byref(n)))
         raw = blob.tobytes()
         return [(raw[int(off[k]):int(off[k + 1])], int(cnt[k]), int(first[k])) for k in range(n.value)]
+
+    def list_checksums(self, nq: int):
+        """(A, S) per query of the ordered lists the last scan_count left on the device (fei_scan_list_checksum)."""
+        a = np.zeros(32, dtype=np.uint64); s = np.zeros(32, dtype=np.uint64)
+        _abi.check(_abi.lib().fei_scan_list_checksum(self._h, nq, _abi.ptr(a), _abi.ptr(s)))
+        return a[:nq], s[:nq]
 
     def timing(self) -> Dict[str, float]:
         t = _abi.ScanTiming()

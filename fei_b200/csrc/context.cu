@@ -118,3 +118,31 @@ extern "C" int fei_host_unregister(void* p) {
   FEI_CUDA(cudaHostUnregister(p));
   return FEI_OK;
 }
+
+/* Measured host <-> device copy bandwidth of a caller buffer (pinned with fei_host_register for the PCIe rate): best of
+ * `reps` timed copies each way, CUDA events on the copy stream.  The roofline of every "from host buffers" number. */
+extern "C" int fei_host_copy_bench(void* host, uint64_t bytes, int reps, float* h2d_gbs, float* d2h_gbs) {
+  FEI_TRY(require_ready());
+  if (!host || !bytes || reps < 1) { set_error("bad argument"); return FEI_E_BADARG; }
+  cudaStream_t s = ctx().copy_stream;
+  DevBuf d;
+  FEI_TRY(d.alloc(bytes));
+  cudaEvent_t e0, e1;
+  FEI_CUDA(cudaEventCreate(&e0)); FEI_CUDA(cudaEventCreate(&e1));
+  float best[2] = {0.f, 0.f};
+  for (int dir = 0; dir < 2; ++dir)
+    for (int r = 0; r < reps + 1; ++r) {
+      FEI_CUDA(cudaEventRecord(e0, s));
+      if (dir == 0) FEI_CUDA(cudaMemcpyAsync(d.p, host, bytes, cudaMemcpyHostToDevice, s));
+      else FEI_CUDA(cudaMemcpyAsync(host, d.p, bytes, cudaMemcpyDeviceToHost, s));
+      FEI_CUDA(cudaEventRecord(e1, s));
+      FEI_CUDA(cudaStreamSynchronize(s));
+      float ms = 0; FEI_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const float gbs = (float)((double)bytes / 1e9 / (ms * 1e-3));
+      if (r > 0 && gbs > best[dir]) best[dir] = gbs;
+    }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (h2d_gbs) *h2d_gbs = best[0];
+  if (d2h_gbs) *d2h_gbs = best[1];
+  return FEI_OK;
+}

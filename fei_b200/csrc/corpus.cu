@@ -198,7 +198,12 @@ extern "C" int fei_corpus_create(fei_corpus** out) {
 
 extern "C" int fei_corpus_destroy(fei_corpus* c) {
   if (!c) return FEI_OK;
+  { std::lock_guard<std::mutex> lock(c->mu); }       // let a scan that another thread still runs on this handle finish
+  cudaStreamSynchronize(ctx().stream);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
   delete c;
   return FEI_OK;
 }
@@ -211,7 +216,7 @@ extern "C" int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h) {
   if (h->n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }
   if (h->n && (!h->hdr_off || !h->body_off || !h->ts || !h->wall || !h->flags8 || !h->fsb)) { set_error("missing corpus array"); return FEI_E_BADARG; }
   Context& cx = ctx();
-  cudaStream_t s = cx.stream;
+  cudaStream_t s = cx.copy_stream;                   // see fei_corpus_load_raw: loads overlap scans of other handles
   uint64_t n = h->n;
   c->n = n; c->global_base = h->global_base; c->loaded = false;
   static const uint64_t zero_off[1] = {0};

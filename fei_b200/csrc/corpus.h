@@ -58,6 +58,7 @@ struct fei_corpus {
   uint32_t n_cols = 0;
   bool has_text_records = false;         // some record's header is parsed from its text (keys not in the dictionary)
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
+  fei::DevBuf stage_raw, stage_raw_off, stage_ms, stage_hlen, stage_blen;   // raw ingest staging (ingest.cu)
   // scan scratch (grown on demand, reused across scans)
   fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors, live_list;
   fei::CompactScratch compact;
@@ -66,6 +67,10 @@ struct fei_corpus {
   uint64_t last_counts[32] = {0};
   fei_scan_timing timing = {};
   cudaEvent_t ev[8] = {nullptr};
+  // chunked scans: compaction / all-gather of a finished chunk run on `side` under the next chunk's scan (scan.cu)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_chunk[16] = {nullptr};
+  cudaEvent_t ev_side = nullptr;
 };
 
 namespace fei {
@@ -74,6 +79,21 @@ int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off
 // builds the header directory from hdr / hdr_off already on the device (hdir.cu)
 int build_header_dir(fei_corpus* c, cudaStream_t s);
 int exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, DevBuf& tmp, cudaStream_t s);
+// Hook of a chunked scan: on_chunk is called on the host right after the work that makes the hit masks of records
+// [rec_begin, rec_end) final has been queued, with `side` already waiting for it; on_done after the last chunk.
+struct ChunkHook {
+  virtual int on_chunk(uint32_t k, uint32_t n_chunks, uint64_t rec_begin, uint64_t rec_end, cudaStream_t side) = 0;
+  virtual int on_done(cudaStream_t side) { return FEI_OK; }
+  virtual ~ChunkHook() {}
+};
+enum { kScanCompactNone = 0, kScanCompactLists = 1 };
+// queues a whole scan (nothing waits for the GPU); force_chunks = 0 lets the scan pick its chunking.  Caller holds c->mu.
+int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_mode, ChunkHook* hook, uint32_t force_chunks);
+int finish_timing(fei_corpus* c, bool compacted);
+void plan_chunks(uint64_t n, uint32_t chunks, uint64_t* rec_bounds /* chunks + 1 */);
+int compact_segments(const uint32_t* masks, uint64_t seg_stride, const uint64_t* seg_n, const uint64_t* seg_base, uint32_t n_seg, uint32_t nq,
+                     CompactScratch& sc, uint64_t stride, uint64_t* lists, uint64_t* totals_out, cudaStream_t s);
+int list_checksum(const uint64_t* list, uint64_t count, DevBuf& tmp, uint64_t* a_out, uint64_t* s_out, cudaStream_t s);
 int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t global_base, CompactScratch& sc,
                   uint64_t* counts_out, DevBuf* lists, uint64_t* stride_out, uint32_t* launches, cudaStream_t s);
 }

@@ -131,13 +131,16 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   if (!c || !h || !raw_off || (h->n && !raw)) { set_error("null argument"); return FEI_E_BADARG; }
   if (h->n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }
   if (h->n && (!h->ts || !h->wall || !h->flags8 || !h->fsb)) { set_error("missing meta array"); return FEI_E_BADARG; }
-  cudaStream_t s = ctx().stream;
+  // loads run on the copy stream: a batch can be uploaded / normalised / tiled into one handle while another handle is being
+  // scanned on the compute stream (streaming e2e use); the staging buffers live in the handle (grow-only) because a
+  // cudaFree in the middle of a pipeline synchronises the whole device
+  cudaStream_t s = ctx().copy_stream;
   uint64_t n = h->n;
   c->loaded = false;
   uint64_t raw_bytes = n ? raw_off[n] : 0;
-  DevBuf d_raw, d_raw_off, d_ms, d_hlen, d_blen;
-  FEI_TRY(d_raw.alloc(raw_bytes + 64)); FEI_TRY(d_raw_off.alloc((n + 1) * 8));
-  FEI_TRY(d_ms.alloc((n ? n : 1) * sizeof(RawMeasure))); FEI_TRY(d_hlen.alloc((n ? n : 1) * 4)); FEI_TRY(d_blen.alloc((n ? n : 1) * 4));
+  DevBuf& d_raw = c->stage_raw; DevBuf& d_raw_off = c->stage_raw_off; DevBuf& d_ms = c->stage_ms; DevBuf& d_hlen = c->stage_hlen; DevBuf& d_blen = c->stage_blen;
+  FEI_TRY(d_raw.ensure(raw_bytes + 64)); FEI_TRY(d_raw_off.ensure((n + 1) * 8));
+  FEI_TRY(d_ms.ensure((n ? n : 1) * sizeof(RawMeasure))); FEI_TRY(d_hlen.ensure((n ? n : 1) * 4)); FEI_TRY(d_blen.ensure((n ? n : 1) * 4));
   if (raw_bytes) FEI_CUDA(cudaMemcpyAsync(d_raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, s));
   FEI_CUDA(cudaMemsetAsync((uint8_t*)d_raw.p + raw_bytes, 0, 64, s));
   FEI_CUDA(cudaMemcpyAsync(d_raw_off.p, raw_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -183,7 +186,7 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   FEI_CUDA(cudaGetLastError());
   FEI_TRY(build_tiles(c, body.as<uint8_t>(), body_off.as<uint64_t>(), s));
   FEI_TRY(build_header_dir(c, s));
-  if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); }
+  if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); d_raw.release(); }
   c->loaded = true;
   return FEI_OK;
 }

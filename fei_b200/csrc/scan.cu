@@ -520,8 +520,12 @@ struct BodyArgs {
   uint64_t n_groups;
   uint32_t* hits;              // in: alive masks (when has_alive), out: final hit masks
   int has_alive;
-  unsigned long long* counter; // [0] = next group, [1] = tile bytes of the groups entered, [3] = tile bytes requested, [4] = live records (gather)
+  unsigned long long* counter; // [1] = tile bytes of the groups entered, [3] = tile bytes requested, [4] = live records (gather)
   unsigned long long gather_max;   // k_body_sticky stands down (and k_body_gather runs) when 0 < counter[4] <= gather_max
+  // one launch covers the groups [g_begin, n_groups): the scan is cut into chunks of whole windows so that the compaction
+  // (and, multi-GPU, the all-gather) of a finished chunk overlaps the next chunk's scan; *next hands out the chunk's groups
+  unsigned long long g_begin;
+  unsigned long long* next;
 };
 
 constexpr int kBodyThreads = 1024;
@@ -619,7 +623,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
 
   for (;;) {
     unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(a.counter, 1ull);
+    if (lane == 0) g = a.g_begin + atomicAdd(a.next, 1ull);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= a.n_groups) break;
     const uint32_t rec = a.grp_rec[g * 32 + lane];
@@ -938,7 +942,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
 
   for (;;) {
     unsigned long long g = 0;
-    if (lane == 0) g = atomicAdd(a.counter, 2ull);
+    if (lane == 0) g = a.g_begin + atomicAdd(a.next, 2ull);
     g = __shfl_sync(0xffffffffu, g, 0);
     if (g >= a.n_groups) break;
     Grp A, B;
@@ -1060,12 +1064,15 @@ static int launch_body(const BodyArgs& a, unsigned grid, size_t smem, cudaStream
 // ---------------------------------------------------------------- compaction
 constexpr int kCompactBlock = 256;          // threads
 constexpr int kCompactPer = 8;              // records per thread -> 2048 records per block
+constexpr uint64_t kCompactRecs = (uint64_t)kCompactBlock * kCompactPer;
 
-// counts[block * nq + q] = records of this block that hit query q
+// counts[block * nq + q] = records of this block that hit query q  (block = blk0 + blockIdx.x: a chunk of the scan
+// compacts its own blocks while the next chunk is still being scanned)
 __global__ void __launch_bounds__(kCompactBlock)
-k_count(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, uint32_t* __restrict__ counts) {
+k_count(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, uint64_t blk0, uint32_t* __restrict__ counts) {
   __shared__ uint32_t sh[32][8];
-  uint64_t base = (uint64_t)blockIdx.x * kCompactBlock * kCompactPer;
+  const uint64_t blk = blk0 + blockIdx.x;
+  uint64_t base = blk * kCompactRecs;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t cnt = 0;                        // lane q accumulates query q
   for (int r = 0; r < kCompactPer; ++r) {
@@ -1081,21 +1088,22 @@ k_count(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, uint32_t* __
   if (threadIdx.x < 32 && threadIdx.x < nq) {
     uint32_t s = 0;
     for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
-    counts[(uint64_t)blockIdx.x * nq + threadIdx.x] = s;
+    counts[blk * nq + threadIdx.x] = s;
   }
 }
 
-// per query: exclusive scan over blocks (one thread block per query; n_blocks up to millions is fine)
-__global__ void k_scan_blocks(const uint32_t* __restrict__ counts, uint64_t nblocks, uint32_t nq,
-                              uint64_t* __restrict__ offsets, uint64_t* __restrict__ totals) {
+// per query: exclusive scan over the blocks [blk0, blk0 + nblocks) (one thread block per query), continuing from
+// carry[q] (the hits of the blocks before blk0) and leaving the new running total there
+__global__ void k_scan_blocks(const uint32_t* __restrict__ counts, uint64_t blk0, uint64_t nblocks, uint32_t nq,
+                              uint64_t* __restrict__ offsets, uint64_t* __restrict__ carry_io) {
   __shared__ uint64_t sh[1024];
   __shared__ uint64_t carry;
   uint32_t q = blockIdx.x;
-  if (threadIdx.x == 0) carry = 0;
+  if (threadIdx.x == 0) carry = carry_io[q];
   __syncthreads();
   for (uint64_t base = 0; base < nblocks; base += blockDim.x) {
     uint64_t b = base + threadIdx.x;
-    uint64_t v = b < nblocks ? counts[b * nq + q] : 0;
+    uint64_t v = b < nblocks ? counts[(blk0 + b) * nq + q] : 0;
     sh[threadIdx.x] = v;
     __syncthreads();
     for (int o = 1; o < blockDim.x; o <<= 1) {
@@ -1105,20 +1113,21 @@ __global__ void k_scan_blocks(const uint32_t* __restrict__ counts, uint64_t nblo
       __syncthreads();
     }
     uint64_t incl = sh[threadIdx.x];
-    if (b < nblocks) offsets[b * nq + q] = carry + incl - v;
+    if (b < nblocks) offsets[(blk0 + b) * nq + q] = carry + incl - v;
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry += incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) totals[q] = carry;
+  if (threadIdx.x == 0) carry_io[q] = carry;
 }
 
 // ordered emit: lists[q * stride + rank] = global_base + i
 __global__ void __launch_bounds__(kCompactBlock)
-k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_t* __restrict__ offsets,
+k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_t* __restrict__ offsets, uint64_t blk0,
        uint64_t global_base, uint64_t stride, uint64_t* __restrict__ lists) {
   __shared__ uint32_t wcnt[8][32];          // [warp][query] hits of this warp's records
-  uint64_t base = (uint64_t)blockIdx.x * kCompactBlock * kCompactPer;
+  const uint64_t blk = blk0 + blockIdx.x;
+  uint64_t base = blk * kCompactRecs;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t m[kCompactPer];
   uint32_t cnt = 0;
@@ -1133,7 +1142,7 @@ k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_
   wcnt[warp][lane] = cnt;
   __syncthreads();
   for (uint32_t q = 0; q < nq; ++q) {
-    uint64_t pos = offsets[(uint64_t)blockIdx.x * nq + q];
+    uint64_t pos = offsets[blk * nq + q];
     for (int w = 0; w < warp; ++w) pos += wcnt[w][q];
     for (int r = 0; r < kCompactPer; ++r) {
       uint32_t bal = __ballot_sync(0xffffffffu, (m[r] >> q) & 1u);
@@ -1145,6 +1154,21 @@ k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_
       pos += __popc(bal);
     }
   }
+}
+
+__global__ void k_fill32(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// Order-sensitive checksum of an index list: sum_k (k + 1) * v[k] and sum_k v[k] (mod 2^64).  Two lists agree on both
+// sums iff (with overwhelming probability) they hold the same indices in the same order; the pair (A, S) of the
+// concatenation of two lists follows from the parts: A = A1 + A2 + len1 * S2.
+__global__ void __launch_bounds__(256) k_list_checksum(const uint64_t* __restrict__ v, uint64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long a = 0, s = 0;
+  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) { a += (k + 1) * v[k]; s += v[k]; }
+  for (int o = 16; o; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); s += __shfl_down_sync(0xffffffffu, s, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, s); }
 }
 
 // ---------------------------------------------------------------- host side
@@ -1179,7 +1203,45 @@ static int check_prog(const uint8_t* prog, uint64_t len) {
   return FEI_OK;
 }
 
-static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
+
+// ---- chunking: the body pass runs as up to kMaxChunks launches over runs of whole windows (a window = kWindow consecutive
+// records = kWindow / 32 groups, so a chunk's hit masks are one contiguous record range).  The moment a chunk's masks are
+// final its compaction (and the hook, e.g. the NCCL all-gather of comm.cu) is queued on the side stream and runs under the
+// next chunk's scan: the 32-pattern scan is shared-memory bound and leaves three quarters of the HBM bandwidth idle.
+constexpr uint32_t kMaxChunks = 16;
+struct ChunkPlan { uint32_t n = 1; uint64_t g[kMaxChunks + 1] = {0}; uint64_t rec[kMaxChunks + 1] = {0}; };
+
+static uint32_t chunk_count(uint64_t n_windows, bool allow) {
+  uint32_t want = 0;
+  if (const char* e = getenv("FEI_SCAN_CHUNKS")) want = (uint32_t)atoi(e);
+  if (!allow) return 1;
+  if (!want) want = (uint32_t)(n_windows / 160);                 // ~650 k records per chunk and up, at most 8 chunks
+  if (want > 8 && !getenv("FEI_SCAN_CHUNKS")) want = 8;
+  if (want > kMaxChunks) want = kMaxChunks;
+  if (want > n_windows) want = (uint32_t)n_windows;
+  return want ? want : 1;
+}
+void plan_chunks(uint64_t n, uint32_t chunks, uint64_t* rec_bounds) {       // shared with comm.cu: every rank derives every rank's bounds
+  const uint64_t n_windows = (n + kWindow - 1) / kWindow;
+  for (uint32_t k = 0; k <= chunks; ++k) { uint64_t r = n_windows * k / chunks * kWindow; rec_bounds[k] = r < n ? r : n; }
+  rec_bounds[chunks] = n;
+}
+
+static int ensure_side(fei_corpus* c) {
+  if (!c->side) {                                              // highest priority: a finished chunk's compaction / all-gather gets the first SM that frees up
+    int lo = 0, hi = 0;
+    FEI_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    FEI_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+  }
+  for (auto& e : c->ev_chunk) if (!e) FEI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (!c->ev_side) FEI_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+  return FEI_OK;
+}
+
+enum { kCompactNone = kScanCompactNone, kCompactLists = kScanCompactLists };
+
+// Everything is queued on the context stream (and the corpus' side stream); nothing here waits for the GPU.
+int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_mode, ChunkHook* hook, uint32_t force_chunks) {
   FEI_TRY(require_ready());
   if (!c || !c->loaded) { set_error("corpus not loaded"); return FEI_E_STATE; }
   FEI_TRY(check_prog(prog, prog_len));
@@ -1189,16 +1251,28 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
   uint64_t n = c->n;
   c->timing = fei_scan_timing{};
   c->last_nq = h.n_queries;
+  for (uint32_t q = 0; q < 32; ++q) c->last_counts[q] = 0;
   FEI_TRY(c->prog.ensure(prog_len + 16));
   FEI_TRY(c->hits.ensure((n ? n : 1) * sizeof(uint32_t)));
-  FEI_TRY(c->work_counter.ensure(8 * sizeof(unsigned long long)));
+  FEI_TRY(c->work_counter.ensure((8 + kMaxChunks) * sizeof(unsigned long long)));
+  FEI_TRY(ensure_side(c));
   FEI_CUDA(cudaEventRecord(c->ev[0], s));
   FEI_CUDA(cudaMemcpyAsync(c->prog.p, prog, prog_len, cudaMemcpyHostToDevice, s));
-  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, 8 * sizeof(unsigned long long), s));
+  FEI_CUDA(cudaMemsetAsync(c->work_counter.p, 0, (8 + kMaxChunks) * sizeof(unsigned long long), s));
   bool need_head = h.head_mask != 0;
   bool need_body = h.off_body_dfa != 0 && h.body_mask != 0;
   if ((h.off_name_dfa[0] || h.off_name_dfa[1] || h.off_name_dfa[2]) && !c->name.p) {
     set_error("program reads filename / id / hostname but the corpus was packed without names"); return FEI_E_STATE;
+  }
+  const uint32_t nq = h.n_queries;
+  const uint64_t nblocks = (n + kCompactRecs - 1) / kCompactRecs;
+  if (compact_mode == kCompactLists) {
+    FEI_TRY(c->compact.blk_counts.ensure((nblocks ? nblocks : 1) * nq * sizeof(uint32_t)));
+    FEI_TRY(c->compact.blk_offsets.ensure((nblocks ? nblocks : 1) * nq * sizeof(uint64_t)));
+    FEI_TRY(c->compact.totals.ensure(32 * sizeof(uint64_t)));
+    FEI_TRY(c->hit_lists.ensure((n ? n : 1) * nq * sizeof(uint64_t)));
+    c->hit_list_stride = n ? n : 1;
+    FEI_CUDA(cudaMemsetAsync(c->compact.totals.p, 0, 32 * sizeof(uint64_t), s));
   }
   FEI_CUDA(cudaEventRecord(c->ev[1], s));
   uint32_t launches = 0;
@@ -1250,51 +1324,88 @@ static int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len) {
     }
   }
   FEI_CUDA(cudaEventRecord(c->ev[2], s));
+
+  // ---- body pass, chunk by chunk
+  fei_prog_dfa d; memset(&d, 0, sizeof(d));
+  size_t smem = 0;
+  int acc_mode = 0; bool direct = false, sticky_kernel = false, gather = false;
   if (n && need_body) {
-    fei_prog_dfa d; memcpy(&d, prog + h.off_body_dfa, sizeof(d));
-    size_t smem = d.table_bytes;
+    memcpy(&d, prog + h.off_body_dfa, sizeof(d));
+    smem = d.table_bytes;
     if (smem > 220 * 1024) { set_error("content automaton needs %zu bytes of shared memory (limit 220 KiB)", smem); return FEI_E_UNSUPPORTED; }
-    BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
-               c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>(), 0ull};
-    unsigned grid = (unsigned)cx.sm_count;
-    uint32_t n_acc = d.n_acc;
-    int acc_mode = d.sticky ? 3 : n_acc <= 32 ? 1 : n_acc <= 64 ? 2 : 0;
-    bool direct = d.n_cols == 256;
-    int rc;
-    if (direct && acc_mode == 3 && (uint64_t)d.n_states * d.row_stride * 2 + kStickyAddrSlack <= kStickyAddrLimit) {
-      if (need_head && n >= 65536) {
-        // header predicates ran first: when they left few records alive, scan those record by record (k_body_gather); both
-        // kernels are launched and the live count on the device decides which one works (no host round trip)
-        a.gather_max = n / kGatherDiv;
-        FEI_TRY(c->live_list.ensure((a.gather_max + 1) * sizeof(uint32_t)));
-        k_live_list<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->hits.as<uint32_t>(), n, c->live_list.as<uint32_t>(), a.counter + 4, a.gather_max);
-        FEI_CUDA(cudaFuncSetAttribute(k_body_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_body_gather<<<grid, kBodyThreads, smem, s>>>(a, c->live_list.as<uint32_t>(), c->rec_pos.as<uint32_t>());
-        launches += 2;
-      }
-      const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
-      FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
-      k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);
-      rc = FEI_OK;
-    } else if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
-    else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
-    FEI_TRY(rc);
-    ++launches;
+    acc_mode = d.sticky ? 3 : d.n_acc <= 32 ? 1 : d.n_acc <= 64 ? 2 : 0;
+    direct = d.n_cols == 256;
+    sticky_kernel = direct && acc_mode == 3 && (uint64_t)d.n_states * d.row_stride * 2 + kStickyAddrSlack <= kStickyAddrLimit;
+    gather = sticky_kernel && need_head && n >= 65536;         // few survivors of the header pass: one thread per record (device-side choice)
   } else if (n && !need_head) {
     // no condition reads the corpus at all (constant queries): every record gets the constant verdict
     // (program.py folds constants into head conditions, so this only happens for empty condition lists)
-    uint32_t all_q = h.n_queries >= 32 ? 0xFFFFFFFFu : ((1u << h.n_queries) - 1u);
-    std::vector<uint32_t> fill(n, all_q);
-    FEI_CUDA(cudaMemcpyAsync(c->hits.p, fill.data(), n * 4, cudaMemcpyHostToDevice, s));
-    FEI_CUDA(cudaStreamSynchronize(s));
+    uint32_t all_q = nq >= 32 ? 0xFFFFFFFFu : ((1u << nq) - 1u);
+    k_fill32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->hits.as<uint32_t>(), n, all_q);
+    ++launches;
+  }
+  ChunkPlan plan;
+  const uint64_t n_windows = (n + kWindow - 1) / kWindow;
+  plan.n = force_chunks ? force_chunks : chunk_count(n_windows, n && need_body && !gather && (compact_mode != kCompactNone || hook));
+  if (plan.n > kMaxChunks) plan.n = kMaxChunks;
+  if (plan.n < 1) plan.n = 1;
+  plan_chunks(n, plan.n, plan.rec);
+  for (uint32_t k = 0; k <= plan.n; ++k) plan.g[k] = (plan.rec[k] + kWindow - 1) / kWindow * (kWindow / 32);
+  plan.g[plan.n] = c->n_groups;
+  const bool side_work = (n && compact_mode != kCompactNone) || hook;
+  BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
+             c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>(), 0ull, 0ull, nullptr};
+  const unsigned grid = (unsigned)cx.sm_count;
+  if (n && need_body && gather) {
+    a.gather_max = n / kGatherDiv;
+    FEI_TRY(c->live_list.ensure((a.gather_max + 1) * sizeof(uint32_t)));
+    k_live_list<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->hits.as<uint32_t>(), n, c->live_list.as<uint32_t>(), a.counter + 4, a.gather_max);
+    FEI_CUDA(cudaFuncSetAttribute(k_body_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.next = a.counter + 8;
+    k_body_gather<<<grid, kBodyThreads, smem, s>>>(a, c->live_list.as<uint32_t>(), c->rec_pos.as<uint32_t>());
+    launches += 2;
+  }
+  for (uint32_t k = 0; k < plan.n; ++k) {
+    if (n && need_body && plan.g[k + 1] > plan.g[k]) {
+      a.g_begin = plan.g[k]; a.n_groups = plan.g[k + 1]; a.next = a.counter + 8 + k;
+      int rc = FEI_OK;
+      if (sticky_kernel) {
+        const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
+        FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
+        k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);
+      } else if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
+      else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
+      FEI_TRY(rc);
+      ++launches;
+    }
+    if (!side_work) continue;
+    FEI_CUDA(cudaEventRecord(c->ev_chunk[k], s));
+    FEI_CUDA(cudaStreamWaitEvent(c->side, c->ev_chunk[k], 0));
+    if (compact_mode == kCompactLists && plan.rec[k + 1] > plan.rec[k]) {
+      const uint64_t b0 = plan.rec[k] / kCompactRecs, b1 = (plan.rec[k + 1] + kCompactRecs - 1) / kCompactRecs;   // chunk bounds are multiples of kWindow (= 2 blocks)
+      k_count<<<(unsigned)(b1 - b0), kCompactBlock, 0, c->side>>>(c->hits.as<uint32_t>(), n, nq, b0, c->compact.blk_counts.as<uint32_t>());
+      k_scan_blocks<<<nq, 1024, 0, c->side>>>(c->compact.blk_counts.as<uint32_t>(), b0, b1 - b0, nq, c->compact.blk_offsets.as<uint64_t>(), c->compact.totals.as<uint64_t>());
+      k_emit<<<(unsigned)(b1 - b0), kCompactBlock, 0, c->side>>>(c->hits.as<uint32_t>(), n, nq, c->compact.blk_offsets.as<uint64_t>(), b0, c->global_base,
+                                                               c->hit_list_stride, c->hit_lists.as<uint64_t>());
+      launches += 3;
+    }
+    if (hook) FEI_TRY(hook->on_chunk(k, plan.n, plan.rec[k], plan.rec[k + 1], c->side));
   }
   FEI_CUDA(cudaEventRecord(c->ev[3], s));
+  if (side_work) {
+    if (hook) FEI_TRY(hook->on_done(c->side));
+    FEI_CUDA(cudaEventRecord(c->ev_side, c->side));
+    FEI_CUDA(cudaStreamWaitEvent(s, c->ev_side, 0));
+  }
+  if (compact_mode == kCompactLists)
+    FEI_CUDA(cudaMemcpyAsync(c->last_counts, c->compact.totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaEventRecord(c->ev[4], s));
   FEI_CUDA(cudaGetLastError());
   c->timing.kernel_launches = launches;
   return FEI_OK;
 }
 
-static int finish_timing(fei_corpus* c, bool compacted) {
+int finish_timing(fei_corpus* c, bool compacted) {
   cudaStream_t s = ctx().stream;
   FEI_CUDA(cudaEventRecord(c->ev[5], s));
   FEI_CUDA(cudaStreamSynchronize(s));
@@ -1302,8 +1413,8 @@ static int finish_timing(fei_corpus* c, bool compacted) {
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[1])); c->timing.h2d_ms = t;
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[1], c->ev[2])); c->timing.head_ms = t;
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[2], c->ev[3])); c->timing.body_ms = t;
-  if (compacted) { FEI_CUDA(cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); c->timing.compact_ms = t; }
-  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[compacted ? 4 : 3], c->ev[5])); c->timing.d2h_ms = t;
+  if (compacted) { FEI_CUDA(cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); c->timing.compact_ms = t; }   // what is left after the last chunk's scan
+  FEI_CUDA(cudaEventElapsedTime(&t, c->ev[4], c->ev[5])); c->timing.d2h_ms = t;
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5])); c->timing.total_ms = t;
   unsigned long long cnt[4] = {0, 0, 0, 0};
   FEI_CUDA(cudaMemcpy(cnt, c->work_counter.as<unsigned long long>(), sizeof(cnt), cudaMemcpyDeviceToHost));
@@ -1312,20 +1423,21 @@ static int finish_timing(fei_corpus* c, bool compacted) {
   return FEI_OK;
 }
 
-// Order-preserving compaction of a mask array into per-query lists of global indices.
-// counts_out[q] = hits of query q; when `lists` is given, lists[q * stride + k] = k-th hit (stride = max count).
+// Order-preserving compaction of a mask array into per-query lists of global indices (one shot, any stream; used for the
+// rank segments of an all-gathered mask array).  counts_out[q] = hits of query q; when `lists` is given,
+// lists[q * stride + k] = k-th hit (stride = max count).
 int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t global_base, CompactScratch& sc,
                   uint64_t* counts_out, DevBuf* lists, uint64_t* stride_out, uint32_t* launches, cudaStream_t s) {
-  uint64_t per_block = (uint64_t)kCompactBlock * kCompactPer;
-  uint64_t nblocks = (n + per_block - 1) / per_block;
+  uint64_t nblocks = (n + kCompactRecs - 1) / kCompactRecs;
   for (uint32_t q = 0; q < nq; ++q) counts_out[q] = 0;
   if (stride_out) *stride_out = 1;
   if (n == 0) return FEI_OK;
   FEI_TRY(sc.blk_counts.ensure(nblocks * nq * sizeof(uint32_t)));
   FEI_TRY(sc.blk_offsets.ensure(nblocks * nq * sizeof(uint64_t)));
   FEI_TRY(sc.totals.ensure(32 * sizeof(uint64_t)));
-  k_count<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, sc.blk_counts.as<uint32_t>());
-  k_scan_blocks<<<nq, 1024, 0, s>>>(sc.blk_counts.as<uint32_t>(), nblocks, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());
+  FEI_CUDA(cudaMemsetAsync(sc.totals.p, 0, 32 * sizeof(uint64_t), s));
+  k_count<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, 0, sc.blk_counts.as<uint32_t>());
+  k_scan_blocks<<<nq, 1024, 0, s>>>(sc.blk_counts.as<uint32_t>(), 0, nblocks, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());
   if (launches) *launches += 2;
   FEI_CUDA(cudaMemcpyAsync(counts_out, sc.totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   FEI_CUDA(cudaStreamSynchronize(s));
@@ -1334,20 +1446,49 @@ int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t globa
     for (uint32_t q = 0; q < nq; ++q) if (counts_out[q] > stride) stride = counts_out[q];
     if (stride_out) *stride_out = stride;
     FEI_TRY(lists->ensure(stride * nq * sizeof(uint64_t)));
-    k_emit<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, sc.blk_offsets.as<uint64_t>(), global_base, stride, lists->as<uint64_t>());
+    k_emit<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, sc.blk_offsets.as<uint64_t>(), 0, global_base, stride, lists->as<uint64_t>());
     if (launches) *launches += 1;
   }
   FEI_CUDA(cudaGetLastError());
   return FEI_OK;
 }
 
-// counts + lists on the device; totals copied to c->last_counts
-static int compact(fei_corpus* c, bool want_lists) {
-  cudaStream_t s = ctx().stream;
-  for (uint32_t q = 0; q < 32; ++q) c->last_counts[q] = 0;
-  FEI_TRY(compact_masks(c->hits.as<uint32_t>(), c->n, c->last_nq, c->global_base, c->compact, c->last_counts,
-                        want_lists ? &c->hit_lists : nullptr, &c->hit_list_stride, &c->timing.kernel_launches, s));
-  FEI_CUDA(cudaEventRecord(c->ev[4], s));
+// Global ordered lists from an all-gathered, rank-major mask array: segment r = masks[r * seg_stride .. + seg_n[r]), its
+// record 0 is global index seg_base[r].  lists[q * stride + k]; totals_out[q] (host) after a final sync.
+int compact_segments(const uint32_t* masks, uint64_t seg_stride, const uint64_t* seg_n, const uint64_t* seg_base, uint32_t n_seg, uint32_t nq,
+                     CompactScratch& sc, uint64_t stride, uint64_t* lists, uint64_t* totals_out, cudaStream_t s) {
+  uint64_t n_max = 0;
+  for (uint32_t r = 0; r < n_seg; ++r) if (seg_n[r] > n_max) n_max = seg_n[r];
+  const uint64_t nb_max = (n_max + kCompactRecs - 1) / kCompactRecs;
+  FEI_TRY(sc.blk_counts.ensure((nb_max ? nb_max : 1) * nq * sizeof(uint32_t)));
+  FEI_TRY(sc.blk_offsets.ensure((nb_max ? nb_max : 1) * nq * sizeof(uint64_t)));
+  FEI_TRY(sc.totals.ensure(32 * sizeof(uint64_t)));
+  FEI_CUDA(cudaMemsetAsync(sc.totals.p, 0, 32 * sizeof(uint64_t), s));
+  for (uint32_t r = 0; r < n_seg; ++r) {
+    const uint64_t n = seg_n[r], nb = (n + kCompactRecs - 1) / kCompactRecs;
+    if (!n) continue;
+    const uint32_t* m = masks + (size_t)r * seg_stride;
+    k_count<<<(unsigned)nb, kCompactBlock, 0, s>>>(m, n, nq, 0, sc.blk_counts.as<uint32_t>());
+    k_scan_blocks<<<nq, 1024, 0, s>>>(sc.blk_counts.as<uint32_t>(), 0, nb, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());   // the carry runs on across segments
+    k_emit<<<(unsigned)nb, kCompactBlock, 0, s>>>(m, n, nq, sc.blk_offsets.as<uint64_t>(), 0, seg_base[r], stride, lists);
+  }
+  if (totals_out) {
+    FEI_CUDA(cudaMemcpyAsync(totals_out, sc.totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    FEI_CUDA(cudaStreamSynchronize(s));
+  }
+  FEI_CUDA(cudaGetLastError());
+  return FEI_OK;
+}
+
+// (A, S) checksums of `count` indices at `list` (device memory); see k_list_checksum
+int list_checksum(const uint64_t* list, uint64_t count, DevBuf& tmp, uint64_t* a_out, uint64_t* s_out, cudaStream_t s) {
+  FEI_TRY(tmp.ensure(16));
+  FEI_CUDA(cudaMemsetAsync(tmp.p, 0, 16, s));
+  if (count) k_list_checksum<<<(unsigned)std::min<uint64_t>((count + 255) / 256, 4096), 256, 0, s>>>(list, count, tmp.as<unsigned long long>());
+  unsigned long long r[2];
+  FEI_CUDA(cudaMemcpyAsync(r, tmp.p, 16, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  *a_out = r[0]; *s_out = r[1];
   return FEI_OK;
 }
 
@@ -1358,7 +1499,7 @@ using namespace fei;
 extern "C" int fei_scan_masks(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint32_t* masks) {
   if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
   std::lock_guard<std::mutex> lock(c->mu);
-  FEI_TRY(run_scan(c, prog, prog_len));
+  FEI_TRY(run_scan(c, prog, prog_len, kCompactNone, nullptr, 0));
   if (masks && c->n) FEI_CUDA(cudaMemcpyAsync(masks, c->hits.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream));
   return finish_timing(c, false);
 }
@@ -1366,10 +1507,10 @@ extern "C" int fei_scan_masks(fei_corpus* c, const uint8_t* prog, uint64_t prog_
 extern "C" int fei_scan_count(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint64_t* nhits) {
   if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
   std::lock_guard<std::mutex> lock(c->mu);
-  FEI_TRY(run_scan(c, prog, prog_len));
-  FEI_TRY(compact(c, true));                 // lists stay on the device for fei_comm_allgather_hits
+  FEI_TRY(run_scan(c, prog, prog_len, kCompactLists, nullptr, 0));     // lists stay on the device (fei_comm_allgather_hits, fei_scan_list_checksum)
+  FEI_TRY(finish_timing(c, true));
   if (nhits) for (uint32_t q = 0; q < c->last_nq; ++q) nhits[q] = c->last_counts[q];
-  return finish_timing(c, true);
+  return FEI_OK;
 }
 
 extern "C" int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_len,
@@ -1377,9 +1518,9 @@ extern "C" int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_l
   if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
   std::lock_guard<std::mutex> lock(c->mu);
   if (!hits || !cap || !nhits) { set_error("null argument"); return FEI_E_BADARG; }
-  FEI_TRY(run_scan(c, prog, prog_len));
-  FEI_TRY(compact(c, true));
+  FEI_TRY(run_scan(c, prog, prog_len, kCompactLists, nullptr, 0));
   cudaStream_t s = ctx().stream;
+  FEI_CUDA(cudaStreamSynchronize(s));                                  // the counts decide how much of every list is copied
   bool truncated = false;
   for (uint32_t q = 0; q < c->last_nq; ++q) {
     nhits[q] = c->last_counts[q];
@@ -1389,6 +1530,33 @@ extern "C" int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_l
   }
   FEI_TRY(finish_timing(c, true));
   if (truncated) { set_error("hit buffer too small for at least one query (see nhits)"); return FEI_E_CAPACITY; }
+  return FEI_OK;
+}
+
+/* copies (a prefix of) the ordered lists the last fei_scan_count left on the device: no second scan */
+extern "C" int fei_scan_fetch_hits(fei_corpus* c, uint32_t nq, uint64_t* const* hits, const uint64_t* cap) {
+  if (!c || !hits || !cap) { set_error("null argument"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (nq == 0 || nq != c->last_nq || !c->hit_lists.p) { set_error("no matching scan result with lists on this corpus"); return FEI_E_STATE; }
+  cudaStream_t s = ctx().stream;
+  bool truncated = false;
+  for (uint32_t q = 0; q < nq; ++q) {
+    uint64_t take = c->last_counts[q] < cap[q] ? c->last_counts[q] : cap[q];
+    if (take < c->last_counts[q]) truncated = true;
+    if (take && hits[q]) FEI_CUDA(cudaMemcpyAsync(hits[q], c->hit_lists.as<uint64_t>() + q * c->hit_list_stride, take * 8, cudaMemcpyDeviceToHost, s));
+  }
+  FEI_CUDA(cudaStreamSynchronize(s));
+  if (truncated) { set_error("hit buffer too small for at least one query"); return FEI_E_CAPACITY; }
+  return FEI_OK;
+}
+
+/* (A, S) checksums of the ordered hit lists the last fei_scan_count / fei_scan_hits left on the device */
+extern "C" int fei_scan_list_checksum(fei_corpus* c, uint32_t nq, uint64_t* a_out, uint64_t* s_out) {
+  if (!c || !a_out || !s_out) { set_error("null argument"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
+  if (nq == 0 || nq != c->last_nq || !c->hit_lists.p) { set_error("no matching scan result with lists on this corpus"); return FEI_E_STATE; }
+  for (uint32_t q = 0; q < nq; ++q)
+    FEI_TRY(list_checksum(c->hit_lists.as<uint64_t>() + q * c->hit_list_stride, c->last_counts[q], c->scan_tmp, a_out + q, s_out + q, ctx().stream));
   return FEI_OK;
 }
 
@@ -1482,7 +1650,7 @@ extern "C" int fei_corpus_token_histogram(fei_corpus* c, const uint8_t* prog, ui
   if (!c || !n_tokens || !tok_off) { set_error("null argument"); return FEI_E_BADARG; }
   std::lock_guard<std::mutex> lock(c->mu);
   *n_tokens = 0; tok_off[0] = 0;
-  FEI_TRY(run_scan(c, prog, prog_len));
+  FEI_TRY(run_scan(c, prog, prog_len, kCompactNone, nullptr, 0));
   fei_prog_hdr h; memcpy(&h, prog, sizeof(h));
   if (h.n_queries != 1 || h.n_slots < 1) { set_error("token histogram wants one query whose first header field names the column"); return FEI_E_BADARG; }
   if (c->n == 0) return finish_timing(c, false);

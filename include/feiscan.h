@@ -49,6 +49,12 @@ int fei_device_info(int* sm_count, uint64_t* hbm_bytes, int* cc_major, int* cc_m
  * speed and asynchronously (cudaHostRegister / cudaHostUnregister).                        */
 int fei_host_register(void* p, uint64_t bytes);
 int fei_host_unregister(void* p);
+/* Measured copy bandwidth (GB/s, best of reps) of a caller buffer to the device and back. */
+int fei_host_copy_bench(void* host, uint64_t bytes, int reps, float* h2d_gbs, float* d2h_gbs);
+
+/* Measured integer-issue peak of the chip (the roofline of the SHA-256 kernel, which is not HBM bound): tera lane-operations
+ * per second of LOP3 / SHF (ALU pipe; IADD3 issues at the same rate), best of `reps` launches; ms = that launch's duration. */
+int fei_microbench_alu(int reps, float* tera_lane_ops, float* ms);
 
 /* ---- packed Memdir corpus ---------------------------------------------------
  * Replaces the per-query file walk of memdir_tools.utils.list_memories
@@ -136,8 +142,18 @@ int fei_corpus_fetch(fei_corpus* c, uint64_t first, uint64_t n,
 int fei_scan_masks(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint32_t* masks);
 int fei_scan_hits(fei_corpus* c, const uint8_t* prog, uint64_t prog_len,
                   uint64_t* const* hits, const uint64_t* cap, uint64_t* nhits);
-/* Count-only variant (no index lists): nhits[q] for every query.                     */
+/* Counts on the host, the ordered lists stay on the device: nhits[q] for every query.
+ * Big content scans run as a few chunks of whole 4096-record windows; the compaction of a
+ * finished chunk runs on a second stream under the next chunk's scan.                  */
 int fei_scan_count(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint64_t* nhits);
+/* Copies the lists the last fei_scan_count left on the device (hits[q] has room for cap[q]
+ * entries; FEI_E_CAPACITY if one is shorter than its list): the second half of fei_scan_hits
+ * for callers that size their buffers from the counts.                                     */
+int fei_scan_fetch_hits(fei_corpus* c, uint32_t nq, uint64_t* const* hits, const uint64_t* cap);
+/* Order-sensitive checksums of the lists the last fei_scan_count / fei_scan_hits left on the
+ * device: a[q] = sum_k (k+1) * list_q[k], s[q] = sum_k list_q[k] (mod 2^64).  A sharded scan
+ * reports the same numbers for the gathered global lists (fei_comm_gathered_checksum).  */
+int fei_scan_list_checksum(fei_corpus* c, uint32_t nq, uint64_t* a, uint64_t* s);
 
 /* Per-call timing of the last scan on this corpus, measured with CUDA events on the
  * launching stream: ms spent in the head kernel, body kernel, compaction, copies.    */
@@ -248,6 +264,25 @@ int fei_comm_destroy(void);
  * global listing order.  counts_out[r*nq + q] = hits of query q on rank r.             */
 int fei_comm_allgather_hits(fei_corpus* c, uint32_t nq, uint64_t* const* hits, const uint64_t* cap,
                             uint64_t* nhits_total, uint64_t* counts_out);
+/* Collective: every rank names the shard it is going to scan.  The ranks exchange (record count,
+ * first global index), allocate the rank-major buffer that receives the hit masks of all shards
+ * and map each other's buffer (CUDA IPC: NVLink / NVSwitch peer memory); FEI_COMM_P2P=0, or a
+ * failed mapping on any rank, keeps the exchange on NCCL.  fei_comm_is_p2p() says which.        */
+int fei_comm_bind_corpus(fei_corpus* c);
+int fei_comm_is_p2p(void);
+/* Collective: the scan of fei_scan_count (masks + ordered local lists) with the hit all-gather
+ * folded in: the scan runs in chunks, and the masks of a finished chunk are written into every
+ * peer's buffer by copy-engine transfers (or a grouped ncclBroadcast) while the next chunk is
+ * scanned.  On return every rank holds the masks of ALL shards, rank-major = global listing
+ * order, and nhits_total[q] = global hits of query q.  The buffers are overwritten as soon as
+ * any rank enters the next gather.                                                            */
+int fei_comm_scan_gather(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint64_t* nhits_total);
+/* Lengths and order-sensitive checksums (see fei_scan_list_checksum) of the GLOBAL ordered hit
+ * lists the last gather on this rank stands for (fei_comm_scan_gather / fei_comm_allgather_hits). */
+int fei_comm_gathered_checksum(uint32_t nq, uint64_t* totals, uint64_t* a, uint64_t* s);
+/* Materialises those global ordered lists on this rank's device from the gathered masks
+ * (dense results); ms = device time of the build.                                            */
+int fei_comm_global_lists(uint32_t nq, uint64_t* totals, float* ms);
 /* min-reduce of (first_bad, kind) over ranks for a range-sharded chain.               */
 int fei_comm_allreduce_first_bad(int64_t* first_bad, int32_t* bad_kind);
 
