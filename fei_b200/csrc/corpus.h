@@ -34,6 +34,7 @@ constexpr uint32_t kMaxCols = 8;           // header value columns kept per corp
 constexpr uint32_t kColUnits = 4;          // 16-byte units per column value (longer values: directory walk)
 constexpr uint16_t kColAbsent = 0xFFFF, kColWalk = 0xFFFE;
 constexpr uint32_t kInvalidRec = 0xFFFFFFFFu;
+#define FEI_MAX_AUX 4
 }
 
 namespace fei {
@@ -58,6 +59,7 @@ struct fei_corpus {
   uint32_t n_cols = 0;
   bool has_text_records = false;         // some record's header is parsed from its text (keys not in the dictionary)
   fei::DevBuf stage_body, stage_body_off, tmp_len, tmp_gunits;   // reused by repeated loads (no cudaMalloc per batch)
+  fei::DevBuf aux[FEI_MAX_AUX]; uint64_t aux_n[FEI_MAX_AUX] = {0};   // host-computed per-record verdict bytes (fei_corpus_set_aux, FEI_C_RECBITS)
   fei::DevBuf stage_raw, stage_raw_off, stage_ms, stage_hlen, stage_blen;   // raw ingest staging (ingest.cu)
   // scan scratch (grown on demand, reused across scans)
   fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors, live_list;

@@ -153,12 +153,23 @@ struct HeadArgs {
   bool prog_in_smem;                               // set by the kernels after stage_prog_head
   const int8_t* slot_col;                          // per program slot: value column to read (k_slot_cols), -1 walk the directory, -2 no record has the field
   const uint16_t* col_len; const uint8_t* col_planes;   // header value columns (hdir.cu)
+  const int64_t* ts;                               // filename timestamps (metadata "timestamp")
+  const uint8_t* aux[FEI_MAX_AUX];                 // host-computed per-record verdict bytes (fei_corpus_set_aux)
 };
 
 constexpr int kHeadThreads = 256;
 
-__device__ __forceinline__ bool eval_meta_cond(const fei_prog_cond& cd, uint32_t flags_acc, int64_t wall, uint32_t fsb) {
+__device__ __forceinline__ bool cmp_i64(int64_t v, int64_t o, uint32_t op) {
+  switch (op) {
+    case FEI_CMP_GT: return v > o; case FEI_CMP_LT: return v < o;
+    case FEI_CMP_GE: return v >= o; case FEI_CMP_LE: return v <= o;
+    case FEI_CMP_EQ: return v == o; default: return v != o;
+  }
+}
+__device__ __forceinline__ bool eval_meta_cond(const HeadArgs& a, uint64_t rec, const fei_prog_cond& cd, uint32_t flags_acc, int64_t wall, uint32_t fsb) {
   switch (cd.kind) {
+    case FEI_C_RECBITS: return (a.aux[cd.ref & (FEI_MAX_AUX - 1)][rec] != 0) != (cd.negate != 0);
+    case FEI_C_TS_CMP: return cmp_i64(a.ts[rec], cd.i64, cd.cmp_op);
     case FEI_C_CONST: return cd.bit != 0;
     case FEI_C_FLAGS: return ((flags_acc >> cd.bit) & 1u) != cd.negate;
     case FEI_C_DATE_CMP: {
@@ -179,6 +190,36 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count);
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity);
+
+// str(int) of a non-negative integer; returns the length
+__device__ __forceinline__ uint32_t format_u64(unsigned long long v, uint8_t* out) {
+  uint8_t tmp[20]; int n = 0;
+  do { tmp[n++] = (uint8_t)('0' + v % 10); v /= 10; } while (v);
+  for (int i = 0; i < n; ++i) out[i] = tmp[n - 1 - i];
+  return (uint32_t)n;
+}
+// str(datetime) of a naive wall-clock second count (no microseconds): "YYYY-MM-DD HH:MM:SS" (civil-from-days, proleptic Gregorian)
+__device__ __forceinline__ uint32_t format_datetime(int64_t wall, uint8_t* out) {
+  int64_t days = wall / 86400; int64_t rem = wall % 86400;
+  if (rem < 0) { rem += 86400; --days; }
+  const int64_t z = days + 719468;
+  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  const uint32_t doe = (uint32_t)(z - era * 146097);
+  const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  int64_t y = (int64_t)yoe + era * 400;
+  const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const uint32_t mp = (5 * doy + 2) / 153;
+  const uint32_t d = doy - (153 * mp + 2) / 5 + 1;
+  const uint32_t m = mp < 10 ? mp + 3 : mp - 9;
+  if (m <= 2) ++y;
+  const uint32_t hh = (uint32_t)(rem / 3600), mi = (uint32_t)(rem % 3600 / 60), ss = (uint32_t)(rem % 60);
+  uint32_t yy = (uint32_t)(y < 0 ? 0 : y > 9999 ? 9999 : y);
+  out[0] = '0' + yy / 1000; out[1] = '0' + yy / 100 % 10; out[2] = '0' + yy / 10 % 10; out[3] = '0' + yy % 10; out[4] = '-';
+  out[5] = '0' + m / 10; out[6] = '0' + m % 10; out[7] = '-'; out[8] = '0' + d / 10; out[9] = '0' + d % 10; out[10] = ' ';
+  out[11] = '0' + hh / 10; out[12] = '0' + hh % 10; out[13] = ':'; out[14] = '0' + mi / 10; out[15] = '0' + mi % 10; out[16] = ':';
+  out[17] = '0' + ss / 10; out[18] = '0' + ss % 10;
+  return 19;
+}
 
 // Phase 2 for one record: header fields (if `parse`), name fields, evaluation of the queries left in `pre`.
 __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint32_t flags_acc, bool parse) {
@@ -304,7 +345,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       slot_acc[s] = reinterpret_cast<const fei_prog_dfa*>(a.prog + slots[s].off_val_dfa)->empty_acc;
       present |= 1u << s;
     }
-  uint32_t name_acc[3] = {0, 0, 0};
+  uint32_t name_acc[FEI_NAME_FIELDS] = {0, 0, 0, 0, 0};
   if (pre & ph->name_mask) {
     for (int k = 0; k < 3; ++k) {
       if (!ph->off_name_dfa[k]) continue;
@@ -313,6 +354,9 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       if (k > 0) { const uint16_t* sp = a.name_spans + 4 * rec + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
       name_acc[k] = dfa_run_at(a.prog, ph->off_name_dfa[k], a.prog_in_smem, nb, nl);
     }
+    // strings Python would format from the metadata: str(timestamp) and str(datetime.fromtimestamp(ts))
+    if (ph->off_meta_dfa[0]) { uint8_t buf[24]; const uint32_t nl = format_u64(a.ts[rec] < 0 ? 0ull : (unsigned long long)a.ts[rec], buf); name_acc[3] = dfa_run_at(a.prog, ph->off_meta_dfa[0], a.prog_in_smem, buf, nl); }
+    if (ph->off_meta_dfa[1]) { uint8_t buf[24]; const uint32_t nl = format_datetime(a.wall[rec], buf); name_acc[4] = dfa_run_at(a.prog, ph->off_meta_dfa[1], a.prog_in_smem, buf, nl); }
   }
   uint32_t alive = 0;
   for (uint32_t q = 0; q < ph->n_queries; ++q) {
@@ -329,10 +373,10 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
           else if (cd.if_missing == 2) { fallback = true; continue; }   // header absent: the next condition is the fallback field
           else r = cd.if_missing != 0;
           break;
-        case FEI_C_NAME: r = ((name_acc[cd.ref] >> cd.bit) & 1u) != cd.negate; break;
+        case FEI_C_NAME: r = ((name_acc[cd.ref < FEI_NAME_FIELDS ? cd.ref : 0] >> cd.bit) & 1u) != cd.negate; break;
         default:
           // meta predicates of a query in `pre` already held in k_head_meta; only a fallback field (skipped there) is still open
-          r = fallback ? eval_meta_cond(cd, flags_acc, a.wall[rec], a.fsb[rec]) : true;
+          r = fallback ? eval_meta_cond(a, rec, cd, flags_acc, a.wall[rec], a.fsb[rec]) : true;
       }
       fallback = false;
       ok = r;
@@ -427,7 +471,7 @@ __global__ void __launch_bounds__(256, 5) k_head_meta(HeadArgs a, Survivor* __re
       const fei_prog_cond cd = conds[c];
       if (cd.kind == FEI_C_SLOT && cd.if_missing == 2) { ++c; continue; }     // header-or-fallback pair: decided in phase 2
 #pragma unroll
-      for (int r = 0; r < kMetaPer; ++r) ok[r] = ok[r] && eval_meta_cond(cd, flags_acc[r], wall[r], fsb[r]);
+      for (int r = 0; r < kMetaPer; ++r) ok[r] = ok[r] && (!valid[r] || eval_meta_cond(a, base + (uint64_t)r * 256, cd, flags_acc[r], wall[r], fsb[r]));
     }
 #pragma unroll
     for (int r = 0; r < kMetaPer; ++r) if (ok[r]) pre[r] |= 1u << q;
@@ -1193,7 +1237,7 @@ static int check_prog(const uint8_t* prog, uint64_t len) {
            d.row_stride >= d.n_cols && 2ull * d.n_states * d.row_stride <= d.trans_bytes && d.n_states <= 65535;
   };
   if (!dfa_ok(h.off_key_dfa) || !dfa_ok(h.off_body_dfa) || !dfa_ok(h.off_flags_dfa) || !dfa_ok(h.off_name_dfa[0]) ||
-      !dfa_ok(h.off_name_dfa[1]) || !dfa_ok(h.off_name_dfa[2])) { set_error("bad DFA descriptor in program"); return FEI_E_BADARG; }
+      !dfa_ok(h.off_name_dfa[1]) || !dfa_ok(h.off_name_dfa[2]) || !dfa_ok(h.off_meta_dfa[0]) || !dfa_ok(h.off_meta_dfa[1])) { set_error("bad DFA descriptor in program"); return FEI_E_BADARG; }
   const fei_prog_slot* sl = reinterpret_cast<const fei_prog_slot*>(prog + h.off_slots);
   for (uint32_t s = 0; s < h.n_slots; ++s) if (!sl[s].off_val_dfa || !dfa_ok(sl[s].off_val_dfa)) { set_error("bad slot DFA"); return FEI_E_BADARG; }
   if (h.n_slots && !h.off_key_dfa) { set_error("slots without a key DFA"); return FEI_E_BADARG; }
@@ -1280,7 +1324,16 @@ int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_
     HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), c->name.as<uint8_t>(), c->name_off.as<uint64_t>(),
                c->name_spans.as<uint16_t>(), c->wall.as<int64_t>(), c->flags8.as<uint64_t>(), c->fsb.as<uint32_t>(), n, c->hits.as<uint32_t>(),
                c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(), false,
-               c->slot_col.as<int8_t>(), c->col_len.as<uint16_t>(), c->col_planes.as<uint8_t>()};
+               c->slot_col.as<int8_t>(), c->col_len.as<uint16_t>(), c->col_planes.as<uint8_t>(), c->ts.as<int64_t>(), {}};
+    {
+      const fei_prog_cond* cds = reinterpret_cast<const fei_prog_cond*>(prog + h.off_conds);
+      for (uint32_t k = 0; k < h.n_conds; ++k)
+        if (cds[k].kind == FEI_C_RECBITS) {
+          const uint32_t x = cds[k].ref;
+          if (x >= FEI_MAX_AUX || !c->aux[x].p || c->aux_n[x] != n) { set_error("program reads aux column %u, which is not set for this corpus state (fei_corpus_set_aux)", x); return FEI_E_STATE; }
+        }
+      for (int x = 0; x < FEI_MAX_AUX; ++x) a.aux[x] = c->aux[x].as<uint8_t>();
+    }
     if (h.n_slots) {                                           // which of the program's fields does each distinct header key of the corpus name?
       FEI_TRY(c->key_lut.ensure(kKeySlots * sizeof(uint32_t)));
       a.key_lut = c->key_lut.as<uint32_t>();
@@ -1307,7 +1360,7 @@ int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_
         for (uint32_t k = qs[q].cond_begin; k < qs[q].cond_end; ++k) {
           const uint8_t kind = cds[k].kind;
           if (kind == FEI_C_SLOT && cds[k].if_missing == 2) { ++k; continue; }      // the fallback field is decided with the header
-          if (kind == FEI_C_FLAGS || kind == FEI_C_DATE_CMP || kind == FEI_C_FOLDER_SET || kind == FEI_C_STATUS_SET) { fuse = false; break; }
+          if (kind == FEI_C_FLAGS || kind == FEI_C_DATE_CMP || kind == FEI_C_FOLDER_SET || kind == FEI_C_STATUS_SET || kind == FEI_C_RECBITS || kind == FEI_C_TS_CMP) { fuse = false; break; }
         }
       }
     }
@@ -1705,4 +1758,137 @@ extern "C" int fei_corpus_token_histogram(fei_corpus* c, const uint8_t* prog, ui
   }
   *n_tokens = slots.size();
   return finish_timing(c, false);
+}
+
+
+// ---------------------------------------------------------------- header values of one field, record by record
+// For conditions only Python can judge value by value (search.py:126-130: Due / Created / Modified / DeletedDate go through
+// dateutil.parser.parse per record), the host needs the VALUE the reference would read for every record: slot 0 of the program
+// resolved with the reference's dict semantics (mode 0: first key whose lower() equals the field, last line of that exact key;
+// mode 1: exact key).  k_slot_spans finds the value's span in the header blob (directory walk, or the text for headers the
+// directory cannot address), k_slot_gather packs the values into one blob that goes back to the host.
+namespace fei {
+__global__ void __launch_bounds__(256) k_slot_spans(HeadArgs a, uint32_t* __restrict__ len_out, uint64_t* __restrict__ src_out) {
+  const uint64_t rec = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (rec >= a.n) return;
+  const fei_prog_hdr* ph = reinterpret_cast<const fei_prog_hdr*>(a.prog);
+  const fei_prog_slot* slots = reinterpret_cast<const fei_prog_slot*>(a.prog + ph->off_slots);
+  const uint32_t mode = slots[0].mode;
+  const uint64_t hoff = a.hdr_off[rec];
+  const uint8_t* h = a.hdr + hoff;
+  const uint32_t hlen = (uint32_t)(a.hdr_off[rec + 1] - hoff);
+  const uint2* ent = a.hdir + a.hdir_off[rec];
+  const uint32_t n_ent = (uint32_t)(a.hdir_off[rec + 1] - a.hdir_off[rec]);
+  bool have = false, have_first = false;
+  uint32_t voff = 0, vlen = 0;
+  if (!(n_ent == 1 && ent[0].x == 0xFFFFFFFFu)) {
+    uint32_t first_key = 0;
+    for (uint32_t j = 0; j < n_ent; ++j) {
+      const uint2 e = ent[j];
+      const uint32_t kid = e.x & 0xFFFFu;
+      if (!(a.key_lut[kid] & 1u)) continue;
+      if (mode == 0) {
+        if (!have_first) { have_first = true; first_key = kid; }
+        else if (first_key != kid) continue;
+      }
+      voff = e.y; vlen = e.x >> 16; have = true;
+    }
+  } else {
+    DfaView keyd = dfa_view(a.prog, ph->off_key_dfa);
+    const uint8_t* hend = h + hlen;
+    const uint8_t* p = h;
+    uint32_t first_off = 0, first_len = 0;
+    while (p < hend) {
+      const uint8_t* eol = p; const uint8_t* colon = nullptr;
+      while (eol < hend && *eol != '\n') { if (!colon && *eol == ':') colon = eol; ++eol; }
+      if (colon) {
+        const uint8_t* ka = p; const uint8_t* kb = colon; strip_span(ka, kb);
+        const uint8_t* va = colon + 1; const uint8_t* vb = eol; strip_span(va, vb);
+        if (dfa_run(keyd, ka, (uint32_t)(kb - ka)) & 1u) {
+          bool take = true;
+          if (mode == 0) {
+            if (!have_first) { have_first = true; first_off = (uint32_t)(ka - h); first_len = (uint32_t)(kb - ka); }
+            else {
+              bool same = first_len == (uint32_t)(kb - ka);
+              for (uint32_t k = 0; same && k < first_len; ++k) same = h[first_off + k] == ka[k];
+              take = same;
+            }
+          }
+          if (take) { voff = (uint32_t)(va - h); vlen = (uint32_t)(vb - va); have = true; }
+        }
+      }
+      p = eol + 1;
+    }
+  }
+  len_out[rec] = have ? vlen : 0u;
+  src_out[rec] = have ? hoff + voff : ~0ull;                     // ~0: the record has no such header
+}
+
+__global__ void __launch_bounds__(256) k_slot_gather(const uint8_t* __restrict__ hdr, const uint32_t* __restrict__ len, const uint64_t* __restrict__ src,
+                                                    const uint64_t* __restrict__ off, uint64_t n, uint8_t* __restrict__ out, uint8_t* __restrict__ present) {
+  const uint64_t rec = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (rec >= n) return;
+  const bool have = src[rec] != ~0ull;
+  present[rec] = have ? 1 : 0;
+  if (!have) return;
+  const uint8_t* p = hdr + src[rec];
+  uint8_t* d = out + off[rec];
+  for (uint32_t k = 0; k < len[rec]; ++k) d[k] = p[k];
+}
+}  // namespace fei
+
+/* prog: any program whose slot 0 names the field (conditions are ignored).  Out: present[n], off[n+1] (value i =
+ * blob[off[i] .. off[i+1]), empty for absent headers).  FEI_E_CAPACITY with the needed size in off[n] when blob_cap is too small. */
+extern "C" int fei_corpus_slot_values(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint8_t* present, uint64_t* off,
+                                      uint8_t* blob, uint64_t blob_cap) {
+  if (!c || !prog || !present || !off) { set_error("null argument"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
+  FEI_TRY(require_ready());
+  if (!c->loaded) { set_error("corpus not loaded"); return FEI_E_STATE; }
+  FEI_TRY(check_prog(prog, prog_len));
+  fei_prog_hdr h; memcpy(&h, prog, sizeof(h));
+  if (h.n_slots < 1) { set_error("program has no header field"); return FEI_E_BADARG; }
+  const uint64_t n = c->n;
+  off[0] = 0;
+  if (n == 0) return FEI_OK;
+  cudaStream_t s = ctx().stream;
+  FEI_TRY(c->prog.ensure(prog_len + 16));
+  FEI_CUDA(cudaMemcpyAsync(c->prog.p, prog, prog_len, cudaMemcpyHostToDevice, s));
+  FEI_TRY(c->key_lut.ensure(kKeySlots * sizeof(uint32_t)));
+  k_key_lut<<<kKeySlots / 128, 128, 0, s>>>(c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->key_tag.as<unsigned long long>(),
+                                            c->key_rep.as<unsigned long long>(), c->key_len.as<uint32_t>(), c->key_lut.as<uint32_t>());
+  HeadArgs a{c->prog.as<uint8_t>(), c->hdr.as<uint8_t>(), c->hdr_off.as<uint64_t>(), nullptr, nullptr, nullptr, c->wall.as<int64_t>(), c->flags8.as<uint64_t>(),
+             c->fsb.as<uint32_t>(), n, nullptr, c->hdir.as<uint2>(), c->hdir_off.as<uint64_t>(), c->key_lut.as<uint32_t>(), false, nullptr, nullptr, nullptr, c->ts.as<int64_t>(), {}};
+  DevBuf d_len, d_src, d_off, d_present, d_out;
+  FEI_TRY(d_len.alloc(n * 4)); FEI_TRY(d_src.alloc(n * 8)); FEI_TRY(d_off.alloc((n + 1) * 8)); FEI_TRY(d_present.alloc(n));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  k_slot_spans<<<grid, 256, 0, s>>>(a, d_len.as<uint32_t>(), d_src.as<uint64_t>());
+  FEI_TRY(exclusive_scan_u32_u64(d_len.as<uint32_t>(), n, d_off.as<uint64_t>(), c->scan_tmp, s));
+  FEI_CUDA(cudaMemcpyAsync(off, d_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  FEI_TRY(d_out.alloc(off[n] + 16));
+  k_slot_gather<<<grid, 256, 0, s>>>(c->hdr.as<uint8_t>(), d_len.as<uint32_t>(), d_src.as<uint64_t>(), d_off.as<uint64_t>(), n, d_out.as<uint8_t>(), d_present.as<uint8_t>());
+  FEI_CUDA(cudaMemcpyAsync(present, d_present.p, n, cudaMemcpyDeviceToHost, s));
+  const bool fits = blob && off[n] <= blob_cap;
+  if (fits && off[n]) FEI_CUDA(cudaMemcpyAsync(blob, d_out.p, off[n], cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  FEI_CUDA(cudaGetLastError());
+  if (!fits) { set_error("value buffer too small: need %llu bytes", (unsigned long long)off[n]); return FEI_E_CAPACITY; }
+  return FEI_OK;
+}
+
+/* Aux column k (0 .. FEI_MAX_AUX-1): one verdict byte per record, read by FEI_C_RECBITS conditions of later scans.  n must be the
+ * corpus' record count; bytes == NULL drops the column.                                                                         */
+extern "C" int fei_corpus_set_aux(fei_corpus* c, uint32_t k, const uint8_t* bytes, uint64_t n) {
+  if (!c || k >= FEI_MAX_AUX) { set_error("bad argument"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
+  FEI_TRY(require_ready());
+  if (!bytes) { c->aux[k].release(); c->aux_n[k] = 0; return FEI_OK; }
+  if (n != c->n) { set_error("aux column has %llu entries, the corpus %llu records", (unsigned long long)n, (unsigned long long)c->n); return FEI_E_BADARG; }
+  cudaStream_t s = ctx().stream;
+  FEI_TRY(c->aux[k].ensure(n + 16));
+  if (n) FEI_CUDA(cudaMemcpyAsync(c->aux[k].p, bytes, n, cudaMemcpyHostToDevice, s));
+  FEI_CUDA(cudaStreamSynchronize(s));
+  c->aux_n[k] = n;
+  return FEI_OK;
 }

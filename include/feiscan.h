@@ -179,6 +179,14 @@ int fei_corpus_token_histogram(fei_corpus* c, const uint8_t* prog, uint64_t prog
                                uint8_t* tok_blob, uint64_t blob_cap, uint64_t* tok_off, uint64_t* tok_count, uint64_t* tok_first,
                                uint64_t cap, uint64_t* n_tokens);
 
+/* The header value the reference would read for one field, for every record (slot 0 of `prog` resolved with the dict semantics of
+ * search.py:121-132 / filter.py:90-91): present[n], off[n+1], blob.  For conditions whose verdict only Python can compute value by
+ * value: the per-record dateutil parses of Due / Created / Modified / DeletedDate (search.py:126-130).  The host judges the DISTINCT
+ * values and hands the verdicts back as an aux column (fei_corpus_set_aux) that FEI_C_RECBITS conditions read in the scan.   */
+int fei_corpus_slot_values(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, uint8_t* present, uint64_t* off,
+                           uint8_t* blob, uint64_t blob_cap);
+int fei_corpus_set_aux(fei_corpus* c, uint32_t k, const uint8_t* bytes, uint64_t n);
+
 /* ---- Memorychain validation -----------------------------------------------------
  * Replaces the loop of MemoryChain.validate_chain (memdir_tools/memorychain.py:596-618)
  * and its inline copy in receive_chain_update (:1059-1078):

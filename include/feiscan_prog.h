@@ -30,8 +30,16 @@ enum {
   FEI_C_NAME       = 4,  /* output `bit` of name-field `ref` DFA: 0 filename, 1 unique_id, 2 hostname      */
   FEI_C_DATE_CMP   = 5,  /* wall-clock microseconds `cmp_op` i64   (search.py:107-108, :166-234)           */
   FEI_C_FOLDER_SET = 6,  /* (set64 >> folder_id) & 1               (host-evaluated per distinct folder)    */
-  FEI_C_STATUS_SET = 7   /* (set64 >> status_id) & 1                                                        */
+  FEI_C_STATUS_SET = 7,  /* (set64 >> status_id) & 1                                                        */
+  FEI_C_RECBITS    = 8,  /* aux column `ref` of the corpus (fei_corpus_set_aux): one host-computed verdict byte per
+                            record, for values only Python can judge (per-record dateutil parses of Due / Created /
+                            Modified / DeletedDate headers, search.py:126-130)                                     */
+  FEI_C_TS_CMP     = 9   /* filename timestamp (int) `cmp_op` i64  (metadata "timestamp", search.py:134-137)       */
 };
+/* FEI_C_NAME refs: 0 filename, 1 unique_id, 2 hostname (spans of the stored file name), and two strings the kernels
+ * format from the meta columns: 3 = str(metadata["timestamp"]) (decimal digits), 4 = str(metadata["date"]) =
+ * "YYYY-MM-DD HH:MM:SS" of datetime.fromtimestamp(ts) (filter.py:94-95; text operators of search.py:148-163 on `date`) */
+#define FEI_NAME_FIELDS 5
 enum { FEI_CMP_GT = 0, FEI_CMP_LT = 1, FEI_CMP_GE = 2, FEI_CMP_LE = 3, FEI_CMP_EQ = 4, FEI_CMP_NE = 5 };
 
 typedef struct fei_prog_hdr {            /* 96 bytes */
@@ -50,7 +58,8 @@ typedef struct fei_prog_hdr {            /* 96 bytes */
   uint32_t name_mask;                    /* queries that read filename / id / hostname                */
   uint32_t head_bytes;                   /* everything before the content automaton (which is serialised last): the part the
                                             head kernels copy into shared memory; 0 = unknown (do not stage)              */
-  uint32_t reserved[4];
+  uint32_t off_meta_dfa[2];              /* name fields 3 and 4: automata over the formatted timestamp / date strings        */
+  uint32_t reserved[2];
 } fei_prog_hdr;
 
 typedef struct fei_prog_dfa {            /* 64 bytes; tables follow at the given offsets            */
