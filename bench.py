@@ -519,7 +519,8 @@ def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
     """Streaming end to end: `batches` batches of raw records (file contents: header text + '---' + body, as read from disk) go from
     pinned host memory through fei_corpus_load_raw (H2D on the copy stream, then UTF-8 validation / newline folding / split / strip /
     tiling / header directory kernels) and fei_scan_hits (k_body + compaction + 32 ordered hit lists D2H).  Two corpus handles
-    alternate: batch k+1 is uploaded and packed while batch k is scanned and its hits travel back."""
+    rotate, each with its own load stream: batch k+2 is being copied while batch k+1 runs through the pack kernels and batch k is
+    scanned and its hits travel back."""
     from concurrent.futures import ThreadPoolExecutor
     from fei_b200.corpus import Corpus
     n = min(args.e2e_entries, corpus.n)
@@ -546,7 +547,7 @@ def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
     barrier()                                           # every rank measures its link while the others use theirs
     _abi.check(lib.fei_host_copy_bench(raw.ctypes.data, min(raw.nbytes, 1 << 30), 3, C.byref(bw_h2d), C.byref(bw_d2h)))
     barrier()
-    cs = [Corpus(), Corpus()]
+    cs = [Corpus(), Corpus(), Corpus()]                # two batches can be in the load pipeline (one copying, one in the pack kernels) while a third is scanned
     bufs = [np.zeros(n, dtype=np.uint64) for _ in range(nq)]
     for b in bufs:
         if lib.fei_host_register(b.ctypes.data, b.nbytes) == 0:
@@ -554,19 +555,19 @@ def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
     ptrs = (C.c_void_p * 32)(*[b.ctypes.data for b in bufs])
     cap = np.zeros(32, dtype=np.uint64); cap[:nq] = n
     nh = np.zeros(32, dtype=np.uint64)
-    pool = ThreadPoolExecutor(1)
+    pool = ThreadPoolExecutor(2)
 
     def load(c):
         assert c.load_raw(arrays).all()
 
     def one_step():
         d2h = 0
-        fut = pool.submit(load, cs[0])
+        futs = {k: pool.submit(load, cs[k % 3]) for k in range(min(2, nb))}
         for k in range(nb):
-            fut.result()
-            if k + 1 < nb:
-                fut = pool.submit(load, cs[(k + 1) % 2])
-            _abi.check(lib.fei_scan_hits(cs[k % 2].handle, prog, len(prog), ptrs, _abi.ptr(cap), _abi.ptr(nh)))
+            futs.pop(k).result()
+            if k + 2 < nb:
+                futs[k + 2] = pool.submit(load, cs[(k + 2) % 3])        # handle (k+2)%3 == (k-1)%3: its scan finished in the previous iteration
+            _abi.check(lib.fei_scan_hits(cs[k % 3].handle, prog, len(prog), ptrs, _abi.ptr(cap), _abi.ptr(nh)))
             d2h += int(nh[:nq].sum()) * 8
         return d2h
     one_step()                                          # warm-up: allocations, first-touch

@@ -136,6 +136,28 @@ class Corpus:
         _abi.check(_abi.lib().fei_scan_list_checksum(self._h, nq, _abi.ptr(a), _abi.ptr(s)))
         return a[:nq], s[:nq]
 
+    def slot_values(self, prog: bytes):
+        """The header value the reference would read for slot 0 of `prog`, record by record (fei_corpus_slot_values):
+        (present[n] bool, off[n+1], blob bytes)."""
+        n = self.n
+        present = np.zeros(max(1, n), dtype=np.uint8); off = np.zeros(n + 1, dtype=np.uint64)
+        blob = np.zeros(max(64, 24 * n), dtype=np.uint8)
+        l = _abi.lib()
+        rc = l.fei_corpus_slot_values(self._h, prog, len(prog), _abi.ptr(present), _abi.ptr(off), _abi.ptr(blob), blob.size)
+        if rc == _abi.FEI_E_CAPACITY:
+            blob = np.zeros(int(off[n]) + 16, dtype=np.uint8)
+            rc = l.fei_corpus_slot_values(self._h, prog, len(prog), _abi.ptr(present), _abi.ptr(off), _abi.ptr(blob), blob.size)
+        _abi.check(rc)
+        return present[:n].astype(bool), off, blob[:int(off[n])]
+
+    def set_aux(self, k: int, verdicts: Optional[np.ndarray]) -> None:
+        """Aux column k: one host-computed verdict byte per record, read by C_RECBITS conditions (fei_corpus_set_aux)."""
+        if verdicts is None:
+            _abi.check(_abi.lib().fei_corpus_set_aux(self._h, k, None, 0))
+            return
+        v = np.ascontiguousarray(verdicts, dtype=np.uint8)
+        _abi.check(_abi.lib().fei_corpus_set_aux(self._h, k, _abi.ptr(v), v.size))
+
     def timing(self) -> Dict[str, float]:
         t = _abi.ScanTiming()
         _abi.check(_abi.lib().fei_scan_last_timing(self._h, C.byref(t)))

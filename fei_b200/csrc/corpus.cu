@@ -121,6 +121,11 @@ __global__ void k_untile(const uint8_t* __restrict__ tiles, const uint64_t* __re
   }
 }
 
+cudaStream_t corpus_load_stream(fei_corpus* c) {
+  if (!c->load_stream && cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->load_stream = nullptr; }
+  return c->load_stream ? c->load_stream : ctx().copy_stream;
+}
+
 int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off, cudaStream_t s) {
   uint64_t n = c->n;
   uint64_t n_windows = (n + kWindow - 1) / kWindow;
@@ -201,6 +206,7 @@ extern "C" int fei_corpus_destroy(fei_corpus* c) {
   { std::lock_guard<std::mutex> lock(c->mu); }       // let a scan that another thread still runs on this handle finish
   cudaStreamSynchronize(ctx().stream);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->load_stream) { cudaStreamSynchronize(c->load_stream); cudaStreamDestroy(c->load_stream); }
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
   if (c->ev_side) cudaEventDestroy(c->ev_side);
@@ -216,7 +222,7 @@ extern "C" int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h) {
   if (h->n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }
   if (h->n && (!h->hdr_off || !h->body_off || !h->ts || !h->wall || !h->flags8 || !h->fsb)) { set_error("missing corpus array"); return FEI_E_BADARG; }
   Context& cx = ctx();
-  cudaStream_t s = cx.copy_stream;                   // see fei_corpus_load_raw: loads overlap scans of other handles
+  cudaStream_t s = corpus_load_stream(c);            // see fei_corpus_load_raw: loads overlap scans (and loads) of other handles
   uint64_t n = h->n;
   c->n = n; c->global_base = h->global_base; c->loaded = false;
   static const uint64_t zero_off[1] = {0};

@@ -71,12 +71,14 @@ struct fei_corpus {
   cudaEvent_t ev[8] = {nullptr};
   // chunked scans: compaction / all-gather of a finished chunk run on `side` under the next chunk's scan (scan.cu)
   cudaStream_t side = nullptr;
+  cudaStream_t load_stream = nullptr;    // loads of this handle (H2D + pack kernels): own stream, so that batches streamed through several handles overlap
   cudaEvent_t ev_chunk[16] = {nullptr};
   cudaEvent_t ev_side = nullptr;
 };
 
 namespace fei {
 // builds tiles from a canonical body blob already on the device (body has >= 32 bytes of slack)
+cudaStream_t corpus_load_stream(fei_corpus* c);   // created on first use; falls back to the context's copy stream
 int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off, cudaStream_t s);
 // builds the header directory from hdr / hdr_off already on the device (hdir.cu)
 int build_header_dir(fei_corpus* c, cudaStream_t s);

@@ -21,15 +21,16 @@
 namespace fei {
 
 // Strict UTF-8 (what bytes.decode("utf-8") accepts): no overlongs, no surrogates, <= U+10FFFF.
-__device__ bool utf8_valid(const uint8_t* p, const uint8_t* end, bool& ascii, bool& lower_inexact) {
-  ascii = true; lower_inexact = false;
+__device__ bool utf8_valid(const uint8_t* p, const uint8_t* end, bool& ascii, bool& has_sigma, bool& has_idot) {
+  ascii = true; has_sigma = false; has_idot = false;
   while (p < end) {
     uint32_t c = *p;
     if (c < 0x80) { ++p; continue; }
     ascii = false;
     if (c >= 0xC2 && c <= 0xDF) {
       if (end - p < 2 || (p[1] & 0xC0) != 0x80) return false;
-      if ((c == 0xC4 && p[1] == 0xB0) || (c == 0xCE && p[1] == 0xA3)) lower_inexact = true;   // U+0130, U+03A3
+      if (c == 0xC4 && p[1] == 0xB0) has_idot = true;         // U+0130: lower() is two characters (handled by the automata)
+      if (c == 0xCE && p[1] == 0xA3) has_sigma = true;        // U+03A3: lower() depends on the context (final sigma)
       p += 2;
     } else if (c >= 0xE0 && c <= 0xEF) {
       if (end - p < 3 || (p[1] & 0xC0) != 0x80 || (p[2] & 0xC0) != 0x80) return false;
@@ -56,7 +57,7 @@ struct RawMeasure {
   uint32_t hdr_raw_len;               // header = raw[0, hdr_raw_len)
   uint32_t body_raw_begin, body_raw_end;
   uint32_t hdr_len, body_len;         // translated lengths
-  uint32_t flags;                     // bit0 valid UTF-8, bit1 has separator, bit2 non-ASCII, bit3 U+0130 / U+03A3 present
+  uint32_t flags;                     // bit0 valid UTF-8, bit1 has separator, bit2 non-ASCII, bit3 U+03A3 present, bit4 U+0130 present
 };
 
 __device__ __forceinline__ uint32_t count_crlf(const uint8_t* p, const uint8_t* end) {
@@ -72,9 +73,9 @@ __global__ void k_raw_measure(const uint8_t* __restrict__ raw, const uint64_t* _
   const uint8_t* p = raw + raw_off[i];
   const uint8_t* end = raw + raw_off[i + 1];
   RawMeasure m{0, 0, 0, 0, 0, 0};
-  bool ascii, inexact;
-  if (utf8_valid(p, end, ascii, inexact)) {
-    m.flags = 1u | (ascii ? 0u : 4u) | (inexact ? 8u : 0u);
+  bool ascii, sigma, idot;
+  if (utf8_valid(p, end, ascii, sigma, idot)) {
+    m.flags = 1u | (ascii ? 0u : 4u) | (sigma ? 8u : 0u) | (idot ? 16u : 0u);
     const uint8_t* sep = nullptr;                              // first "---" anywhere (utils.py:105)
     for (const uint8_t* q = p; q + 2 < end; ++q) if (q[0] == '-' && q[1] == '-' && q[2] == '-') { sep = q; break; }
     const uint8_t* ba = sep ? sep + 3 : p;                     // no separator: the whole text is the body (utils.py:107-109)
@@ -114,7 +115,7 @@ __global__ void k_fix_fsb(const RawMeasure* __restrict__ ms, uint64_t n, uint32_
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t f = ms[i].flags;
-  uint32_t bits = ((f & 2u) ? 0u : FEI_REC_NO_SEPARATOR) | ((f & 4u) ? FEI_REC_NONASCII : 0u) | ((f & 8u) ? FEI_REC_LOWER_INEXACT : 0u);
+  uint32_t bits = ((f & 2u) ? 0u : FEI_REC_NO_SEPARATOR) | ((f & 4u) ? FEI_REC_NONASCII : 0u) | ((f & 8u) ? FEI_REC_HAS_SIGMA : 0u) | ((f & 16u) ? FEI_REC_HAS_IDOT : 0u);
   fsb[i] = (fsb[i] & 0x00FFFFFFu) | (bits << 24);
 }
 
@@ -134,7 +135,7 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   // loads run on the copy stream: a batch can be uploaded / normalised / tiled into one handle while another handle is being
   // scanned on the compute stream (streaming e2e use); the staging buffers live in the handle (grow-only) because a
   // cudaFree in the middle of a pipeline synchronises the whole device
-  cudaStream_t s = ctx().copy_stream;
+  cudaStream_t s = corpus_load_stream(c);
   uint64_t n = h->n;
   c->loaded = false;
   uint64_t raw_bytes = n ? raw_off[n] : 0;

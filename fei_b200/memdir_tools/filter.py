@@ -15,7 +15,7 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 import numpy as np
 
 from .. import packer
-from ..program import C_BODY, C_FLAGS, C_NAME, C_SLOT, NAME_HOST, NAME_ID, Cond, ProgramBuilder, const
+from ..program import C_BODY, C_FLAGS, C_NAME, C_SLOT, NAME_DATE_STR, NAME_HOST, NAME_ID, NAME_TS_STR, Cond, ProgramBuilder, const
 from ..regexc import Pattern
 from . import utils as U
 from .utils import move_memory, update_memory_flags, STANDARD_FOLDERS  # noqa: F401  (reference re-exports)
@@ -35,8 +35,9 @@ def _compile_filter_conditions(conditions: Sequence[Dict[str, Any]]) -> List[Con
         elif field in ("unique_id", "hostname"):             # header first, else str(metadata[field]) (filter.py:94-95)
             out.append(Cond(C_SLOT, pattern=pat, negate=negate, field=field, mode=1, if_missing=2))
             out.append(Cond(C_NAME, pattern=pat, negate=negate, which=NAME_ID if field == "unique_id" else NAME_HOST))
-        elif field in ("timestamp", "date"):
-            raise NotImplementedError(f"filter conditions on metadata {field!r} are not supported on the GPU yet")
+        elif field in ("timestamp", "date"):                 # str(metadata[field]): decimal digits / "YYYY-MM-DD HH:MM:SS" (filter.py:94-95)
+            out.append(Cond(C_SLOT, pattern=pat, negate=negate, field=field, mode=1, if_missing=2))
+            out.append(Cond(C_NAME, pattern=pat, negate=negate, which=NAME_TS_STR if field == "timestamp" else NAME_DATE_STR))
         else:                                                # missing field: passes iff negated (filter.py:97-102)
             out.append(Cond(C_SLOT, pattern=pat, negate=negate, field=field, mode=1, if_missing=1 if negate else 0))
     return out

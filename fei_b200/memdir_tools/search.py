@@ -10,16 +10,17 @@ on the host and operate on the hit list exactly as the reference does (search.py
 from __future__ import annotations
 
 import calendar
+import math
 import re
-from datetime import datetime
+from datetime import datetime, timedelta
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import dateutil.parser
 import numpy as np
 
 from .. import packer
-from ..program import (C_BODY, C_CONST, C_DATE_CMP, C_FLAGS, C_FOLDER_SET, C_NAME, C_SLOT, C_STATUS_SET, CMP, NAME_FILENAME,
-                       NAME_HOST, NAME_ID, Cond, ProgramBuilder, const)
+from ..program import (C_BODY, C_CONST, C_DATE_CMP, C_FLAGS, C_FOLDER_SET, C_NAME, C_RECBITS, C_SLOT, C_STATUS_SET, C_TS_CMP, CMP, MAX_AUX,
+                       NAME_DATE_STR, NAME_FILENAME, NAME_HOST, NAME_ID, NAME_TS_STR, Cond, ProgramBuilder, const)
 from ..regexc import Pattern, compile_patterns
 from . import utils as U
 
@@ -115,8 +116,9 @@ def parse_search_args(args_str: str) -> SearchQuery:
 class _Raises:
     """A condition that raises in the reference for every record that reaches it with a non-None value."""
 
-    def __init__(self, exc: Exception, presence: Optional[Cond]):
+    def __init__(self, exc: Exception, presence: Optional[Cond], exc_of=None):
         self.exc, self.presence = exc, presence
+        self.exc_of = exc_of                 # record index -> the exception that record raises (when the records differ in that)
 
 
 def _string_pattern(op: str, v2: Any, v1_name: str):
@@ -224,9 +226,9 @@ def _compile_one(field: Any, op: str, v2: Any, include_content: bool, pm) -> Lis
         bits = sum(1 << i for i, v in enumerate(verdicts) if v)
         return [Cond(C_FOLDER_SET if low == "folder" else C_STATUS_SET, set64=bits)]
     if low in _DATE_HEADERS:
-        raise NotImplementedError(f"conditions on the {field!r} header go through dateutil per record; not supported on the GPU yet")
+        return _compile_date_header(field, op, v2, pm)
     if low == "timestamp":
-        raise NotImplementedError("conditions on metadata 'timestamp' are not supported on the GPU yet")
+        return _compile_timestamp(field, op, v2, pm)
     pat, neg = _string_pattern(op, v2, field)
     if low in ("unique_id", "hostname"):                                  # header first, metadata otherwise (search.py:121-137)
         if isinstance(pat, (bool, Exception)):
@@ -238,8 +240,13 @@ def _compile_one(field: Any, op: str, v2: Any, include_content: bool, pm) -> Lis
 
 def _compile_date(op: str, v2: Any) -> List[Any]:
     """`date` is datetime.fromtimestamp(ts) (utils.py:94); the operand goes through dateutil (search.py:166-198)."""
-    if op not in CMP:
-        raise NotImplementedError(f"operator {op!r} on the date field (str(datetime) text match) is not supported on the GPU yet")
+    if op not in CMP:                                    # text operators read str(datetime) = "YYYY-MM-DD HH:MM:SS" (search.py:148-163, :237-239)
+        pat, neg = _string_pattern(op, v2, "date")
+        if isinstance(pat, bool):
+            return [const(pat)]
+        if isinstance(pat, Exception):
+            return [_Raises(pat, None)]
+        return [Cond(C_NAME, pattern=pat, negate=neg, which=NAME_DATE_STR)]
     if not isinstance(v2, datetime):
         try:
             v2 = dateutil.parser.parse(str(v2))
@@ -255,13 +262,173 @@ def _compile_date(op: str, v2: Any) -> List[Any]:
     return [Cond(C_DATE_CMP, op=CMP[op], i64=micros)]
 
 
+
+def _int_cmp_cond(op: str, v2: Any) -> List[Any]:
+    """metadata["timestamp"] (an int) against a non-string operand: Python's int comparison semantics (search.py:166-234)."""
+    if isinstance(v2, datetime):
+        if op in ("=", "!="):
+            return [const(op == "!=")]
+        return [_Raises(TypeError(f"'{op}' not supported between instances of 'int' and 'datetime.datetime'"), None)]
+    if isinstance(v2, bool):
+        v2 = int(v2)
+    if isinstance(v2, float):
+        if math.isnan(v2):
+            return [const(op == "!=")]
+        if math.isinf(v2):
+            return [const({">": v2 < 0, ">=": v2 < 0, "<": v2 > 0, "<=": v2 > 0, "=": False, "!=": True}[op])]
+        if v2 != math.floor(v2):
+            if op in ("=", "!="):
+                return [const(op == "!=")]
+            lo, hi = math.floor(v2), math.ceil(v2)
+            op, v2 = (">", lo) if op in (">", ">=") else ("<", hi)
+        else:
+            v2 = int(v2)
+    if not isinstance(v2, int):
+        if op in ("=", "!="):
+            return [const(op == "!=")]                    # int == <other object> is False
+        return [_Raises(TypeError(f"'{op}' not supported between instances of 'int' and '{type(v2).__name__}'"), None)]
+    big = (1 << 63) - 1
+    if v2 > big or v2 < -big:
+        return [const({">": v2 < 0, ">=": v2 < 0, "<": v2 > 0, "<=": v2 > 0, "=": False, "!=": True}[op])]
+    return [Cond(C_TS_CMP, op=CMP[op], i64=int(v2))]
+
+
+def _compile_timestamp(field: str, op: str, v2: Any, pm) -> List[Any]:
+    """`timestamp`: a header of that name wins (search.py:121-132), else metadata["timestamp"], an int (search.py:134-137)."""
+    absent = Cond(C_SLOT, pattern=Pattern("regex", "", re.IGNORECASE), negate=True, field=field, mode=0, if_missing=1)   # true iff no such header
+    pat, neg = _string_pattern(op, v2, field)
+    hdr = [const(pat)] if isinstance(pat, bool) else [_Raises(pat, None)] if isinstance(pat, Exception) else None
+    if op in ("contains", "matches", "startswith", "endswith", "has_tag", "has_flag"):      # str(value1): same text semantics for both sources
+        if hdr is not None:
+            return hdr
+        return [Cond(C_SLOT, pattern=pat, negate=neg, field=field, mode=0, if_missing=2), Cond(C_NAME, pattern=pat, negate=neg, which=NAME_TS_STR)]
+    if op not in CMP:
+        return [const(False)]
+    # comparison operators: the metadata int and a header string behave differently
+    if isinstance(v2, str):
+        if op in ("=", "!="):                             # int == str is False; header str == str compares lower-cased
+            meta = const(op == "!=")
+        else:
+            kind = "datetime.datetime" if v2 == "now" or re.match(r"now([+-])(\d+)([dwmy])", v2) else "str"
+            meta = _Raises(TypeError(f"'{op}' not supported between instances of 'int' and '{kind}'"), absent)
+        if isinstance(meta, _Raises):
+            return [meta] + (hdr if hdr is not None else [Cond(C_SLOT, pattern=pat, negate=neg, field=field, mode=0)])
+        if hdr is not None and isinstance(pat, bool) and pat == meta.value:
+            return [meta]
+        if hdr is not None:
+            raise NotImplementedError("timestamp condition whose header and metadata forms disagree in kind")
+        return [Cond(C_SLOT, pattern=pat, negate=neg, field=field, mode=0, if_missing=2), meta]
+    meta = _int_cmp_cond(op, v2)
+    # a non-string operand against a header string: str == int is False, str < int raises
+    if op in ("=", "!="):
+        hdr_c = const(op == "!=")
+        if len(meta) == 1 and isinstance(meta[0], Cond) and meta[0].kind == C_CONST and meta[0].value == hdr_c.value:
+            return meta
+        present = Cond(C_SLOT, pattern=Pattern("regex", "", re.IGNORECASE), negate=(op == "="), field=field, mode=0, if_missing=2)
+        return [present] + meta if not isinstance(meta[0], _Raises) else meta
+    exc = TypeError(f"'{op}' not supported between instances of 'str' and '{type(v2).__name__}'")
+    present = Cond(C_SLOT, pattern=Pattern("regex", "", re.IGNORECASE), field=field, mode=0)
+    return [_Raises(exc, present)] + meta
+
+
+def _parse_dt(value: str):
+    """dateutil.parser.parse as search.py:126-130 calls it, plus whether the result depends on today's date (missing
+    fields are taken from `default` = today): such values must be parsed again for every query."""
+    try:
+        a = dateutil.parser.parse(value, default=datetime(2001, 1, 1))
+        b = dateutil.parser.parse(value, default=datetime(2002, 2, 2))
+    except (ValueError, TypeError, OverflowError):
+        return None, False
+    return a, a != b
+
+
+def _judge_value(v1: Any, op: str, v2: Any) -> bool:
+    """The reference's comparison of ONE resolved field value with the operand (search.py:141-242), applied on the host to
+    the distinct values of a date-like header (a datetime when dateutil could parse it, else the raw string).  May raise TypeError."""
+    if op == "contains":
+        return str(v2).lower() in str(v1).lower()
+    if op == "matches":
+        try:
+            return re.search(str(v2), str(v1), re.IGNORECASE) is not None
+        except re.error:
+            return False
+    if op == "startswith":
+        return str(v1).lower().startswith(str(v2).lower())
+    if op == "endswith":
+        return str(v1).lower().endswith(str(v2).lower())
+    if op == "has_tag":
+        return str(v2).lower() in [t.strip() for t in str(v1).lower().split(",")]
+    if op == "has_flag":
+        return str(v2).upper() in str(v1)
+    if op not in CMP:
+        return False
+    if isinstance(v1, datetime) and not isinstance(v2, datetime):
+        try:
+            v2 = dateutil.parser.parse(str(v2))
+        except (ValueError, TypeError):
+            return False
+    if op in ("=", "!="):
+        if isinstance(v1, str) and isinstance(v2, str):
+            return (v1.lower() == v2.lower()) == (op == "=")
+        return (v1 == v2) == (op == "=")
+    if isinstance(v2, str) and v2.startswith("now"):
+        now = datetime.now()
+        if v2 == "now":
+            v2 = now
+        else:
+            m = re.match(r"now([+-])(\d+)([dwmy])", v2)
+            if m:
+                k = int(m.group(2)) * (-1 if m.group(1) == "-" else 1)
+                v2 = now + timedelta(days=k * {"d": 1, "w": 7, "m": 30, "y": 365}[m.group(3)])
+    return {">": lambda: v1 > v2, "<": lambda: v1 < v2, ">=": lambda: v1 >= v2, "<=": lambda: v1 <= v2}[op]()
+
+
+def _compile_date_header(field: str, op: str, v2: Any, pm) -> List[Any]:
+    """Due / Created / Modified / DeletedDate: the header value goes through dateutil per record (search.py:126-130).  The GPU hands
+    back every record's value (fei_corpus_slot_values), the host judges the DISTINCT values with the reference's rules and returns the
+    verdicts as aux columns the scan reads (C_RECBITS): one for 'condition holds', one for 'the reference would raise here'."""
+    present, inv, distinct = pm.header_values(field)
+    ok = np.zeros(len(distinct) + 1, dtype=np.uint8)      # last entry: absent header (None -> False, search.py:144-145)
+    bad = np.zeros(len(distinct) + 1, dtype=np.uint8)
+    first_exc: Optional[Exception] = None
+    excs: Dict[int, Exception] = {}
+    for k, text in enumerate(distinct):
+        parsed = pm.parsed_dates.get(text)
+        if parsed is None:
+            parsed = pm.parsed_dates[text] = _parse_dt(text)
+        dt, today_dependent = parsed
+        if today_dependent:
+            dt = dateutil.parser.parse(text)
+        try:
+            ok[k] = 1 if _judge_value(dt if dt is not None else text, op, v2) else 0
+        except TypeError as e:
+            bad[k] = 1
+            excs[k] = e
+            first_exc = first_exc or e
+    out: List[Any] = []
+    if bad.any():
+        out.append(_Raises(first_exc, Cond(C_RECBITS, which=pm.new_aux(bad[inv])), exc_of=lambda i: excs[int(inv[i])]))
+    out.append(Cond(C_RECBITS, which=pm.new_aux(ok[inv])))
+    return out
+
+
 # ----------------------------------------------------------------------------- search
+_LOWER_KINDS = ("contains", "startswith", "endswith", "equals", "has_tag")
+
+
+def check_sigma(pm, conds: Sequence[Cond], ranges) -> None:
+    """str.lower() maps U+03A3 to a final or a medial sigma depending on its neighbours (search.py:148-163 read values through
+    lower()); every other character, U+0130's two-character expansion included, is modelled exactly by the automata.  A needle
+    without any sigma cannot tell the two forms apart, so only a sigma-bearing needle over records that hold U+03A3 is refused."""
+    risky = [c for c in conds if c.pattern is not None and c.pattern.kind in _LOWER_KINDS and ("σ" in c.pattern.text or "ς" in c.pattern.text)]
+    if risky and pm.sigma_in(ranges):
+        raise NotImplementedError("the searched records hold a capital sigma and the operand contains a sigma: str.lower() picks the "
+                                  "final or medial form from the context; refused rather than answered inexactly")
+
+
 def _scan_ranges(pm, conds: List[Cond], ranges: List[Tuple[int, int]]) -> np.ndarray:
     """Ordered hit indices (pack order restricted / re-ordered to the requested segments)."""
-    lower_kinds = ("contains", "startswith", "endswith", "equals", "has_tag")
-    if pm.arrays.get("any_lower_inexact") and any(c.pattern is not None and c.pattern.kind in lower_kinds for c in conds):
-        raise NotImplementedError("corpus holds U+0130 / capital sigma: str.lower() on those records is context dependent; "
-                                  "lower-case string operators are refused rather than answered inexactly")
+    check_sigma(pm, conds, ranges)
     pb = ProgramBuilder()
     pb.add_query(conds)
     hits = pm.corpus.scan_hits(pb.build(), 1)[0].astype(np.int64)
@@ -307,21 +474,24 @@ def _get_field_value(memory: Dict[str, Any], field: str) -> Any:
 def search_memories(query: SearchQuery, folders: Optional[List[str]] = None, statuses: Optional[List[str]] = None,
                     debug: bool = False) -> List[Dict[str, Any]]:
     pm = packer.packed()
-    ranges = pm.ranges(folders, statuses)
-    pm.report_skipped(folders, statuses)
-    compiled = compile_conditions(query.conditions, query.include_content, pm)
-    conds: List[Cond] = []
-    for item in compiled:
-        if isinstance(item, _Raises):
-            # the reference raises as soon as one record reaches this condition with a value
-            probe = conds + ([item.presence] if item.presence is not None else [])
-            if len(_scan_ranges(pm, probe or [const(True)], ranges)):
-                raise item.exc
-            conds.append(const(False))                   # nobody reaches it: everything was rejected earlier
-            break
-        conds.append(item)
-    hits = _scan_ranges(pm, conds or [const(True)], ranges)
-    results = [packer.memory_dict(pm.recs[i], query.include_content) for i in hits.tolist()]
+    with pm.lock:                                        # one snapshot of the packed corpus (and its aux columns) for the whole request
+        ranges = pm.ranges(folders, statuses)
+        pm.report_skipped(folders, statuses)
+        pm.begin_query()
+        compiled = compile_conditions(query.conditions, query.include_content, pm)
+        conds: List[Cond] = []
+        for item in compiled:
+            if isinstance(item, _Raises):
+                # the reference raises as soon as one record reaches this condition with a value
+                probe = conds + ([item.presence] if item.presence is not None else [])
+                reached = _scan_ranges(pm, probe or [const(True)], ranges)
+                if len(reached):
+                    raise (item.exc_of(int(reached[0])) if item.exc_of else item.exc)
+                conds.append(const(False))               # nobody reaches it: everything was rejected earlier
+                break
+            conds.append(item)
+        hits = _scan_ranges(pm, conds or [const(True)], ranges)
+        results = [packer.memory_dict(pm.recs[i], query.include_content) for i in hits.tolist()]
     if query.sort_by:
         try:
             results.sort(key=lambda x: _get_field_value(x, query.sort_by) or "", reverse=query.sort_reverse)

@@ -145,9 +145,9 @@ def search_memories(query: str, folders: List[str] = None, statuses: List[str] =
     pm = packer.packed()
     ranges = pm.ranges(folders, statuses)
     pm.report_skipped(folders, statuses)
-    if pm.arrays.get("any_lower_inexact"):
-        raise NotImplementedError("corpus holds U+0130 / capital sigma: str.lower() on those records is context dependent; "
-                                  "the substring search is refused rather than answered inexactly")
+    if ("σ" in low or "ς" in low) and pm.sigma_in(ranges):
+        raise NotImplementedError("the searched records hold a capital sigma and the query contains a sigma: str.lower() picks the "
+                                  "final or medial form from the context; refused rather than answered inexactly")
     pb = ProgramBuilder()
     pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", low), field="", mode=2)])
     if not headers_only:

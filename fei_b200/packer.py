@@ -13,6 +13,7 @@ from __future__ import annotations
 import calendar
 import os
 import re
+import threading
 from datetime import datetime
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -20,7 +21,7 @@ import numpy as np
 
 from .memdir_tools import utils as U
 
-REC_NO_SEPARATOR, REC_NONASCII, REC_LOWER_INEXACT = 1, 2, 4
+REC_NO_SEPARATOR, REC_NONASCII, REC_HAS_SIGMA, REC_HAS_IDOT = 1, 2, 4, 8
 _LIST_RE = re.compile(r"\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*")          # utils.py:223
 
 
@@ -160,8 +161,10 @@ def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, i
         text = r["hdr_text"] + r["body_text"]
         if not text.isascii():
             b |= REC_NONASCII
-            if "İ" in text or "Σ" in text:
-                b |= REC_LOWER_INEXACT
+            if "Σ" in text:
+                b |= REC_HAS_SIGMA
+            if "İ" in text:
+                b |= REC_HAS_IDOT
         bits[i] = b
     ts = np.array([r["ts"] for r in recs], dtype=np.int64)
     wall = np.array([calendar.timegm(r["date"].timetuple()) for r in recs], dtype=np.int64)
@@ -170,7 +173,7 @@ def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, i
                     for i, r in enumerate(recs)], dtype=np.uint32)
     return {"n": n, "global_base": global_base, "hdr": hdr, "hdr_off": hdr_off, "body": body, "body_off": body_off,
             "name": name, "name_off": name_off, "name_spans": spans.reshape(-1), "ts": ts, "wall": wall, "flags8": f8, "fsb": fsb,
-            "any_lower_inexact": bool((bits & REC_LOWER_INEXACT).any()) if n else False}
+            "rec_bits": bits[:n].astype(np.uint8)}
 
 
 def raw_arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, int], global_base: int = 0) -> Dict[str, Any]:
@@ -217,6 +220,10 @@ class PackedMemdir:
         self.file_cache: Dict[Tuple, bytes] = {}
         self.files_read = 0          # files whose content was read from disk by the last build (incremental-sync telemetry)
         self.bad: Dict[Tuple[str, str], List[str]] = {}      # undecodable files per directory, reported on every listing
+        self.lock = threading.RLock()                        # one query at a time plans aux columns / scans this corpus state
+        self._field_values: Dict[str, Tuple[np.ndarray, np.ndarray, List[str]]] = {}
+        self.parsed_dates: Dict[str, Tuple[Any, bool]] = {}  # header value -> (dateutil result | None, depends on today's date)
+        self._aux_next = 0
 
     @staticmethod
     def tree_signature(base: str) -> Tuple:
@@ -256,6 +263,7 @@ class PackedMemdir:
         if upload:
             from .corpus import Corpus
             self.corpus = Corpus().load(self.arrays)
+            self._field_values = {}
         return self
 
     def _build_raw(self) -> "PackedMemdir":
@@ -314,10 +322,59 @@ class PackedMemdir:
                 self.segments[(folder, st)] = (pos, pos + k)
                 pos += k
         self.corpus = corpus
+        self._field_values = {}
         fsb = corpus.fetch_meta()["fsb"] if corpus.n else np.zeros(0, dtype=np.uint32)
-        arrays["any_lower_inexact"] = bool(((fsb >> 24) & REC_LOWER_INEXACT).any())
+        arrays["rec_bits"] = (fsb >> 24).astype(np.uint8)
         self.arrays = arrays
         return self
+
+    # ---- per-record header values for conditions only Python can judge (search.py:126-130)
+    def header_values(self, field: str) -> Tuple[np.ndarray, np.ndarray, List[str]]:
+        """(present[n], inv[n], distinct): the value _get_field_value would read for `field` (first key whose lower() equals
+        field.lower(), last line of that exact key), record by record, as an index into the list of distinct values
+        (len(distinct) for records without the header).  Extracted by the GPU once per packed corpus state."""
+        key = field.lower()
+        got = self._field_values.get(key)
+        if got is None:
+            from .program import C_SLOT, Cond, ProgramBuilder
+            from .regexc import Pattern
+            pb = ProgramBuilder()
+            pb.add_query([Cond(C_SLOT, pattern=Pattern("regex", "", re.IGNORECASE), field=field, mode=0)])
+            present, off, blob = self.corpus.slot_values(pb.build())
+            n = self.corpus.n
+            raw = blob.tobytes()
+            index: Dict[bytes, int] = {}
+            inv = np.empty(n, dtype=np.int64)
+            o = off.astype(np.int64)
+            for i in range(n):
+                if not present[i]:
+                    inv[i] = -1
+                    continue
+                inv[i] = index.setdefault(raw[o[i]:o[i + 1]], len(index))
+            distinct = [b.decode("utf-8") for b in index]
+            inv[inv < 0] = len(distinct)
+            got = self._field_values[key] = (present, inv, distinct)
+        return got
+
+    def sigma_in(self, ranges: Sequence[Tuple[int, int]]) -> bool:
+        """Does a record of these index ranges hold U+03A3 (the one character whose str.lower() the automata do not model)?"""
+        bits = self.arrays.get("rec_bits")
+        if bits is None or not len(bits):
+            return False
+        return any(bool((bits[a:b] & REC_HAS_SIGMA).any()) for a, b in ranges)
+
+    def begin_query(self) -> None:
+        self._aux_next = 0
+
+    def new_aux(self, verdicts: np.ndarray) -> int:
+        """Uploads one per-record verdict column for the query being compiled; returns its index (C_RECBITS.which)."""
+        from .program import MAX_AUX
+        if self._aux_next >= MAX_AUX:
+            raise NotImplementedError(f"more than {MAX_AUX} host-judged header conditions in one query")
+        k = self._aux_next
+        self._aux_next += 1
+        self.corpus.set_aux(k, verdicts)
+        return k
 
     def report_skipped(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> None:
         """The reference prints `Error processing <file>: <error>` each time a directory is listed (utils.py:247-248)."""

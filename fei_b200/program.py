@@ -15,9 +15,10 @@ import numpy as np
 from .regexc import Dfa, Pattern, compile_patterns
 
 MAGIC, VERSION = 0x50494546, 1
-C_CONST, C_BODY, C_SLOT, C_FLAGS, C_NAME, C_DATE_CMP, C_FOLDER_SET, C_STATUS_SET = range(8)
+C_CONST, C_BODY, C_SLOT, C_FLAGS, C_NAME, C_DATE_CMP, C_FOLDER_SET, C_STATUS_SET, C_RECBITS, C_TS_CMP = range(10)
 CMP = {">": 0, "<": 1, ">=": 2, "<=": 3, "=": 4, "!=": 5}
-NAME_FILENAME, NAME_ID, NAME_HOST = 0, 1, 2
+NAME_FILENAME, NAME_ID, NAME_HOST, NAME_TS_STR, NAME_DATE_STR = 0, 1, 2, 3, 4     # 3 / 4: str(metadata["timestamp"]) / str(metadata["date"]), formatted by the kernels
+MAX_AUX = 4                            # aux verdict columns per corpus (FEI_C_RECBITS)
 SMEM_TABLE_LIMIT = 200 * 1024          # body automaton must fit the CTA's shared memory
 HEAD_SMEM_WINDOW = 32 * 1024           # scan.cu kHeadProgSmem: the program head the head kernels stage per CTA
 HEAD_DIRECT_LIMIT = 12 * 1024          # a head automaton up to this size is stored byte-indexed
@@ -27,7 +28,8 @@ HEAD_DIRECT_LIMIT = 12 * 1024          # a head automaton up to this size is sto
 class Cond:
     """One condition.  kind + what it reads:
        const(value) | body(pattern) | slot(field, mode, empty_if_missing, pattern) | flags(pattern)
-       | name(which, pattern) | date_cmp(op, micros) | folder_set(bits) | status_set(bits)"""
+       | name(which, pattern) | date_cmp(op, micros) | folder_set(bits) | status_set(bits)
+       | recbits(which = aux column, negate) | ts_cmp(op, i64)"""
     kind: int
     pattern: Optional[Pattern] = None
     negate: bool = False
@@ -161,7 +163,7 @@ class ProgramBuilder:
     def build(self) -> bytes:
         body = _FieldDfa("content")
         flags = _FieldDfa("flags")
-        names = [_FieldDfa("filename"), _FieldDfa("id"), _FieldDfa("hostname")]
+        names = [_FieldDfa("filename"), _FieldDfa("id"), _FieldDfa("hostname"), _FieldDfa("str(timestamp)"), _FieldDfa("str(date)")]
         slots: List[Tuple[str, int, bool]] = []          # (field, mode, empty_if_missing)
         slot_dfas: List[_FieldDfa] = []
         slot_index: Dict[Tuple, int] = {}
@@ -194,6 +196,10 @@ class ProgramBuilder:
                         ref = c.which; bit = names[c.which].bit(c.pattern)
                     elif c.kind == C_CONST:
                         bit = 1 if c.value else 0
+                    elif c.kind == C_RECBITS:
+                        if not 0 <= c.which < MAX_AUX:
+                            raise NotImplementedError("aux column index out of range")
+                        ref = c.which
                 recs.append((c.kind, ref, bit, 1 if c.negate else 0, c.if_missing, c.op, c.i64, c.set64))
             qranges.append((begin, len(recs)))
 
@@ -232,9 +238,9 @@ class ProgramBuilder:
             if tb > 220 * 1024:
                 raise NotImplementedError(f"content automaton needs {tb} bytes of shared memory (limit 220 KiB)")
         _pad16(blob)
-        struct.pack_into("<20I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
+        struct.pack_into("<22I", blob, 0, MAGIC, VERSION, len(blob), len(self.queries), len(recs), off_conds, off_queries,
                          len(slots), off_slots, off_key, off_body, off_flags, off_names[0], off_names[1], off_names[2],
-                         head_mask, body_mask, slot_mask, name_mask, head_bytes)
+                         head_mask, body_mask, slot_mask, name_mask, head_bytes, off_names[3], off_names[4])
         return bytes(blob)
 
 

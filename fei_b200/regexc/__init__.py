@@ -297,13 +297,30 @@ class Pattern:
     flags: int = 0
 
 
-def _lit_chain(n: Nfa, a: int, text: str, lowered: bool) -> int:
-    cur = a
+_IDOT: RangeSet = ((0x130, 0x130),)
+
+
+def _lit_chain(n: Nfa, a: int, text: str, lowered: bool, end_half: bool = False, start_half_from: Optional[int] = None) -> int:
+    """States a -> ... -> end that consume `text`.  lowered: the VALUE is read through str.lower().  lower() is per character
+    except U+0130, which becomes the two characters 'i' + U+0307: one input character then advances the needle by two
+    ('i', U+0307), by its last one (needle ends in 'i' and may end inside the expansion: `end_half`, for contains /
+    startswith) or lets a match begin at the combining dot (`start_half_from` = the state an unanchored match starts from,
+    for contains / endswith).  (Capital sigma's final-form rule is the one context-dependent case left: the host layer refuses
+    needles containing a sigma on corpora that hold U+03A3.)"""
+    states = [a]
     for ch in text:
         b = n.new()
-        n.c(cur, lower_leaf_set(ord(ch)) if lowered else ((ord(ch), ord(ch)),), b)
-        cur = b
-    return cur
+        n.c(states[-1], lower_leaf_set(ord(ch)) if lowered else ((ord(ch), ord(ch)),), b)
+        states.append(b)
+    if lowered and text:
+        for p in range(len(text) - 1):
+            if text[p] == "i" and text[p + 1] == "\u0307":
+                n.c(states[p], _IDOT, states[p + 2])
+        if end_half and text[-1] == "i":
+            n.c(states[-2], _IDOT, states[-1])
+        if start_half_from is not None and text[0] == "\u0307":
+            n.c(start_half_from, _IDOT, states[1])
+    return states[-1]
 
 
 def add_pattern(n: Nfa, pid: int, pat: Pattern) -> None:
@@ -324,16 +341,16 @@ def add_pattern(n: Nfa, pid: int, pat: Pattern) -> None:
     if k in ("contains", "exact_contains"):
         lowered = k == "contains"
         u = n.new(); n.e(n.start, u); n.c(u, _ANY_ALL, u)
-        end = _lit_chain(n, u, pat.text, lowered)
+        end = _lit_chain(n, u, pat.text, lowered, end_half=True, start_half_from=u)
         n.accept[end] = pid
         return
     if k == "startswith":
-        end = _lit_chain(n, n.start, pat.text, True)
+        end = _lit_chain(n, n.start, pat.text, True, end_half=True)
         n.accept[end] = pid
         return
     if k == "endswith":
         u = n.new(); n.e(n.start, u); n.c(u, _ANY_ALL, u)
-        end = _lit_chain(n, u, pat.text, True)
+        end = _lit_chain(n, u, pat.text, True, start_half_from=u)
         acc = n.new(); n.e(end, acc, A_EOS)
         n.accept[acc] = pid
         return

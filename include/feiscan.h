@@ -77,7 +77,8 @@ typedef struct fei_corpus fei_corpus;
 
 #define FEI_REC_NO_SEPARATOR  0x01u  /* no "---": headers = {}, body = whole text (utils.py:107-109) */
 #define FEI_REC_NONASCII      0x02u  /* record contains non-ASCII bytes                               */
-#define FEI_REC_LOWER_INEXACT 0x04u  /* str.lower() of the record is not per-code-point (U+0130, final sigma) */
+#define FEI_REC_HAS_SIGMA     0x04u  /* record holds U+03A3: its str.lower() depends on the context (final sigma, search.py:148-163)  */
+#define FEI_REC_HAS_IDOT      0x08u  /* record holds U+0130, whose lower() is two characters (the automata expand it)               */
 
 typedef struct fei_corpus_host {
   uint64_t n;

@@ -31,6 +31,12 @@ ADVERSARIAL = [
     ("", "cur", "1700000511.adv00013.hostA:2,Fjunk", b"Subject: trailing junk after flags\n---\nflags F then lowercase junk"),
     (".Projects/Python", "new", "1700000512.adv00014.hostA:2,", b"---\n---\nbody starts with a separator"),
     ("", "new", "1700000513.adv00015.hostA:2,", b"Subject: empty body\nTags: python\n---"),
+    # round 2: values only dateutil can judge, a timestamp header, and the two characters whose str.lower() is not one-to-one
+    ("", "cur", "1700000514.adv00016.hostA:2,S", b"Subject: someday due\nDue: someday\nModified: 2024-02-30\nTags: python\n---\nunparseable dates stay strings"),
+    ("", "cur", "1700000515.adv00017.hostA:2,", b"Subject: aware created\nCreated: 2031-01-01T10:00:00+02:00\nDue: 2030-05-05 00:00:00\n---\ntz-aware Created header"),
+    (".Projects/AI", "cur", "1700000516.adv00018.hostA:2,F", b"Subject: partial due\nDue: May 5\nModified: 2024-02-10\nCreated: 10 Jan 2031 08:00\n---\nyear comes from today"),
+    ("", "new", "1700000517.adv00019.hostA:2,", b"Subject: header named timestamp\nTimestamp: 12345\nDUE: 2030-05-05\ndue: 1999-01-01\n---\nthe header wins over the metadata"),
+    ("", "cur", "1700000518.adv00020.hostA:2,P", "Subject: \u0130stanbul \u03a3\u039f\u03a6\u0399\u0391\nTags: \u0130zmir, x\n---\n\u0130 in the body, and \u039f\u0394\u03a5\u03a3\u03a3\u0395\u03a5\u03a3 too\nreact".encode()),
 ]
 
 QUERIES = [
@@ -74,11 +80,48 @@ QUERIES = [
     ("hostname_meta", [("hostname", "contains", "host-c")], False, None, None),
     ("unknown_op", [("Tags", "fuzzy", "x")], False, None, None),
     ("subject_ne", [("Subject", "!=", "x")], False, None, None),
+    # round 2 -- date-like headers through dateutil (search.py:126-130, :166-234)
+    ("due_eq", [("Due", "=", "2030-05-05")], False, None, None),
+    ("due_ne_garbage", [("Due", "!=", "garbage")], False, None, None),
+    ("due_gt_now", [("Due", ">", "now")], False, [".Projects/AI", ".Projects/Python"], None),       # every Due there parses: parse("now") fails -> False
+    ("due_gt_date", [("due", ">", "2023-12-01")], False, None, None),
+    ("due_le_date", [("DUE", "<=", "2023-12-10 00:00")], False, None, None),
+    ("due_contains_year", [("Due", "contains", "2030")], False, None, None),
+    ("due_eq_someday", [("Due", "=", "SOMEDAY")], False, None, None),
+    ("due_matches", [("Due", "matches", "^2030-05-05 00")], False, None, None),
+    ("due_ne_date", [("Due", "!=", "2030-05-05")], False, None, None),
+    ("created_eq_aware", [("Created", "=", "2031-01-01T08:00:00+00:00")], False, None, None),
+    ("created_ne_naive", [("Created", "!=", "2031-01-01 08:00")], False, None, None),
+    ("modified_startswith", [("Modified", "startswith", "2024-02")], False, None, None),
+    ("modified_lt", [("modified", "<", "2024-02-20")], False, None, None),
+    ("deleteddate_absent", [("DeletedDate", "!=", "x")], False, None, None),
+    # metadata timestamp (search.py:134-137) and text operators on the date field (search.py:148-163)
+    ("ts_contains", [("timestamp", "contains", "17000005")], False, None, None),
+    ("ts_eq_int", [("timestamp", "=", 1700000504)], False, None, None),
+    ("ts_eq_str", [("timestamp", "=", "1700000504")], False, None, None),
+    ("ts_eq_hdr", [("timestamp", "=", "12345")], False, None, None),
+    ("ts_ne_str", [("timestamp", "!=", "x")], False, None, None),
+    ("ts_matches", [("timestamp", "matches", "^1700000[01]")], False, None, None),
+    ("date_contains", [("date", "contains", "2023-11-14 22:2")], False, None, None),
+    ("date_matches", [("date", "matches", r"^2023-11-1[45] 2")], False, None, None),
+    ("date_has_flag", [("date", "has_flag", "22:21")], False, None, None),
+    ("date_endswith", [("date", "endswith", ":40")], False, None, None),
+    # U+0130 lowers to two characters; a needle without sigma cannot see which sigma U+03A3 lowers to
+    ("idot_contains_dotted", [("Subject", "contains", "i\u0307stanbul")], False, None, None),
+    ("idot_contains_plain", [("Subject", "contains", "istanbul")], False, None, None),
+    ("idot_startswith_i", [("Subject", "startswith", "i")], False, None, None),
+    ("idot_tag", [("Tags", "has_tag", "\u0130zmir")], False, None, None),
+    ("idot_content", [("content", "contains", "i\u0307 in")], True, None, None),
+    ("sigma_free_needle", [("Subject", "contains", "\u03bf\u03c6\u03b9\u03b1")], False, None, None),
 ]
 
 RAISING = [
     ("priority_gt_now", [("Priority", ">", "now-1d")], "TypeError"),
     ("date_gt_aware", [("date", ">", "2023-11-14T22:14:00+02:00")], "TypeError"),
+    ("created_gt_naive", [("Created", ">", "2020-01-01")], "TypeError"),
+    ("due_gt_now_unparseable", [("Due", ">", "now")], "TypeError"),
+    ("ts_gt_str", [("timestamp", ">", "5")], "TypeError"),
+    ("due_gt_now_minus", [("Subject", "contains", "someday"), ("Due", ">", "now-1d")], "TypeError"),
 ]
 
 SORTED = [
@@ -99,6 +142,8 @@ FILTERS_EXTRA = [
     {"name": "lowercase-key", "conditions": [("tags", "python", False)], "actions": [{"type": "move", "target_folder": ".Trash"}]},
     {"name": "uid", "conditions": [("unique_id", "^adv", False), ("content", "python", True)], "actions": []},
     {"name": "empty", "conditions": [], "actions": [{"type": "move", "target_folder": ".Trash"}]},
+    {"name": "meta-ts", "conditions": [("timestamp", "^17000005", False)], "actions": [{"type": "flag", "flags": "S", "mode": "add"}]},
+    {"name": "meta-date", "conditions": [("date", "2023-11-14 22:2", False), ("content", "python", True)], "actions": []},
 ]
 
 

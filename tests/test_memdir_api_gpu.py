@@ -55,6 +55,31 @@ def test_raising_queries_raise_typeerror(api):
             search_memories(_query(q["conditions"], False))
 
 
+def test_raising_query_raises_the_first_reached_records_error(api):
+    """Mixed raising kinds under one condition: the reference raises what the FIRST record reaching it raises."""
+    from fei_b200.memdir_tools.search import search_memories
+    base, g = api
+    conds = [("Created", ">", "2020-01-01")]
+    mems = mo.listing(base, None, None, False)
+    with pytest.raises(TypeError) as want:
+        mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])
+    with pytest.raises(TypeError) as got:
+        search_memories(_query(conds, False))
+    assert str(got.value) == str(want.value)
+
+
+def test_sigma_needle_over_capital_sigma_records_is_refused_not_guessed(api):
+    """str.lower() turns U+03A3 into a final or medial sigma depending on its neighbours: the one case the automata do not model.
+    Only a needle that itself holds a sigma can see the difference, and only where such records are searched."""
+    from fei_b200.memdir_tools.search import search_memories
+    q = _query([("Subject", "contains", "\u03c3\u03bf\u03c6\u03b9\u03b1")], False)
+    with pytest.raises(NotImplementedError):
+        search_memories(q)
+    assert search_memories(q, folders=[".Projects/Python"]) == []          # no capital sigma in the searched records: answered
+    hit = search_memories(_query([("Subject", "contains", "\u03bf\u03c6\u03b9\u03b1")], False))
+    assert [m["metadata"]["unique_id"] for m in hit] == ["adv00020"]      # sigma-free needle over the same record: exact
+
+
 def test_sort_and_pagination(api):
     from fei_b200.memdir_tools.search import search_memories
     base, g = api
