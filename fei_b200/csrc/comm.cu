@@ -196,10 +196,9 @@ extern "C" int fei_comm_scan_gather(fei_corpus* c, const uint8_t* prog, uint64_t
   if (g.bound != c || g.shard_n[g.rank] != c->n || g.shard_base[g.rank] != c->global_base) { set_error("corpus is not the one bound with fei_comm_bind_corpus (or it was reloaded since)"); return FEI_E_STATE; }
   // the same chunk count on every rank: from the longest shard
   const uint64_t w_max = (g.n_max + kWindow - 1) / kWindow;
-  uint32_t chunks = w_max >= 320 ? 2 : 1;
+  uint32_t chunks = (uint32_t)(w_max / 80);                    // logical chunks of ONE scan launch (window counters), ~300 k records each
   if (const char* e = getenv("FEI_SCAN_CHUNKS")) chunks = (uint32_t)atoi(e);
   if (chunks > kMaxHookChunks) chunks = kMaxHookChunks;
-  if (chunks > 8 && !getenv("FEI_SCAN_CHUNKS")) chunks = 8;
   if (chunks < 1) chunks = 1;
   GatherHook hook; hook.c = c; hook.chunks = chunks;
   FEI_TRY(run_scan(c, prog, prog_len, kScanCompactLists, &hook, chunks));

@@ -62,7 +62,7 @@ struct fei_corpus {
   fei::DevBuf aux[FEI_MAX_AUX]; uint64_t aux_n[FEI_MAX_AUX] = {0};   // host-computed per-record verdict bytes (fei_corpus_set_aux, FEI_C_RECBITS)
   fei::DevBuf stage_raw, stage_raw_off, stage_ms, stage_hlen, stage_blen;   // raw ingest staging (ingest.cu)
   // scan scratch (grown on demand, reused across scans)
-  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors, live_list;
+  fei::DevBuf prog, hits, hit_lists, work_counter, scan_tmp, survivors, live_list, win_done;
   fei::CompactScratch compact;
   uint64_t hit_list_stride = 0;          // entries per query in hit_lists (last fei_scan_hits)
   uint32_t last_nq = 0;

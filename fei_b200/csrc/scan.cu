@@ -570,7 +570,17 @@ struct BodyArgs {
   // (and, multi-GPU, the all-gather) of a finished chunk overlaps the next chunk's scan; *next hands out the chunk's groups
   unsigned long long g_begin;
   unsigned long long* next;
+  // window w (groups [w * kWindow / 32, (w + 1) * kWindow / 32)) is finished when win_done[w] reaches kWindow / 32: the side stream
+  // waits on these counters (k_wait_windows) to compact / send a finished run of windows while this kernel is still scanning
+  unsigned int* win_done;
 };
+constexpr uint32_t kGroupsPerWindow = kWindow / 32;
+__device__ __forceinline__ void signal_group_done(const BodyArgs& a, unsigned long long g, int lane) {
+  if (!a.win_done) return;
+  __threadfence();                                   // this lane's hit mask is visible device-wide ...
+  __syncwarp();
+  if (lane == 0) atomicAdd(a.win_done + g / kGroupsPerWindow, 1u);   // ... before the group counts as done
+}
 
 constexpr int kBodyThreads = 1024;
 
@@ -676,7 +686,11 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     uint32_t alive = 0;
     if (rec != kInvalidRec) alive = a.has_alive ? a.hits[rec] : all_q;
     const bool live = alive != 0;
-    if (__ballot_sync(0xffffffffu, live) == 0) continue;      // nobody in this group can still match: skip its bytes
+    if (__ballot_sync(0xffffffffu, live) == 0) {              // nobody in this group can still match: skip its bytes
+      if (rec != kInvalidRec && !a.has_alive) a.hits[rec] = 0;
+      signal_group_done(a, g, lane);
+      continue;
+    }
     const uint8_t* row = a.tiles + a.grp_base[g] * 16;
     const uint32_t maxu = __shfl_sync(0xffffffffu, units, 0);
     if (lane == 0) touched += (a.grp_base[g + 1] - a.grp_base[g]) * 16;
@@ -716,6 +730,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     } else if (rec != kInvalidRec && !a.has_alive) {
       a.hits[rec] = 0;
     }
+    signal_group_done(a, g, lane);
   }
   if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
@@ -998,6 +1013,8 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
     ragged_pair(A, B);
     close_group(A);
     close_group(B);
+    signal_group_done(a, g, lane);
+    if (g + 1 < a.n_groups) signal_group_done(a, g + 1, lane);
   }
   if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
@@ -1166,7 +1183,8 @@ __global__ void k_scan_blocks(const uint32_t* __restrict__ counts, uint64_t blk0
 }
 
 // ordered emit: lists[q * stride + rank] = global_base + i
-__global__ void __launch_bounds__(kCompactBlock)
+// (32 registers: one CTA of it fits next to a 1024-thread scan CTA that leaves 8 K of the SM's registers free)
+__global__ void __launch_bounds__(kCompactBlock, 8)
 k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_t* __restrict__ offsets, uint64_t blk0,
        uint64_t global_base, uint64_t stride, uint64_t* __restrict__ lists) {
   __shared__ uint32_t wcnt[8][32];          // [warp][query] hits of this warp's records
@@ -1198,6 +1216,21 @@ k_emit(const uint32_t* __restrict__ hits, uint64_t n, uint32_t nq, const uint64_
       pos += __popc(bal);
     }
   }
+}
+
+// Side-stream gate of a pipelined scan: one warp spins until every window of [w0, w1) is finished (see BodyArgs::win_done).
+// A warp that sleeps between polls costs the scan nothing; the time limit only guards against a scan kernel that died.
+__global__ void k_wait_windows(const volatile unsigned int* __restrict__ win_done, uint64_t w0, uint64_t w1, unsigned long long* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const long long t0 = clock64();
+  for (;;) {
+    bool ok = true;
+    for (uint64_t w = w0 + lane; w < w1; w += 32) ok = ok && win_done[w] >= kGroupsPerWindow;
+    if (__all_sync(0xffffffffu, ok)) break;
+    if (clock64() - t0 > 20000000000ll) { if (lane == 0) atomicExch(err, 1ull); break; }     // ~10 s
+    __nanosleep(1000);
+  }
+  __threadfence();
 }
 
 __global__ void k_fill32(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
@@ -1255,12 +1288,13 @@ static int check_prog(const uint8_t* prog, uint64_t len) {
 constexpr uint32_t kMaxChunks = 16;
 struct ChunkPlan { uint32_t n = 1; uint64_t g[kMaxChunks + 1] = {0}; uint64_t rec[kMaxChunks + 1] = {0}; };
 
-static uint32_t chunk_count(uint64_t n_windows, bool allow) {
+static uint32_t chunk_count(uint64_t n_windows, bool allow, bool watermark) {
   uint32_t want = 0;
   if (const char* e = getenv("FEI_SCAN_CHUNKS")) want = (uint32_t)atoi(e);
   if (!allow) return 1;
-  if (!want) want = 1;                                           // (a chunk launch costs ~0.2 ms of persistent-kernel tail: measured, no gain on one GPU)
-  if (want > 8 && !getenv("FEI_SCAN_CHUNKS")) want = 8;
+  // logical chunks of a single launch are nearly free (a one-warp gate kernel each): ~300 k records and up, at most 16; separate
+  // launches cost a kernel tail each, so without the window counters the scan stays in one piece unless asked otherwise
+  if (!want) want = watermark ? (uint32_t)(n_windows / 80) : 1;
   if (want > kMaxChunks) want = kMaxChunks;
   if (want > n_windows) want = (uint32_t)n_windows;
   return want ? want : 1;
@@ -1397,18 +1431,50 @@ int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_
     k_fill32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->hits.as<uint32_t>(), n, all_q);
     ++launches;
   }
-  ChunkPlan plan;
   const uint64_t n_windows = (n + kWindow - 1) / kWindow;
-  plan.n = force_chunks ? force_chunks : chunk_count(n_windows, n && need_body && !gather && (compact_mode != kCompactNone || hook));
+  const bool side_work = (n && compact_mode != kCompactNone) || hook;
+  BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
+             c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>(), 0ull, 0ull, nullptr, nullptr};
+  const unsigned grid = (unsigned)cx.sm_count;
+  // One launch, logical chunks: with side work to overlap, the scan kernel is launched ONCE over all groups and publishes finished
+  // windows (win_done); the side stream gates each chunk's compaction / exchange on them with k_wait_windows.  Cutting the scan into
+  // several LAUNCHES instead (FEI_SCAN_CHUNK_LAUNCHES=1) costs ~0.2 ms of persistent-kernel tail per launch (measured on 10 M entries:
+  // 14.3 ms in one launch, 15.8 ms in eight).
+  const bool env_launches = getenv("FEI_SCAN_CHUNK_LAUNCHES") && getenv("FEI_SCAN_CHUNK_LAUNCHES")[0] == '1';
+  const bool chunkable = n && need_body && !gather && side_work;
+  const bool watermark = chunkable && !env_launches;
+  ChunkPlan plan;
+  plan.n = force_chunks ? force_chunks : chunk_count(n_windows, chunkable, watermark);
   if (plan.n > kMaxChunks) plan.n = kMaxChunks;
   if (plan.n < 1) plan.n = 1;
   plan_chunks(n, plan.n, plan.rec);
   for (uint32_t k = 0; k <= plan.n; ++k) plan.g[k] = (plan.rec[k] + kWindow - 1) / kWindow * (kWindow / 32);
   plan.g[plan.n] = c->n_groups;
-  const bool side_work = (n && compact_mode != kCompactNone) || hook;
-  BodyArgs a{c->prog.as<uint8_t>(), c->tiles.as<uint8_t>(), c->grp_base.as<uint64_t>(), c->grp_rec.as<uint32_t>(), c->grp_len.as<uint32_t>(),
-             c->n_groups, c->hits.as<uint32_t>(), need_head ? 1 : 0, c->work_counter.as<unsigned long long>(), 0ull, 0ull, nullptr};
-  const unsigned grid = (unsigned)cx.sm_count;
+  auto launch_body_range = [&](uint64_t g0, uint64_t g1, uint32_t slot) -> int {
+    a.g_begin = g0; a.n_groups = g1; a.next = a.counter + 8 + slot;
+    int rc = FEI_OK;
+    if (sticky_kernel) {
+      const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
+      FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
+      k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);
+    } else if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
+    else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
+    FEI_TRY(rc);
+    ++launches;
+    return FEI_OK;
+  };
+  auto side_chunk = [&](uint32_t k) -> int {                    // compaction + hook of chunk k, queued on the side stream
+    if (compact_mode == kCompactLists && plan.rec[k + 1] > plan.rec[k]) {
+      const uint64_t b0 = plan.rec[k] / kCompactRecs, b1 = (plan.rec[k + 1] + kCompactRecs - 1) / kCompactRecs;   // chunk bounds are multiples of kWindow (= 2 blocks)
+      k_count<<<(unsigned)(b1 - b0), kCompactBlock, 0, c->side>>>(c->hits.as<uint32_t>(), n, nq, b0, c->compact.blk_counts.as<uint32_t>());
+      k_scan_blocks<<<nq, 256, 0, c->side>>>(c->compact.blk_counts.as<uint32_t>(), b0, b1 - b0, nq, c->compact.blk_offsets.as<uint64_t>(), c->compact.totals.as<uint64_t>());
+      k_emit<<<(unsigned)(b1 - b0), kCompactBlock, 0, c->side>>>(c->hits.as<uint32_t>(), n, nq, c->compact.blk_offsets.as<uint64_t>(), b0, c->global_base,
+                                                               c->hit_list_stride, c->hit_lists.as<uint64_t>());
+      launches += 3;
+    }
+    if (hook) FEI_TRY(hook->on_chunk(k, plan.n, plan.rec[k], plan.rec[k + 1], c->side));
+    return FEI_OK;
+  };
   if (n && need_body && gather) {
     a.gather_max = n / kGatherDiv;
     FEI_TRY(c->live_list.ensure((a.gather_max + 1) * sizeof(uint32_t)));
@@ -1418,31 +1484,26 @@ int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_
     k_body_gather<<<grid, kBodyThreads, smem, s>>>(a, c->live_list.as<uint32_t>(), c->rec_pos.as<uint32_t>());
     launches += 2;
   }
-  for (uint32_t k = 0; k < plan.n; ++k) {
-    if (n && need_body && plan.g[k + 1] > plan.g[k]) {
-      a.g_begin = plan.g[k]; a.n_groups = plan.g[k + 1]; a.next = a.counter + 8 + k;
-      int rc = FEI_OK;
-      if (sticky_kernel) {
-        const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
-        FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
-        k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);
-      } else if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
-      else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
-      FEI_TRY(rc);
-      ++launches;
+  if (watermark && plan.n > 1) {
+    FEI_TRY(c->win_done.ensure((n_windows + 1) * sizeof(unsigned int)));
+    FEI_CUDA(cudaMemsetAsync(c->win_done.p, 0, (n_windows + 1) * sizeof(unsigned int), s));
+    a.win_done = c->win_done.as<unsigned int>();
+    FEI_CUDA(cudaEventRecord(c->ev_chunk[0], s));              // head pass done, counters zeroed: the side stream may start polling
+    FEI_CUDA(cudaStreamWaitEvent(c->side, c->ev_chunk[0], 0));
+    FEI_TRY(launch_body_range(0, c->n_groups, 0));
+    for (uint32_t k = 0; k < plan.n; ++k) {
+      const uint64_t w0 = plan.rec[k] / kWindow, w1 = (plan.rec[k + 1] + kWindow - 1) / kWindow;
+      if (w1 > w0) { k_wait_windows<<<1, 32, 0, c->side>>>(c->win_done.as<unsigned int>(), w0, w1, a.counter + 5); ++launches; }
+      FEI_TRY(side_chunk(k));
     }
-    if (!side_work) continue;
-    FEI_CUDA(cudaEventRecord(c->ev_chunk[k], s));
-    FEI_CUDA(cudaStreamWaitEvent(c->side, c->ev_chunk[k], 0));
-    if (compact_mode == kCompactLists && plan.rec[k + 1] > plan.rec[k]) {
-      const uint64_t b0 = plan.rec[k] / kCompactRecs, b1 = (plan.rec[k + 1] + kCompactRecs - 1) / kCompactRecs;   // chunk bounds are multiples of kWindow (= 2 blocks)
-      k_count<<<(unsigned)(b1 - b0), kCompactBlock, 0, c->side>>>(c->hits.as<uint32_t>(), n, nq, b0, c->compact.blk_counts.as<uint32_t>());
-      k_scan_blocks<<<nq, 1024, 0, c->side>>>(c->compact.blk_counts.as<uint32_t>(), b0, b1 - b0, nq, c->compact.blk_offsets.as<uint64_t>(), c->compact.totals.as<uint64_t>());
-      k_emit<<<(unsigned)(b1 - b0), kCompactBlock, 0, c->side>>>(c->hits.as<uint32_t>(), n, nq, c->compact.blk_offsets.as<uint64_t>(), b0, c->global_base,
-                                                               c->hit_list_stride, c->hit_lists.as<uint64_t>());
-      launches += 3;
+  } else {
+    for (uint32_t k = 0; k < plan.n; ++k) {
+      if (n && need_body && plan.g[k + 1] > plan.g[k]) FEI_TRY(launch_body_range(plan.g[k], plan.g[k + 1], k));
+      if (!side_work) continue;
+      FEI_CUDA(cudaEventRecord(c->ev_chunk[k], s));
+      FEI_CUDA(cudaStreamWaitEvent(c->side, c->ev_chunk[k], 0));
+      FEI_TRY(side_chunk(k));
     }
-    if (hook) FEI_TRY(hook->on_chunk(k, plan.n, plan.rec[k], plan.rec[k + 1], c->side));
   }
   FEI_CUDA(cudaEventRecord(c->ev[3], s));
   if (side_work) {
@@ -1469,10 +1530,11 @@ int finish_timing(fei_corpus* c, bool compacted) {
   if (compacted) { FEI_CUDA(cudaEventElapsedTime(&t, c->ev[3], c->ev[4])); c->timing.compact_ms = t; }   // what is left after the last chunk's scan
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[4], c->ev[5])); c->timing.d2h_ms = t;
   FEI_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5])); c->timing.total_ms = t;
-  unsigned long long cnt[4] = {0, 0, 0, 0};
+  unsigned long long cnt[6] = {0, 0, 0, 0, 0, 0};
   FEI_CUDA(cudaMemcpy(cnt, c->work_counter.as<unsigned long long>(), sizeof(cnt), cudaMemcpyDeviceToHost));
   c->timing.body_bytes_touched = cnt[1];
   c->timing.body_bytes_read = cnt[3];
+  if (cnt[5]) { set_error("pipelined scan: the side stream gave up waiting for the scan kernel's finished windows"); return FEI_E_CUDA; }
   return FEI_OK;
 }
 
@@ -1490,7 +1552,7 @@ int compact_masks(const uint32_t* masks, uint64_t n, uint32_t nq, uint64_t globa
   FEI_TRY(sc.totals.ensure(32 * sizeof(uint64_t)));
   FEI_CUDA(cudaMemsetAsync(sc.totals.p, 0, 32 * sizeof(uint64_t), s));
   k_count<<<(unsigned)nblocks, kCompactBlock, 0, s>>>(masks, n, nq, 0, sc.blk_counts.as<uint32_t>());
-  k_scan_blocks<<<nq, 1024, 0, s>>>(sc.blk_counts.as<uint32_t>(), 0, nblocks, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());
+  k_scan_blocks<<<nq, 256, 0, s>>>(sc.blk_counts.as<uint32_t>(), 0, nblocks, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());
   if (launches) *launches += 2;
   FEI_CUDA(cudaMemcpyAsync(counts_out, sc.totals.p, nq * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   FEI_CUDA(cudaStreamSynchronize(s));
@@ -1522,7 +1584,7 @@ int compact_segments(const uint32_t* masks, uint64_t seg_stride, const uint64_t*
     if (!n) continue;
     const uint32_t* m = masks + (size_t)r * seg_stride;
     k_count<<<(unsigned)nb, kCompactBlock, 0, s>>>(m, n, nq, 0, sc.blk_counts.as<uint32_t>());
-    k_scan_blocks<<<nq, 1024, 0, s>>>(sc.blk_counts.as<uint32_t>(), 0, nb, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());   // the carry runs on across segments
+    k_scan_blocks<<<nq, 256, 0, s>>>(sc.blk_counts.as<uint32_t>(), 0, nb, nq, sc.blk_offsets.as<uint64_t>(), sc.totals.as<uint64_t>());   // the carry runs on across segments
     k_emit<<<(unsigned)nb, kCompactBlock, 0, s>>>(m, n, nq, sc.blk_offsets.as<uint64_t>(), 0, seg_base[r], stride, lists);
   }
   if (totals_out) {
