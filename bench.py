@@ -362,7 +362,7 @@ def main():
     parity.update(run_parity(args, rank, world, dist, corpus, prog, nq, lib, _abi))
     line["parity"] = parity
     if dist:
-        line["multi_gpu"] = run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, allmax, step_ms)
+        line["multi_gpu"] = run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, allmax, step_ms, step)
 
     # end-to-end through the C ABI from pinned host buffers, every rank on its own batches (own PCIe link)
     barrier()
@@ -479,12 +479,23 @@ def run_parity(args, rank, world, dist, corpus, prog, nq, lib, _abi):
     return out
 
 
-def run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, allmax, step_ms):
+def run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, allmax, step_ms, step):
     """cfg5's other leg and the list form of the result: (a) the cfg-2 query on the full shards, exchanged with the sparse grouped-
     broadcast all-gatherv of the compacted lists; (b) the GLOBAL ordered lists of the 32-pattern batch materialised on every rank
     from the gathered masks (what a caller that wants indices rather than masks pays on top of a step)."""
     out = {}
     n_total = args.entries * world
+    step(); barrier()                                   # the gathered masks of the batch are the last exchange on every rank again
+    gl = np.zeros(32, dtype=np.uint64); lms = C.c_float()
+    vals = []
+    for _ in range(3):
+        _abi.check(lib.fei_comm_global_lists(32, _abi.ptr(gl), C.byref(lms)))
+        vals.append(lms.value)
+    lists_ms = allmax(float(np.mean(vals[1:])))
+    out["global_ordered_lists"] = {"build_ms": lists_ms, "ms_per_step_including_lists": step_ms + lists_ms,
+                                   "value_including_lists": n_total / ((step_ms + lists_ms) * 1e-3), "unit": "memories/s",
+                                   "list_bytes_per_rank": int(gl.sum()) * 8,
+                                   "note": "32 global ordered index lists built on every rank's device from the gathered masks (k_count / k_scan_blocks / k_emit over the rank segments)"}
     pr = batch_cfg2_program(n_total)
     tot = np.zeros(32, dtype=np.uint64)
 
@@ -502,16 +513,6 @@ def run_multi_extra(args, rank, world, dist, corpus, st, lib, _abi, barrier, all
     out["cfg2_query_sparse_allgatherv"] = {"ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": "memories/s", "hits_total": int(tot[0]),
                                            "wire": "counts all-gather + one grouped ncclBroadcast per (rank, query) list segment",
                                            "query": "Tags has_tag python AND flags has_flag F AND date > median AND content matches react|angular"}
-    gl = np.zeros(32, dtype=np.uint64); lms = C.c_float()
-    vals = []
-    for _ in range(3):
-        _abi.check(lib.fei_comm_global_lists(32, _abi.ptr(gl), C.byref(lms)))
-        vals.append(lms.value)
-    lists_ms = allmax(float(np.mean(vals[1:])))
-    out["global_ordered_lists"] = {"build_ms": lists_ms, "ms_per_step_including_lists": step_ms + lists_ms,
-                                   "value_including_lists": n_total / ((step_ms + lists_ms) * 1e-3), "unit": "memories/s",
-                                   "list_bytes_per_rank": int(gl.sum()) * 8,
-                                   "note": "32 global ordered index lists built on every rank's device from the gathered masks (k_count / k_scan_blocks / k_emit over the rank segments)"}
     return out
 
 

@@ -57,6 +57,11 @@ class ScanTiming(C.Structure):
                 ("body_bytes_touched", C.c_uint64), ("body_bytes_read", C.c_uint64)]
 
 
+class DirlistView(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("names", C.c_void_p), ("name_off", C.c_void_p), ("ts", C.c_void_p), ("wall", C.c_void_p), ("mtime_ns", C.c_void_p),
+                ("ino", C.c_void_p), ("size", C.c_void_p), ("flags8", C.c_void_p), ("spans", C.c_void_p), ("status", C.c_void_p), ("flags_len", C.c_void_p)]
+
+
 class JsonCol(C.Structure):
     _fields_ = [("tag", C.c_void_p), ("uniform_tag", C.c_int32), ("num", C.c_void_p), ("str", C.c_void_p), ("str_off", C.c_void_p)]
 
@@ -76,6 +81,11 @@ _SIGS = {
     "fei_host_unregister": (C.c_int, [_P]),
     "fei_microbench_alu": (C.c_int, [C.c_int, _P, _P]),
     "fei_host_copy_bench": (C.c_int, [_P, _U64, C.c_int, _P, _P]),
+    "fei_dir_list": (C.c_int, [C.c_char_p, _P]),
+    "fei_dirlist_view_get": (C.c_int, [_P, _P]),
+    "fei_dirlist_free": (None, [_P]),
+    "fei_read_files": (C.c_int, [C.c_char_p, _P, _P, _U64, _P, _P, C.c_int, _P, _P]),
+    "fei_write_files": (C.c_int, [C.c_char_p, _P, _P, _P, _P, _U64, C.c_int]),
     "fei_corpus_create": (C.c_int, [_P]),
     "fei_corpus_destroy": (C.c_int, [_P]),
     "fei_corpus_load": (C.c_int, [_P, _P]),
@@ -83,6 +93,9 @@ _SIGS = {
     "fei_corpus_synth": (C.c_int, [_P, _U64, _U64, _U64]),
     "fei_corpus_stats_get": (C.c_int, [_P, _P]),
     "fei_corpus_fetch": (C.c_int, [_P, _U64, _U64, _P, _U64, _P, _P, _U64, _P, _P, _P, _P, _P]),
+    "fei_corpus_fetch_records": (C.c_int, [_P, _P, _U64, _P, _U64, _P, _P, _U64, _P]),
+    "fei_corpus_save": (C.c_int, [_P, C.c_char_p]),
+    "fei_corpus_load_snapshot": (C.c_int, [_P, C.c_char_p, _P]),
     "fei_scan_masks": (C.c_int, [_P, _P, _U64, _P]),
     "fei_scan_hits": (C.c_int, [_P, _P, _U64, _P, _P, _P]),
     "fei_scan_count": (C.c_int, [_P, _P, _U64, _P]),

@@ -1,0 +1,199 @@
+// Host side of the one-time pack: what utils.list_memories does per directory (memdir_tools/utils.py:202-253) as native,
+// multi-threaded code -- readdir + the file-name grammar + stat, the stable newest-first order, and the file reads (pread into one
+// contiguous, optionally pinned, buffer that fei_corpus_load_raw uploads).  The text work (decode, newline folding, '---' split,
+// strip) stays on the GPU (ingest.cu).  No per-file work is left in Python.
+#include "../../include/feiscan.h"
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <thread>
+#include <vector>
+#include <dirent.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace fei { void set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2))); }
+using fei::set_error;
+
+struct fei_dirlist {
+  std::string blob;                     // names back to back
+  std::vector<uint64_t> name_off;       // n + 1
+  std::vector<int64_t> ts, wall, mtime_ns;
+  std::vector<uint64_t> ino, size, flags8;
+  std::vector<uint16_t> spans;          // 4 per entry: unique_id start, length, hostname start, length (bytes inside the name)
+  std::vector<uint8_t> status;          // 1 = a memory file (grammar matched, ASCII fast path); 2 = let Python's re / int() / datetime decide
+  std::vector<int64_t> flags_len;       // number of flag letters (> 7 cannot be packed)
+};
+
+namespace {
+
+// `\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*` as a prefix match (utils.py:223, :81).  Python's \d also matches non-ASCII digits: names that
+// do not start with an ASCII digit but with a byte >= 0x80 are handed to Python (status 2).
+int parse_name(const char* s, size_t len, int64_t* ts, uint16_t* spans, uint64_t* flags8, int64_t* nflags) {
+  size_t i = 0;
+  if (len && (unsigned char)s[0] >= 0x80) return 2;
+  while (i < len && s[i] >= '0' && s[i] <= '9') ++i;
+  if (i == 0) return 0;
+  if (i < len && (unsigned char)s[i] >= 0x80) return 2;            // could be more (Unicode) digits
+  if (i > 18) return 2;                                            // int() is unbounded; int64 is not
+  if (i >= len || s[i] != '.') return 0;
+  int64_t t = 0;
+  for (size_t k = 0; k < i; ++k) t = t * 10 + (s[k] - '0');
+  size_t a = ++i;
+  while (i < len && ((s[i] >= 'a' && s[i] <= 'z') || (s[i] >= '0' && s[i] <= '9'))) ++i;
+  if (i == a || i >= len || s[i] != '.') return 0;
+  // `[a-z0-9]+\.` then `[^:]+:2,`: the regex backtracks over where the first group ends only if the remainder fails; since group 2
+  // cannot contain '.', its end is the first '.' after at least one character -- no alternative split exists.
+  size_t ue = i;
+  size_t b = ++i;
+  while (i < len && s[i] != ':') ++i;
+  if (i == b || i + 2 >= len + 0 || i >= len) return 0;
+  if (len - i < 3 || s[i + 1] != '2' || s[i + 2] != ',') return 0;
+  size_t he = i;
+  i += 3;
+  uint64_t f = 0; int64_t nf = 0;
+  while (i < len && s[i] >= 'A' && s[i] <= 'Z') { if (nf < 7) f |= (uint64_t)(unsigned char)s[i] << (8 * nf); ++nf; ++i; }
+  if (a > 0xFFFF || he > 0xFFFF) return 2;
+  *ts = t;
+  spans[0] = (uint16_t)a; spans[1] = (uint16_t)(ue - a); spans[2] = (uint16_t)b; spans[3] = (uint16_t)(he - b);
+  *flags8 = f | ((uint64_t)(nf < 7 ? nf : 7) << 56);
+  *nflags = nf;
+  return 1;
+}
+
+}  // namespace
+
+extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
+  if (!path || !out) { set_error("null argument"); return FEI_E_BADARG; }
+  *out = nullptr;
+  DIR* d = opendir(path);
+  if (!d) {
+    if (errno == ENOENT) { *out = new fei_dirlist(); (*out)->name_off.push_back(0); return FEI_OK; }     // os.path.exists(path) false: empty listing
+    set_error("opendir(%s): %s", path, strerror(errno)); return FEI_E_BADARG;
+  }
+  const int dfd = dirfd(d);
+  struct Ent { std::string name; int64_t ts, wall, mtime; uint64_t ino, size, f8; uint16_t sp[4]; uint8_t st; int64_t nf; };
+  std::vector<Ent> ents;
+  while (struct dirent* de = readdir(d)) {
+    const char* nm = de->d_name;
+    if (nm[0] == '.' && (nm[1] == 0 || (nm[1] == '.' && nm[2] == 0))) continue;
+    Ent e; e.ts = 0; e.f8 = 0; e.nf = 0; memset(e.sp, 0, sizeof(e.sp));
+    const size_t len = strlen(nm);
+    const int st = parse_name(nm, len, &e.ts, e.sp, &e.f8, &e.nf);
+    if (st == 0) continue;
+    e.st = (uint8_t)st; e.name.assign(nm, len);
+    struct stat sb;
+    if (fstatat(dfd, nm, &sb, 0) != 0) { e.ino = 0; e.size = 0; e.mtime = -1; e.st = 2; }          // vanished / unreadable: Python reports it
+    else { e.ino = sb.st_ino; e.size = (uint64_t)sb.st_size; e.mtime = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec; }
+    e.wall = 0;
+    if (e.st == 1) {                                               // datetime.fromtimestamp(ts): naive local wall clock (utils.py:94)
+      time_t tt = (time_t)e.ts; struct tm tmv;
+      if (!localtime_r(&tt, &tmv) || tmv.tm_year + 1900 > 9999) e.st = 2;
+      else e.wall = (int64_t)timegm(&tmv);
+    }
+    ents.push_back(std::move(e));
+  }
+  closedir(d);
+  // newest first, ties in readdir order (utils.py:251: sort(key=timestamp, reverse=True) is stable); entries Python must judge go last
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { if (a.st != b.st) return a.st < b.st; return a.st == 1 && a.ts > b.ts; });
+  fei_dirlist* l = new fei_dirlist();
+  const size_t n = ents.size();
+  l->name_off.reserve(n + 1); l->name_off.push_back(0);
+  for (const Ent& e : ents) {
+    l->blob += e.name; l->name_off.push_back(l->blob.size());
+    l->ts.push_back(e.ts); l->wall.push_back(e.wall); l->mtime_ns.push_back(e.mtime); l->ino.push_back(e.ino); l->size.push_back(e.size);
+    l->flags8.push_back(e.f8); l->status.push_back(e.st); l->flags_len.push_back(e.nf);
+    for (int k = 0; k < 4; ++k) l->spans.push_back(e.sp[k]);
+  }
+  *out = l;
+  return FEI_OK;
+}
+
+extern "C" int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v) {
+  if (!l || !v) { set_error("null argument"); return FEI_E_BADARG; }
+  v->n = l->ts.size();
+  v->names = reinterpret_cast<const uint8_t*>(l->blob.data()); v->name_off = l->name_off.data();
+  v->ts = l->ts.data(); v->wall = l->wall.data(); v->mtime_ns = l->mtime_ns.data(); v->ino = l->ino.data(); v->size = l->size.data();
+  v->flags8 = l->flags8.data(); v->spans = l->spans.data(); v->status = l->status.data(); v->flags_len = l->flags_len.data();
+  return FEI_OK;
+}
+
+extern "C" void fei_dirlist_free(fei_dirlist* l) { delete l; }
+
+// Reads n files of one directory into dst at dst_off[i] (capacity dst_off[i+1] - dst_off[i]): `threads` workers, open + pread +
+// close each.  got[i] = bytes read (a file that grew is cut at its capacity and flagged), err[i] = errno or 0.
+extern "C" int fei_read_files(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* dst, const uint64_t* dst_off,
+                              int threads, uint64_t* got, int32_t* err) {
+  if (!dir || (n && (!names || !name_off || !dst || !dst_off || !got || !err))) { set_error("null argument"); return FEI_E_BADARG; }
+  if (threads < 1) threads = 1;
+  if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+  const int dfd = open(dir, O_RDONLY | O_DIRECTORY);
+  if (dfd < 0) { set_error("open(%s): %s", dir, strerror(errno)); return FEI_E_BADARG; }
+  std::atomic<uint64_t> next{0};
+  auto work = [&]() {
+    std::string nm;
+    for (;;) {
+      const uint64_t i0 = next.fetch_add(64);
+      if (i0 >= n) break;
+      const uint64_t i1 = i0 + 64 < n ? i0 + 64 : n;
+      for (uint64_t i = i0; i < i1; ++i) {
+        nm.assign(reinterpret_cast<const char*>(names) + name_off[i], name_off[i + 1] - name_off[i]);
+        got[i] = 0; err[i] = 0;
+        const int fd = openat(dfd, nm.c_str(), O_RDONLY);
+        if (fd < 0) { err[i] = errno; continue; }
+        const uint64_t cap = dst_off[i + 1] - dst_off[i];
+        uint64_t done = 0;
+        while (done < cap) {
+          const ssize_t r = pread(fd, dst + dst_off[i] + done, cap - done, (off_t)done);
+          if (r < 0) { if (errno == EINTR) continue; err[i] = errno; break; }
+          if (r == 0) break;
+          done += (uint64_t)r;
+        }
+        if (!err[i] && done == cap) { char probe; if (pread(fd, &probe, 1, (off_t)done) == 1) err[i] = EFBIG; }      // grew since it was listed
+        got[i] = done;
+        close(fd);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  close(dfd);
+  return FEI_OK;
+}
+
+// Test / bench tooling: writes n files (contents blob/off, names names/name_off) into `dir` with `threads` workers.
+extern "C" int fei_write_files(const char* dir, const uint8_t* names, const uint64_t* name_off, const uint8_t* blob, const uint64_t* off, uint64_t n, int threads) {
+  if (!dir || (n && (!names || !name_off || !blob || !off))) { set_error("null argument"); return FEI_E_BADARG; }
+  if (threads < 1) threads = 1;
+  const int dfd = open(dir, O_RDONLY | O_DIRECTORY);
+  if (dfd < 0) { set_error("open(%s): %s", dir, strerror(errno)); return FEI_E_BADARG; }
+  std::atomic<uint64_t> next{0};
+  std::atomic<int> bad{0};
+  auto work = [&]() {
+    std::string nm;
+    for (;;) {
+      const uint64_t i = next.fetch_add(1);
+      if (i >= n) break;
+      nm.assign(reinterpret_cast<const char*>(names) + name_off[i], name_off[i + 1] - name_off[i]);
+      const int fd = openat(dfd, nm.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+      if (fd < 0) { bad = errno; continue; }
+      uint64_t done = 0; const uint64_t len = off[i + 1] - off[i];
+      while (done < len) { const ssize_t r = write(fd, blob + off[i] + done, len - done); if (r <= 0) { if (errno == EINTR) continue; bad = errno ? errno : EIO; break; } done += (uint64_t)r; }
+      close(fd);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  close(dfd);
+  if (bad) { set_error("writing files into %s: %s", dir, strerror(bad)); return FEI_E_BADARG; }
+  return FEI_OK;
+}

@@ -110,6 +110,32 @@ int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* 
  * Memdir (fei_b200/csrc/synth.cuh), generated on the GPU.                           */
 int fei_corpus_synth(fei_corpus* c, uint64_t seed, uint64_t first, uint64_t n);
 
+/* ---- native directory listing / file reads (host only; the one-time pack of utils.list_memories, utils.py:202-253) ----
+ * fei_dir_list: the entries of one cur/new/tmp directory whose names match the listing grammar `\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*`
+ * (utils.py:223), newest filename timestamp first, ties in readdir (= os.listdir) order (utils.py:251), with what
+ * parse_memory_filename (utils.py:74-95) extracts and a stat of every file (inode / size / mtime: the change detector of the
+ * incremental sync).  status[i]: 1 = parsed natively; 2 = a name only Python's re / int() / datetime can judge (non-ASCII leading
+ * digits, more than 18 digits, years past 9999, a file that vanished): listed last, the caller decides.  A missing directory
+ * lists as empty (utils.py:216-217).                                                                                        */
+typedef struct fei_dirlist fei_dirlist;
+typedef struct fei_dirlist_view {
+  uint64_t n;
+  const uint8_t* names; const uint64_t* name_off;      /* n + 1 offsets */
+  const int64_t* ts; const int64_t* wall; const int64_t* mtime_ns;
+  const uint64_t* ino; const uint64_t* size; const uint64_t* flags8;
+  const uint16_t* spans;                               /* 4 per entry, like fei_corpus_host.name_spans */
+  const uint8_t* status; const int64_t* flags_len;
+} fei_dirlist_view;
+int fei_dir_list(const char* path, fei_dirlist** out);
+int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v);
+void fei_dirlist_free(fei_dirlist* l);
+/* n files of one directory read by `threads` workers into dst[dst_off[i] .. dst_off[i+1]) (capacities from the listing's sizes);
+ * got[i] = bytes read, err[i] = errno (EFBIG: the file grew since it was listed).  dst may be pinned (fei_host_register).     */
+int fei_read_files(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* dst, const uint64_t* dst_off,
+                   int threads, uint64_t* got, int32_t* err);
+/* tooling: write n files into an existing directory with `threads` workers (synthetic trees for tests and the bench).          */
+int fei_write_files(const char* dir, const uint8_t* names, const uint64_t* name_off, const uint8_t* blob, const uint64_t* off, uint64_t n, int threads);
+
 typedef struct fei_corpus_stats {
   uint64_t n, global_base;
   uint64_t hdr_bytes, body_bytes, tile_bytes, name_bytes;
@@ -124,6 +150,16 @@ int fei_corpus_fetch(fei_corpus* c, uint64_t first, uint64_t n,
                      uint8_t* hdr, uint64_t hdr_cap, uint64_t* hdr_off,
                      uint8_t* body, uint64_t body_cap, uint64_t* body_off,
                      int64_t* ts, int64_t* wall, uint64_t* flags8, uint32_t* fsb);
+
+/* Header text and body of the m records idx[0..m) (any order), for materialising hits without keeping file contents on the host.
+ * hdr_off / body_off get m + 1 offsets; hdr / body may be NULL to only size the buffers; FEI_E_CAPACITY if a blob is too small.  */
+int fei_corpus_fetch_records(fei_corpus* c, const uint64_t* idx, uint64_t m, uint8_t* hdr, uint64_t hdr_cap, uint64_t* hdr_off,
+                             uint8_t* body, uint64_t body_cap, uint64_t* body_off);
+/* Snapshot of the packed corpus (everything fei_corpus_load* built) in one file, and its restore: the file is streamed through a
+ * ring of pinned buffers, reader threads ahead of the copy engine; gbs = bytes restored per second (CUDA events).  A process
+ * restart then costs a file read instead of a walk + pack of the Memdir tree (utils.py:202-253 re-reads every file per query). */
+int fei_corpus_save(fei_corpus* c, const char* path);
+int fei_corpus_load_snapshot(fei_corpus* c, const char* path, float* gbs);
 
 /* ---- scan ---------------------------------------------------------------------
  * Replaces the hot loops of memdir_tools.search.search_memories
