@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--e2e-entries", type=int, default=1_000_000, help="records per streamed batch of the end-to-end leg")
     ap.add_argument("--e2e-batches", type=int, default=10, help="batches per end-to-end step (10 x 1 M = the 10 M-entry configuration)")
     ap.add_argument("--parity-entries", type=int, default=500_000, help="records per rank of the sharded-vs-unsharded parity run")
-    ap.add_argument("--api-files", type=int, default=200_000, help="files of the on-disk Memdir for the Python-API extra")
+    ap.add_argument("--api-files", type=int, default=1_000_000, help="files of the on-disk Memdir for the Python-API extra")
     ap.add_argument("--chain-blocks", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=60000)
     ap.add_argument("--no-extra", action="store_true")
@@ -595,6 +595,9 @@ def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
 
 
 def api_on_disk(n_files: int):
+    """The drop-in entry points end to end on an on-disk Memdir of n_files files (page-cached): cold = native listing + multi-threaded
+    reads + GPU pack + scan; warm = the packed corpus is reused (inotify says nothing changed); then one new file (incremental
+    sync), a snapshot save / restore, and the oracle (the reference's algorithm on one host core) on a sub-tree for the per-file rate."""
     import contextlib, io, shutil, tempfile
     from fei_b200 import packer, synth
     from fei_b200.memdir_tools import filter as gfilter, search as gsearch, utils as gutils
@@ -603,32 +606,55 @@ def api_on_disk(n_files: int):
     try:
         base = os.path.join(scratch, "Memdir")
         t0 = time.perf_counter()
-        synth.write_memdir(base, [synth.record(SEED, i) for i in range(n_files)])
+        synth.write_memdir_native(base, SEED, 0, n_files)
         write_s = time.perf_counter() - t0
         gutils.set_memdir_base(base)
         q = gsearch.SearchQuery(); q.add_condition("content", "matches", r"kubernetes.*docker|docker.*kubernetes"); q.add_condition("Tags", "has_tag", "python")
         q.with_content(True)
+        q0 = gsearch.SearchQuery(); q0.add_condition("content", "matches", r"quagga.*zebra")          # no hits: the cost without materialisation
         sink = io.StringIO()
         with contextlib.redirect_stdout(sink):
             t0 = time.perf_counter(); cold = gsearch.search_memories(q); cold_s = time.perf_counter() - t0
-            warm = []
+            pm = packer.packed()
+            warm, warm0 = [], []
             for _ in range(5):
                 t0 = time.perf_counter(); res = gsearch.search_memories(q); warm.append(time.perf_counter() - t0)
+                t0 = time.perf_counter(); gsearch.search_memories(q0.with_content(True)); warm0.append(time.perf_counter() - t0)
             t0 = time.perf_counter(); stats = gfilter.apply_filters(dry_run=True); filt_first_s = time.perf_counter() - t0     # compiles the filters' automata
             t0 = time.perf_counter(); stats = gfilter.apply_filters(dry_run=True); filt_s = time.perf_counter() - t0
+            gutils.save_memory(".Projects/AI", "fresh body about kubernetes and docker", {"Tags": "python,new", "Subject": "fresh"}, "P")
+            t0 = time.perf_counter(); res2 = gsearch.search_memories(q); inc_s = time.perf_counter() - t0
+            inc = {"ms": inc_s * 1e3, "files_read": pm.files_read, "windows_packed": pm.windows_packed, "hits": len(res2)}
+            snap = os.path.join(scratch, "snap")
+            t0 = time.perf_counter(); pm.save_snapshot(snap); save_s = time.perf_counter() - t0
+            snap_bytes = os.path.getsize(snap + ".corpus")
+            packer.drop()
+            t0 = time.perf_counter(); pm2 = packer.PackedMemdir.from_snapshot(base, snap); load_s = time.perf_counter() - t0
+            packer._cache[base] = pm2
+            t0 = time.perf_counter(); res3 = gsearch.search_memories(q); resync_s = time.perf_counter() - t0
+            snapshot = {"bytes": snap_bytes, "save_s": save_s, "restore_s": load_s, "restore_gbs_device_events": pm2.snapshot_gbs,
+                        "restore_gbs_wall": snap_bytes / load_s / 1e9, "first_query_after_restore_s": resync_s, "files_read_after_restore": pm2.files_read,
+                        "hits": len(res3)}
+            sub_f, sub_s = [".Projects/AI"], ["new"]
             t0 = time.perf_counter()
-            mems = mo.listing(base, None, None, True)
+            mems = mo.listing(base, sub_f, sub_s, True)
             want = mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in (("content", "matches", r"kubernetes.*docker|docker.*kubernetes"), ("Tags", "has_tag", "python"))])
             cpu_s = time.perf_counter() - t0
-        assert len(cold) == len(res)
-        return {"files": n_files, "write_tree_s": write_s, "query": "content matches kubernetes.*docker|docker.*kubernetes AND Tags has_tag python",
+            sub = gsearch.search_memories(q, sub_f, sub_s)
+        assert len(cold) == len(res) and len(res2) == len(res) + 1 and len(res3) == len(res2)
+        assert [m["filename"] for m in sub] == [mems[i]["filename"] for i in want], "API result differs from the oracle on the sub-tree"
+        return {"files": n_files, "write_tree_s": write_s, "query": "content matches kubernetes.*docker|docker.*kubernetes AND Tags has_tag python (with_content)",
                 "search_memories_cold_s": cold_s, "search_memories_warm_ms": float(np.median(warm)) * 1e3, "hits": len(res),
+                "search_memories_warm_no_hits_ms": float(np.median(warm0)) * 1e3,
+                "materialisation_ms_per_1k_hits": (float(np.median(warm)) - float(np.median(warm0))) * 1e3 / max(1, len(res)) * 1000,
                 "apply_filters_default_dry_run_first_ms": filt_first_s * 1e3, "apply_filters_default_dry_run_warm_ms": filt_s * 1e3,
                 "apply_filters_stats": {k: stats.get(k) for k in ("total_memories", "filters_applied", "actions_taken", "memories_modified")},
-                "cpu_oracle_same_search_s": cpu_s, "cpu_oracle_note": "oracle: lists, reads, parses and matches every file on one host core, as the reference does on every call",
-                "memories_per_s_warm": n_files / float(np.median(warm)), "memories_per_s_cold": n_files / cold_s, "memories_per_s_cpu_oracle": n_files / cpu_s}
+                "incremental_one_new_file": inc, "snapshot": snapshot, "host_cores": usable_cores(), "read_threads": packer.READ_THREADS,
+                "cpu_oracle_subtree": {"files": len(mems), "s": cpu_s, "memories_per_s": len(mems) / cpu_s,
+                                       "note": "oracle: lists, reads, parses and matches every file of the sub-tree on one host core, as the reference does on every call"},
+                "memories_per_s_warm": n_files / float(np.median(warm)), "memories_per_s_cold": n_files / cold_s}
     finally:
-        packer._cache.clear()
+        packer.drop()
         shutil.rmtree(scratch, ignore_errors=True)
 
 

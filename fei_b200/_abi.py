@@ -115,6 +115,7 @@ _SIGS = {
     "fei_chain_mine": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _U64, C.c_uint32, _U64, _P, _P, _P]),
     "fei_synth_record_host": (C.c_int, [_U64, _U64, _P, C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "fei_synth_block_host": (C.c_int, [_U64, _U64, _P, _P, _P, _P, _P]),
+    "fei_synth_write_tree": (C.c_int, [C.c_char_p, C.c_char_p, _U64, _U64, _U64, C.c_int]),
     "fei_comm_unique_id": (C.c_int, [_P]),
     "fei_comm_init": (C.c_int, [_P, C.c_int, C.c_int]),
     "fei_comm_destroy": (C.c_int, []),

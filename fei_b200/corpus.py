@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -135,6 +136,30 @@ class Corpus:
         a = np.zeros(32, dtype=np.uint64); s = np.zeros(32, dtype=np.uint64)
         _abi.check(_abi.lib().fei_scan_list_checksum(self._h, nq, _abi.ptr(a), _abi.ptr(s)))
         return a[:nq], s[:nq]
+
+    def fetch_records(self, idx: np.ndarray, want_body: bool = True):
+        """Header text and body of arbitrary records (fei_corpus_fetch_records): (hdr bytes, hdr_off[m+1], body bytes, body_off[m+1])."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint64)
+        m = idx.size
+        ho = np.zeros(m + 1, dtype=np.uint64); bo = np.zeros(m + 1, dtype=np.uint64)
+        l = _abi.lib()
+        _abi.check(l.fei_corpus_fetch_records(self._h, _abi.ptr(idx), m, None, 0, _abi.ptr(ho), None, 0, _abi.ptr(bo)))
+        hdr = np.zeros(max(1, int(ho[m])), dtype=np.uint8)
+        body = np.zeros(max(1, int(bo[m])) if want_body else 1, dtype=np.uint8)
+        _abi.check(l.fei_corpus_fetch_records(self._h, _abi.ptr(idx), m, _abi.ptr(hdr), hdr.size, _abi.ptr(ho),
+                                              _abi.ptr(body) if want_body else None, body.size, _abi.ptr(bo)))
+        return hdr[:int(ho[m])].tobytes(), ho, (body[:int(bo[m])].tobytes() if want_body else b""), bo
+
+    def save(self, path: str) -> None:
+        _abi.check(_abi.lib().fei_corpus_save(self._h, os.fsencode(path)))
+
+    def load_snapshot(self, path: str) -> float:
+        """Restores a corpus saved with save(); returns the restore rate in GB/s (CUDA events around the upload)."""
+        gbs = C.c_float()
+        _abi.check(_abi.lib().fei_corpus_load_snapshot(self._h, os.fsencode(path), C.byref(gbs)))
+        st = self.stats()
+        self.n, self.global_base = st["n"], st["global_base"]
+        return float(gbs.value)
 
     def slot_values(self, prog: bytes):
         """The header value the reference would read for slot 0 of `prog`, record by record (fei_corpus_slot_values):

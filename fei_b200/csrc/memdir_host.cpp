@@ -197,3 +197,54 @@ extern "C" int fei_write_files(const char* dir, const uint8_t* names, const uint
   if (bad) { set_error("writing files into %s: %s", dir, strerror(bad)); return FEI_E_BADARG; }
   return FEI_OK;
 }
+
+// ---------------------------------------------------------------- synthetic tree on disk (tests / bench tooling)
+#include "synth.cuh"
+#include <sys/types.h>
+
+// Writes records [first, first + n) of the deterministic synthetic Memdir (synth.cuh) as Maildir files under `base`
+// ("<ts>.<uid>.<hostname>:2,<flags>" in <folder>/<status>/, content = header text + "---\n" + body, utils.py:129-151), `threads`
+// workers.  The directories must exist.  Same bytes as fei_b200.synth.write_memdir(record(seed, i)).
+extern "C" int fei_synth_write_tree(const char* base, const char* hostname, uint64_t seed, uint64_t first, uint64_t n, int threads) {
+  if (!base || !hostname) { set_error("null argument"); return FEI_E_BADARG; }
+  static const char* const kFolders[4] = {"", ".Projects/Python", ".Projects/AI", ".ToDoLater/Learning"};
+  static const char* const kStatus[3] = {"cur", "new", "tmp"};
+  if (threads < 1) threads = 1;
+  std::atomic<uint64_t> next{0};
+  std::atomic<int> bad{0};
+  auto work = [&]() {
+    std::vector<uint8_t> buf;
+    std::string path;
+    for (;;) {
+      const uint64_t k0 = next.fetch_add(256);
+      if (k0 >= n) break;
+      const uint64_t k1 = k0 + 256 < n ? k0 + 256 : n;
+      for (uint64_t k = k0; k < k1; ++k) {
+        const uint64_t i = first + k;
+        feisynth::CountSink ch; feisynth::gen_header(ch, seed, i);
+        feisynth::CountSink cb; feisynth::gen_body(cb, seed, i);
+        buf.resize((size_t)ch.n + 4 + cb.n);
+        { feisynth::WriteSink w(buf.data()); feisynth::gen_header(w, seed, i); }
+        memcpy(buf.data() + ch.n, "---\n", 4);
+        { feisynth::WriteSink w(buf.data() + ch.n + 4); feisynth::gen_body(w, seed, i); }
+        const feisynth::RecMeta m = feisynth::gen_meta(seed, i);
+        char name[160];
+        snprintf(name, sizeof(name), "%lld.%.8s.%s:2,%.*s", (long long)m.ts, m.uid, hostname, (int)m.nflags, m.flags);
+        path.assign(base);
+        if (kFolders[m.folder][0]) { path += '/'; path += kFolders[m.folder]; }
+        path += '/'; path += kStatus[m.status]; path += '/'; path += name;
+        const int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) { bad = errno; continue; }
+        size_t done = 0;
+        while (done < buf.size()) { const ssize_t r = write(fd, buf.data() + done, buf.size() - done); if (r <= 0) { if (errno == EINTR) continue; bad = errno ? errno : EIO; break; } done += (size_t)r; }
+        close(fd);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  if (bad) { set_error("writing the synthetic tree under %s: %s", base, strerror(bad)); return FEI_E_BADARG; }
+  return FEI_OK;
+}

@@ -73,26 +73,27 @@ class MemoryArchiver:
         """bool[len(criteria_list), n]: which packed records match which criteria dict."""
         now = now or datetime.now()
         pm = packer.packed()
-        plans = [compile_criteria(c, now) for c in criteria_list]
-        queries: List[List[Cond]] = []
-        for plan in plans:
-            for alts in plan:
-                queries.extend(alts)
-        out = np.ones((len(plans), pm.corpus.n), dtype=bool)
-        masks = np.zeros((0, pm.corpus.n), dtype=np.uint32)
-        for lo in range(0, len(queries), 32):
-            pb = ProgramBuilder()
-            for q in queries[lo:lo + 32]:
-                pb.add_query(q)
-            masks = np.vstack([masks, pm.corpus.scan_masks(pb.build())[None, :]])
-        qi = 0
-        for r, plan in enumerate(plans):
-            for alts in plan:
-                hit = np.zeros(pm.corpus.n, dtype=bool)
-                for _ in alts:
-                    hit |= (masks[qi // 32] >> np.uint32(qi % 32)) & np.uint32(1) != 0
-                    qi += 1
-                out[r] &= hit
+        with pm.lock:
+            plans = [compile_criteria(c, now) for c in criteria_list]
+            queries: List[List[Cond]] = []
+            for plan in plans:
+                for alts in plan:
+                    queries.extend(alts)
+            out = np.ones((len(plans), pm.n), dtype=bool)
+            masks = np.zeros((0, pm.n), dtype=np.uint32)
+            for lo in range(0, len(queries), 32):
+                pb = ProgramBuilder()
+                for q in queries[lo:lo + 32]:
+                    pb.add_query(q)
+                masks = np.vstack([masks, pm.scan_masks(pb.build())[None, :]])
+            qi = 0
+            for r, plan in enumerate(plans):
+                for alts in plan:
+                    hit = np.zeros(pm.n, dtype=bool)
+                    for _ in alts:
+                        hit |= (masks[qi // 32] >> np.uint32(qi % 32)) & np.uint32(1) != 0
+                        qi += 1
+                    out[r] &= hit
         return out
 
     def _memory_matches_criteria(self, memory: Dict[str, Any], criteria: Dict[str, Any]) -> bool:
@@ -123,7 +124,7 @@ class MemoryArchiver:
             self.add_cleanup_rule({"status": "obsolete|deprecated"}, "trash")
         pm = packer.packed()
         matched = self.match_criteria([r["criteria"] for r in self.cleanup_rules])
-        gone = np.zeros(pm.corpus.n, dtype=bool)               # acted upon by an earlier rule (real runs re-list after every rule)
+        gone = np.zeros(pm.n, dtype=bool)               # acted upon by an earlier rule (real runs re-list after every rule)
         for rule, row in zip(self.cleanup_rules, matched):
             action = rule["action"]
             for folder in U.get_memdir_folders():
@@ -132,7 +133,7 @@ class MemoryArchiver:
                 pm.report_skipped([folder], ["cur"])
                 lo, hi = pm.segments.get((folder, "cur"), (0, 0))
                 for i in (np.nonzero(row[lo:hi] & ~gone[lo:hi])[0] + lo).tolist():
-                    memory = packer.memory_dict(pm.recs[i], True)
+                    memory = pm.materialize([i], True)[0]
                     if action == "trash":
                         if not dry_run:
                             U.move_memory(memory["filename"], folder, self.trash_folder, "cur", "cur")

@@ -117,31 +117,33 @@ class FilterManager:
 
     def match_matrix(self, pm: "packer.PackedMemdir") -> np.ndarray:
         """mask[i] bit f = filter f accepts record i; 32 filters per pass."""
-        n = pm.corpus.n
+        n = pm.n
         masks = np.zeros((max(1, (len(self.filters) + 31) // 32), n), dtype=np.uint32)
         for g in range(0, len(self.filters), 32):
             pb = ProgramBuilder()
             for f in self.filters[g:g + 32]:
                 conds = _compile_filter_conditions(f.conditions)
                 pb.add_query(conds if conds else [const(True)])
-            masks[g // 32] = pm.corpus.scan_masks(pb.build())
+            masks[g // 32] = pm.scan_masks(pb.build())
         return masks
 
     def process_memories(self, folders: List[str] = None, statuses: List[str] = None, dry_run: bool = False) -> Dict[str, Any]:
         if statuses is None:
             statuses = ["new"]
         pm = packer.packed()
-        ranges = pm.ranges(folders, statuses)
-        pm.report_skipped(folders, statuses)
-        masks = self.match_matrix(pm) if self.filters and pm.corpus.n else np.zeros((1, pm.corpus.n), dtype=np.uint32)
-        idx = np.concatenate([np.arange(a, b) for a, b in ranges]) if ranges else np.zeros(0, dtype=np.int64)
+        with pm.lock:                                        # the match matrix and the matched records come from one corpus state
+            ranges = pm.ranges(folders, statuses)
+            pm.report_skipped(folders, statuses)
+            masks = self.match_matrix(pm) if self.filters and pm.n else np.zeros((1, pm.n), dtype=np.uint32)
+            idx = np.concatenate([np.arange(a, b) for a, b in ranges]) if ranges else np.zeros(0, dtype=np.int64)
+            any_hit = np.zeros(pm.n, dtype=bool)
+            for row in masks:
+                any_hit |= row != 0
+            matched = idx[any_hit[idx]] if idx.size else idx
+            memories = pm.materialize(matched, True)         # the reference gathers every memory before it acts (filter.py:213-216)
         stats = {"total_memories": int(idx.size), "filters_applied": 0, "actions_taken": 0, "memories_modified": 0, "details": []}
         modified = set()
-        any_hit = np.zeros(pm.corpus.n, dtype=bool)
-        for row in masks:
-            any_hit |= row != 0
-        for i in idx[any_hit[idx]].tolist() if idx.size else []:
-            memory = packer.memory_dict(pm.recs[i], True)
+        for i, memory in zip(matched.tolist(), memories):
             applied = []
             for fi, f in enumerate(self.filters):
                 if not (int(masks[fi // 32, i]) >> (fi % 32)) & 1:

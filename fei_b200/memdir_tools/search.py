@@ -431,7 +431,7 @@ def _scan_ranges(pm, conds: List[Cond], ranges: List[Tuple[int, int]]) -> np.nda
     check_sigma(pm, conds, ranges)
     pb = ProgramBuilder()
     pb.add_query(conds)
-    hits = pm.corpus.scan_hits(pb.build(), 1)[0].astype(np.int64)
+    hits = pm.scan_hits(pb.build(), 1)[0]
     parts = []
     for a, b in ranges:
         lo, hi = np.searchsorted(hits, a), np.searchsorted(hits, b)
@@ -491,7 +491,7 @@ def search_memories(query: SearchQuery, folders: Optional[List[str]] = None, sta
                 break
             conds.append(item)
         hits = _scan_ranges(pm, conds or [const(True)], ranges)
-        results = [packer.memory_dict(pm.recs[i], query.include_content) for i in hits.tolist()]
+        results = pm.materialize(hits, query.include_content)
     if query.sort_by:
         try:
             results.sort(key=lambda x: _get_field_value(x, query.sort_by) or "", reverse=query.sort_reverse)

@@ -143,26 +143,26 @@ def search_memories(query: str, folders: List[str] = None, statuses: List[str] =
     from ..regexc import Pattern
     low = query.lower()
     pm = packer.packed()
-    ranges = pm.ranges(folders, statuses)
-    pm.report_skipped(folders, statuses)
-    if ("σ" in low or "ς" in low) and pm.sigma_in(ranges):
-        raise NotImplementedError("the searched records hold a capital sigma and the query contains a sigma: str.lower() picks the "
-                                  "final or medial form from the context; refused rather than answered inexactly")
-    pb = ProgramBuilder()
-    pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", low), field="", mode=2)])
-    if not headers_only:
-        pb.add_query([Cond(C_BODY, pattern=Pattern("contains", low))])
-    nq = 1 if headers_only else 2
-    per_query = [h.astype(np.int64) for h in pm.corpus.scan_hits(pb.build(), nq)]
-    hits = per_query[0] if nq == 1 else np.union1d(per_query[0], per_query[1])       # sorted = listing order inside a segment
-    results = []
-    for a, b in ranges:
-        lo, hi = np.searchsorted(hits, a), np.searchsorted(hits, b)
-        for i in hits[lo:hi].tolist():
-            memory = packer.memory_dict(pm.recs[i], True)
-            if not headers_only:
-                content = memory["content"]
-                memory["content_preview"] = content[:100] + "..." if len(content) > 100 else content
-                del memory["content"]
-            results.append(memory)
+    with pm.lock:                                        # ranges, scan and materialisation from one corpus state
+        ranges = pm.ranges(folders, statuses)
+        pm.report_skipped(folders, statuses)
+        if ("σ" in low or "ς" in low) and pm.sigma_in(ranges):
+            raise NotImplementedError("the searched records hold a capital sigma and the query contains a sigma: str.lower() picks the "
+                                      "final or medial form from the context; refused rather than answered inexactly")
+        pb = ProgramBuilder()
+        pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", low), field="", mode=2)])
+        if not headers_only:
+            pb.add_query([Cond(C_BODY, pattern=Pattern("contains", low))])
+        nq = 1 if headers_only else 2
+        per_query = pm.scan_hits(pb.build(), nq)
+        hits = per_query[0] if nq == 1 else np.union1d(per_query[0], per_query[1])       # sorted = listing order inside a segment
+        results = []
+        for a, b in ranges:
+            lo, hi = np.searchsorted(hits, a), np.searchsorted(hits, b)
+            for memory in pm.materialize(hits[lo:hi], True):
+                if not headers_only:
+                    content = memory["content"]
+                    memory["content_preview"] = content[:100] + "..." if len(content) > 100 else content
+                    del memory["content"]
+                results.append(memory)
     return results

@@ -1,31 +1,891 @@
-"""Pack an on-disk Memdir into the canonical arrays of include/feiscan.h (the one-time ingest).
+"""Pack an on-disk Memdir into the device-resident corpus and keep it in sync (the one-time ingest).
 
-Replaces the per-query walk of utils.list_memories (memdir_tools/utils.py:202-253): files are read
-once, in exactly the reference's listing order — folders in os.walk order (utils.py:48), statuses
-cur/new/tmp, inside a directory os.listdir order stably sorted by filename timestamp, newest first
-(utils.py:220,251) — decoded like `open(path, "r")` (UTF-8 strict, universal newlines; undecodable
-files are reported and skipped, utils.py:247-248), split at the first '---' (utils.py:105), body
-.strip()ped (utils.py:120).  Header *parsing* is left to the GPU (k_head); the host only parses the
-headers of records it has to materialise as result dicts.
+Replaces the per-query walk of utils.list_memories (memdir_tools/utils.py:202-253).  Files are read once, in exactly the
+reference's listing order -- folders in os.walk order (utils.py:48), statuses cur/new/tmp, inside a directory os.listdir order
+stably sorted by filename timestamp, newest first (utils.py:220,251) -- and decoded like `open(path, "r")` (UTF-8 strict,
+universal newlines; undecodable files are reported and skipped, utils.py:247-248).
+
+Who does what:
+  * native host code (csrc/memdir_host.cpp): readdir + file-name grammar + stat per directory, multi-threaded file reads;
+  * GPU (csrc/ingest.cu, corpus.cu, hdir.cu): UTF-8 validation, newline folding, first-'---' split (utils.py:105), body .strip()
+    (utils.py:120), body tiling, header directory / value columns;
+  * this module: which directories changed (inotify, directory mtimes), the diff of a re-listed directory against its cached
+    listing by (name, inode, size, mtime), and the bookkeeping of listing order.  Per-record state lives in numpy arrays.
+
+Incremental sync.  The packed corpus is a BASE corpus (built once, in listing order) plus a small DELTA corpus: new or rewritten
+files are read and appended to the delta (one or a few 4096-record windows re-tiled, not the shard); removed files become
+tombstones; a rename -- move_memory / update_memory_flags are renames, utils.py:255-297, :354-388 -- is recognised by
+(inode, size, mtime) and carried over without reading the file (its packed text moves from the device into the delta with the
+new name, flags and folder).  Listing order is a permutation kept on the host: hits come back as device record ids and are
+mapped to listing positions.  When the delta or the tombstones outgrow a fraction of the base, everything is repacked.
 """
 from __future__ import annotations
 
 import calendar
+import ctypes as C
 import os
 import re
+import struct
 import threading
+import time
 from datetime import datetime
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from . import _abi
 from .memdir_tools import utils as U
 
 REC_NO_SEPARATOR, REC_NONASCII, REC_HAS_SIGMA, REC_HAS_IDOT = 1, 2, 4, 8
 _LIST_RE = re.compile(r"\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*")          # utils.py:223
+MAX_BODY = 32 << 20                                                # packed layout limit per record (corpus.cu)
+MAX_RAW_BATCH = 40 << 30                                           # raw bytes packed in one go
+READ_THREADS = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+_KEY_DT = np.dtype([("ino", "u8"), ("size", "u8"), ("mtime", "i8")])
 
 
+# ----------------------------------------------------------------------------- native directory listing
+class DirListing:
+    """One cur/new/tmp directory as arrays, in the reference's listing order (fei_dir_list + the entries Python must judge)."""
+    __slots__ = ("n", "names", "name_off", "ts", "wall", "flags8", "spans", "ino", "size", "mtime_ns", "bad")
+
+    def name_bytes(self, i: int) -> bytes:
+        return self.names[int(self.name_off[i]):int(self.name_off[i + 1])]
+
+    def name(self, i: int) -> str:
+        return os.fsdecode(self.name_bytes(i))
+
+    def key(self) -> np.ndarray:
+        """Identity of every entry's content: a changed key means the file must be read again."""
+        k = np.zeros(self.n, dtype=_KEY_DT)
+        k["ino"], k["size"], k["mtime"] = self.ino, self.size, self.mtime_ns
+        return k
+
+
+def _arr(p, dt, k):
+    if not k:
+        return np.zeros(0, dtype=dt)
+    return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(k,)).copy()
+
+
+def list_dir(path: str) -> DirListing:
+    l = _abi.lib()
+    h = C.c_void_p()
+    _abi.check(l.fei_dir_list(os.fsencode(path), C.byref(h)))
+    try:
+        v = _abi.DirlistView()
+        _abi.check(l.fei_dirlist_view_get(h, C.byref(v)))
+        n = int(v.n)
+        name_off = _arr(v.name_off, np.uint64, n + 1)
+        blob = C.string_at(v.names, int(name_off[n])) if n else b""
+        status = _arr(v.status, np.uint8, n)
+        nflags = _arr(v.flags_len, np.int64, n)
+        cols = {"ts": _arr(v.ts, np.int64, n), "wall": _arr(v.wall, np.int64, n), "flags8": _arr(v.flags8, np.uint64, n),
+                "ino": _arr(v.ino, np.uint64, n), "size": _arr(v.size, np.uint64, n), "mtime_ns": _arr(v.mtime_ns, np.int64, n)}
+        spans = _arr(v.spans, np.uint16, 4 * n).reshape(-1, 4)
+    finally:
+        l.fei_dirlist_free(h)
+    d = DirListing()
+    d.bad = []
+    keep = np.ones(n, dtype=bool)
+    extra: List[Tuple[int, int, Dict[str, Any]]] = []                 # entries Python judged: (ts, original index, fields)
+    for i in np.nonzero((status != 1) | (nflags > 7) | (cols["size"] > MAX_BODY))[0].tolist():
+        keep[i] = False
+        name = os.fsdecode(blob[int(name_off[i]):int(name_off[i + 1])])
+        try:
+            if status[i] == 1:
+                raise NotImplementedError("more than 7 flag letters" if nflags[i] > 7 else "a file over 32 MiB does not fit the packed layout")
+            if not _LIST_RE.match(name):                              # what the reference does for this name (utils.py:223-233)
+                continue
+            m = U.FILENAME_RE.match(name)
+            if not m:
+                raise ValueError(f"Invalid memory filename: {name}")
+            ts = int(m.group(1))
+            date = datetime.fromtimestamp(ts)
+            st = os.stat(os.path.join(path, name))
+            if len(m.group(4)) > 7 or st.st_size > MAX_BODY or not -(1 << 62) < ts < (1 << 62):
+                raise NotImplementedError("beyond the packed layout (more than 7 flag letters, a file over 32 MiB or a timestamp past int64)")
+            sp = [len(os.fsencode(name[:x])) for x in (m.start(2), m.end(2), m.start(3), m.end(3))]
+            f8 = len(m.group(4)) << 56
+            for k, ch in enumerate(m.group(4)):
+                f8 |= ord(ch) << (8 * k)
+            extra.append((ts, i, {"name": os.fsencode(name), "ts": ts, "wall": calendar.timegm(date.timetuple()), "flags8": f8,
+                                  "spans": (sp[0], sp[1] - sp[0], sp[2], sp[3] - sp[2]), "ino": st.st_ino, "size": st.st_size, "mtime_ns": st.st_mtime_ns}))
+        except Exception as e:                                        # reported like the reference reports a bad file (utils.py:247-248)
+            d.bad.append(f"Error processing {name}: {e}")
+    idx = np.nonzero(keep)[0]
+    lens = (name_off[1:] - name_off[:-1]).astype(np.int64)
+    if len(idx) == n:
+        d.names, d.name_off = blob, name_off
+    else:
+        d.names = b"".join(blob[int(name_off[i]):int(name_off[i + 1])] for i in idx.tolist())
+        d.name_off = np.zeros(len(idx) + 1, dtype=np.uint64)
+        np.cumsum(lens[idx], out=d.name_off[1:])
+    for k, a in cols.items():
+        setattr(d, k, a[idx])
+    d.spans = spans[idx]
+    d.n = len(idx)
+    for ts, _i, f in sorted(extra, key=lambda t: (-t[0], t[1])):       # merge the Python-judged entries at their timestamp position
+        pos = int(np.searchsorted(-d.ts, -ts, side="right"))
+        a = int(d.name_off[pos])
+        d.names = d.names[:a] + f["name"] + d.names[a:]
+        d.name_off = np.concatenate([d.name_off[:pos + 1], d.name_off[pos:] + np.uint64(len(f["name"]))])
+        for k in ("ts", "wall", "flags8", "ino", "size", "mtime_ns"):
+            a_ = getattr(d, k)
+            setattr(d, k, np.insert(a_, pos, np.array(f[k]).astype(a_.dtype)))
+        d.spans = np.insert(d.spans, pos, np.array(f["spans"], dtype=np.uint16), axis=0)
+        d.n += 1
+    return d
+
+
+def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray, List[Tuple[int, str]]]:
+    """Contents of the selected entries (all when sel is None): (raw blob, offsets[k+1], [(k, error message)])."""
+    if sel is None:
+        names, name_off, sizes = d.names, d.name_off, d.size
+    else:
+        sel = np.asarray(sel, dtype=np.int64)
+        names = b"".join(d.name_bytes(i) for i in sel.tolist())
+        name_off = np.zeros(len(sel) + 1, dtype=np.uint64)
+        np.cumsum((d.name_off[1:] - d.name_off[:-1])[sel], out=name_off[1:])
+        sizes = d.size[sel]
+    k = len(sizes)
+    off = np.zeros(k + 1, dtype=np.uint64)
+    np.cumsum(sizes, out=off[1:])
+    raw = np.empty(max(1, int(off[k])), dtype=np.uint8)
+    got = np.zeros(max(1, k), dtype=np.uint64)
+    err = np.zeros(max(1, k), dtype=np.int32)
+    nbuf = np.frombuffer(names, dtype=np.uint8) if names else np.zeros(1, dtype=np.uint8)
+    _abi.check(_abi.lib().fei_read_files(os.fsencode(path), _abi.ptr(nbuf), _abi.ptr(np.ascontiguousarray(name_off)), k, _abi.ptr(raw), _abi.ptr(off),
+                                        READ_THREADS, _abi.ptr(got), _abi.ptr(err)))
+    problems: List[Tuple[int, str]] = []
+    short = np.nonzero((err[:k] != 0) | (got[:k] != sizes))[0]
+    if len(short):                                                    # shrunk, grew or vanished between stat and read: read those again, one by one
+        parts = [raw[int(off[i]):int(off[i + 1])].tobytes() for i in range(k)]
+        for i in short.tolist():
+            name = os.fsdecode(names[int(name_off[i]):int(name_off[i + 1])])
+            try:
+                with open(os.path.join(path, name), "rb") as f:
+                    parts[i] = f.read()
+            except OSError as e:
+                parts[i] = b""
+                problems.append((i, f"Error processing {name}: {e}"))
+        off = np.zeros(k + 1, dtype=np.uint64)
+        np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=k), out=off[1:])
+        raw = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if off[k] else np.zeros(1, dtype=np.uint8)
+    return raw, off, problems
+
+
+# ----------------------------------------------------------------------------- change notification
+class _Watcher:
+    """inotify on every cur/new/tmp directory: a directory is dirty when something was created, deleted, renamed, or WRITTEN in
+    place in it (the reference rewrites memory files in place, folders.py:575, archiver.py:591; a directory's mtime does not see
+    that).  Without inotify the packer falls back to directory mtimes plus a periodic native re-listing (FEI_REVALIDATE_S)."""
+    _MASK = 0x2 | 0x4 | 0x8 | 0x40 | 0x80 | 0x100 | 0x200 | 0x400 | 0x800       # MODIFY ATTRIB CLOSE_WRITE MOVED_FROM MOVED_TO CREATE DELETE DELETE_SELF MOVE_SELF
+    _Q_OVERFLOW, _IGNORED = 0x4000, 0x8000
+
+    def __init__(self):
+        self.fd = -1
+        self.wd_of: Dict[str, int] = {}
+        self.path_of: Dict[int, str] = {}
+        if os.environ.get("FEI_INOTIFY", "1") == "0":
+            return
+        try:
+            self.libc = C.CDLL(None, use_errno=True)
+            fd = self.libc.inotify_init1(0o4000 | 0o2000000)           # IN_NONBLOCK | IN_CLOEXEC
+            if fd >= 0:
+                self.fd = fd
+        except Exception:
+            self.fd = -1
+
+    @property
+    def ok(self) -> bool:
+        return self.fd >= 0
+
+    def watch(self, path: str) -> bool:
+        if not self.ok:
+            return False
+        if path in self.wd_of:
+            return True
+        wd = self.libc.inotify_add_watch(self.fd, os.fsencode(path), self._MASK)
+        if wd < 0:
+            return False
+        self.wd_of[path] = wd
+        self.path_of[wd] = path
+        return True
+
+    def drain(self) -> Optional[set]:
+        """Paths with events since the last call; None = 'everything may have changed' (queue overflow / no inotify)."""
+        if not self.ok:
+            return None
+        dirty = set()
+        while True:
+            try:
+                buf = os.read(self.fd, 1 << 16)
+            except BlockingIOError:
+                break
+            except OSError:
+                return None
+            if not buf:
+                break
+            o = 0
+            while o + 16 <= len(buf):
+                wd, mask, _cookie, ln = struct.unpack_from("iIII", buf, o)
+                o += 16 + ln
+                if mask & self._Q_OVERFLOW:
+                    return None
+                p = self.path_of.get(wd)
+                if p is not None:
+                    dirty.add(p)
+                    if mask & self._IGNORED:                           # the directory itself went away
+                        self.wd_of.pop(p, None); self.path_of.pop(wd, None)
+        return dirty
+
+    def close(self) -> None:
+        if self.fd >= 0:
+            os.close(self.fd)
+            self.fd = -1
+
+
+# ----------------------------------------------------------------------------- packed tree
+class _Seg:
+    """Cached state of one (folder, status) directory: its listing + the device record id of every entry."""
+    __slots__ = ("listing", "dev", "mtime_ns", "bad")
+
+
+def _headers_of(text: str) -> Dict[str, str]:
+    headers: Dict[str, str] = {}
+    for line in text.strip().split("\n"):
+        k, colon, v = line.partition(":")
+        if colon:
+            headers[k.strip()] = v.strip()
+    return headers
+
+
+def _decode_error(data: bytes) -> str:
+    try:
+        data.decode("utf-8")
+        return "invalid UTF-8"
+    except UnicodeDecodeError as e:
+        return str(e)
+
+
+class PackedMemdir:
+    """Host bookkeeping for one packed tree: listing order as arrays + the device corpora (base + delta)."""
+
+    def __init__(self, base: str):
+        self.base = base
+        self.lock = threading.RLock()                        # one request at a time syncs / plans aux columns / scans this tree
+        self.folders: List[str] = []
+        self.folder_ids: Dict[str, int] = {}
+        self.segs: Dict[Tuple[str, str], _Seg] = {}
+        self.segments: Dict[Tuple[str, str], Tuple[int, int]] = {}       # (folder, status) -> listing positions [a, b)
+        self.corpus = None                                   # base corpus (device ids 0 .. n_base)
+        self.delta = None                                    # delta corpus (device ids n_base ..)
+        self.n_base = 0
+        self.n_delta = 0
+        self.delta_raw: List[bytes] = []                     # contents of the delta's records (small): the delta is re-packed as a whole
+        self.n = 0                                           # listed records
+        self.identity = True                                 # device id == listing position (fresh base, no delta, no tombstones)
+        self.dev = np.zeros(0, dtype=np.int64)               # listing position -> device record id
+        self.pos_of_dev = np.zeros(0, dtype=np.int64)        # device record id -> listing position (-1: tombstone)
+        self.arrays: Dict[str, np.ndarray] = {}              # listing-order meta columns: ts, wall, flags8, fsb, rec_bits
+        self.files_read = 0                                  # files whose content was read from disk by the last sync
+        self.windows_packed = 0                              # 4096-record windows (re)tiled by the last sync
+        self.full_packs = 0
+        self.snapshot_gbs: Optional[float] = None
+        self.watcher = _Watcher()
+        self.last_full_check = 0.0
+        self._field_values: Dict[str, Tuple[np.ndarray, np.ndarray, List[str]]] = {}
+        self.parsed_dates: Dict[str, Tuple[Any, bool]] = {}
+        self._aux_next = 0
+        self._seg_index: Optional[Tuple[List[Tuple[str, str]], np.ndarray]] = None
+
+    # ---- tree walk
+    def _walk(self) -> List[str]:
+        out = []
+        for root, dirs, _ in os.walk(self.base):
+            if any(st in dirs for st in U.STANDARD_FOLDERS):
+                rel = os.path.relpath(root, self.base)
+                out.append("" if rel == "." else rel)
+        if len(out) > 65535:
+            raise NotImplementedError("more than 65535 folders")
+        return out
+
+    def _dir(self, folder: str, st: str) -> str:
+        return os.path.join(self.base, folder, st) if folder else os.path.join(self.base, st)
+
+    def _order(self) -> List[Tuple[str, str]]:
+        return [(f, st) for f in self.folders for st in U.STANDARD_FOLDERS]
+
+    # ---- sync
+    def sync(self) -> "PackedMemdir":
+        """Bring the packed corpus up to date with the tree.  Cheap when nothing changed: one os.walk over the folder tree, one
+        stat per cur/new/tmp directory and a drain of the inotify queue."""
+        with self.lock:
+            folders = self._walk()
+            dirty_paths = self.watcher.drain()
+            now = time.monotonic()
+            recheck = float(os.environ.get("FEI_REVALIDATE_S", "1.0"))
+            full_check = self.corpus is None or folders != self.folders or (dirty_paths is None and now - self.last_full_check >= recheck)
+            changed: List[Tuple[str, str]] = []
+            for folder in folders:
+                for st in U.STANDARD_FOLDERS:
+                    path = self._dir(folder, st)
+                    seg = self.segs.get((folder, st))
+                    isdir = os.path.isdir(path)
+                    watched = self.watcher.watch(path) if isdir else True
+                    try:
+                        mt = os.stat(path).st_mtime_ns
+                    except OSError:
+                        mt = -1
+                    if (seg is None or seg.mtime_ns != mt or full_check or (dirty_paths is not None and path in dirty_paths)
+                            or (isdir and not watched and now - self.last_full_check >= recheck)):
+                        changed.append((folder, st))
+            if full_check or changed:
+                self.last_full_check = now
+            if self.corpus is None or folders != self.folders:
+                self._full_pack(folders)
+            elif changed:
+                self._incremental(changed)
+            return self
+
+    def _list(self, folder: str, st: str) -> Tuple[DirListing, int]:
+        path = self._dir(folder, st)
+        try:
+            mt = os.stat(path).st_mtime_ns
+        except OSError:
+            mt = -1
+        return list_dir(path), mt
+
+    def _fsb_of(self, key: Tuple[str, str]) -> int:
+        return (self.folder_ids[key[0]] & 0xFFFF) | (U.STANDARD_FOLDERS.index(key[1]) << 16)
+
+    def _full_pack(self, folders: List[str]) -> None:
+        from .corpus import Corpus
+        self.folders = folders
+        self.folder_ids = {f: i for i, f in enumerate(folders)}
+        order = self._order()
+        segs: Dict[Tuple[str, str], _Seg] = {}
+        raws: List[np.ndarray] = []
+        sizes: List[np.ndarray] = []
+        files = total = 0
+        for key in order:
+            listing, mt = self._list(*key)
+            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.dev = np.zeros(listing.n, dtype=np.int64)
+            segs[key] = seg
+            if listing.n:
+                raw, off, problems = read_files(self._dir(*key), listing)
+                seg.bad.extend(msg for _i, msg in problems)
+                raws.append(raw[:int(off[-1])]); sizes.append((off[1:] - off[:-1]).astype(np.int64)); files += listing.n
+                total += int(off[-1])
+                if total > MAX_RAW_BATCH:
+                    raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
+        self.files_read = files
+        n = files
+        raw = np.concatenate(raws) if raws else np.zeros(1, dtype=np.uint8)
+        raw_off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            np.cumsum(np.concatenate(sizes), out=raw_off[1:])
+        corpus = Corpus()
+        keep = np.ones(n, dtype=bool)
+        while True:
+            arrays = self._raw_arrays(segs, order, keep, raw, raw_off)
+            valid = corpus.load_raw(arrays)
+            if valid.all():
+                break
+            alive = np.nonzero(keep)[0]
+            for j in alive[~valid].tolist():                           # undecodable files: reported and skipped (utils.py:247-248)
+                keep[j] = False
+                key, i = self._locate(segs, order, j)
+                segs[key].bad.append(f"Error processing {segs[key].listing.name(i)}: {_decode_error(raw[int(raw_off[j]):int(raw_off[j + 1])].tobytes())}")
+        pos = start = 0
+        for key in order:                                              # drop the skipped entries from the listings; device id = listing position
+            seg = segs[key]
+            k = seg.listing.n
+            sel = keep[start:start + k]
+            if not sel.all():
+                seg.listing = _subset(seg.listing, np.nonzero(sel)[0])
+            seg.dev = np.arange(pos, pos + seg.listing.n, dtype=np.int64)
+            pos += seg.listing.n
+            start += k
+        old, old_delta = self.corpus, self.delta
+        self.segs = segs
+        self.corpus, self.delta, self.n_base, self.n_delta = corpus, None, corpus.n, 0
+        self.delta_raw = []
+        self.windows_packed = (corpus.n + 4095) // 4096
+        self.full_packs += 1
+        self._rebuild_listing()
+        for c in (old, old_delta):
+            if c is not None:
+                c.close()
+
+    @staticmethod
+    def _locate(segs, order, j):
+        for key in order:
+            k = segs[key].listing.n
+            if j < k:
+                return key, j
+            j -= k
+        raise IndexError(j)
+
+    def _raw_arrays(self, segs, order, keep, raw, raw_off) -> Dict[str, Any]:
+        cols: Dict[str, List[np.ndarray]] = {k: [] for k in ("ts", "wall", "flags8", "spans", "fsb")}
+        names, lens = [], []
+        for key in order:
+            L = segs[key].listing
+            if not L.n:
+                continue
+            cols["ts"].append(L.ts); cols["wall"].append(L.wall); cols["flags8"].append(L.flags8); cols["spans"].append(L.spans)
+            cols["fsb"].append(np.full(L.n, self._fsb_of(key), dtype=np.uint32))
+            names.append(L.names); lens.append((L.name_off[1:] - L.name_off[:-1]).astype(np.int64))
+        n_all = len(keep)
+        cat = lambda k, dt: (np.concatenate(cols[k]) if cols[k] else np.zeros(0, dtype=dt))
+        ts, wall, f8, fsb = cat("ts", np.int64), cat("wall", np.int64), cat("flags8", np.uint64), cat("fsb", np.uint32)
+        spans = np.concatenate(cols["spans"]) if cols["spans"] else np.zeros((0, 4), dtype=np.uint16)
+        nlen = np.concatenate(lens) if lens else np.zeros(0, dtype=np.int64)
+        nblob = b"".join(names)
+        if keep.all():
+            sel_raw, sel_off = raw, raw_off
+            name = np.frombuffer(nblob, dtype=np.uint8).copy() if nblob else np.zeros(1, dtype=np.uint8)
+            name_off = np.zeros(n_all + 1, dtype=np.uint64); np.cumsum(nlen, out=name_off[1:])
+        else:
+            idx = np.nonzero(keep)[0]
+            noff = np.zeros(n_all + 1, dtype=np.int64); np.cumsum(nlen, out=noff[1:])
+            parts = [raw[int(raw_off[j]):int(raw_off[j + 1])].tobytes() for j in idx.tolist()]
+            sel_off = np.zeros(len(idx) + 1, dtype=np.uint64); np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=len(idx)), out=sel_off[1:])
+            sel_raw = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if sel_off[-1] else np.zeros(1, dtype=np.uint8)
+            nm = b"".join(nblob[int(noff[j]):int(noff[j + 1])] for j in idx.tolist())
+            name = np.frombuffer(nm, dtype=np.uint8).copy() if nm else np.zeros(1, dtype=np.uint8)
+            name_off = np.zeros(len(idx) + 1, dtype=np.uint64); np.cumsum(nlen[idx], out=name_off[1:])
+            ts, wall, f8, fsb, spans = ts[idx], wall[idx], f8[idx], fsb[idx], spans[idx]
+        n = len(ts)
+        return {"n": n, "global_base": 0, "raw": sel_raw, "raw_off": np.ascontiguousarray(sel_off), "name": name if n else None,
+                "name_off": name_off if n else None, "name_spans": np.ascontiguousarray(spans.reshape(-1)) if n else None,
+                "ts": np.ascontiguousarray(ts), "wall": np.ascontiguousarray(wall), "flags8": np.ascontiguousarray(f8), "fsb": np.ascontiguousarray(fsb)}
+
+    # ---- incremental
+    def _incremental(self, changed: List[Tuple[str, str]]) -> None:
+        """Re-list the changed directories, diff them against their cached listings, and apply the difference to the device."""
+        fresh: Dict[Tuple[str, str], _Seg] = {}
+        rem_dev: List[int] = []
+        rem_key: List[Tuple[int, int, int]] = []
+        new_entries: List[Tuple[Tuple[str, str], np.ndarray]] = []
+        any_change = False
+        for key in changed:
+            old = self.segs.get(key)
+            listing, mt = self._list(*key)
+            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.dev = np.full(listing.n, -1, dtype=np.int64)
+            fresh[key] = seg
+            if old is not None and old.listing.n:
+                old_names = {old.listing.name_bytes(i): i for i in range(old.listing.n)}
+                ok_, nk_ = old.listing.key(), listing.key()
+                used = np.zeros(old.listing.n, dtype=bool)
+                for i in range(listing.n):                             # same name + same (inode, size, mtime) = same packed record
+                    j = old_names.get(listing.name_bytes(i))
+                    if j is not None and ok_[j] == nk_[i]:
+                        seg.dev[i] = old.dev[j]; used[j] = True
+                for j in np.nonzero(~used)[0].tolist():
+                    rem_dev.append(int(old.dev[j])); rem_key.append((int(ok_[j]["ino"]), int(ok_[j]["size"]), int(ok_[j]["mtime"])))
+                if old.bad:                                            # undecodable files that did not change stay reported without being read again
+                    seg.bad.extend(m for m in old.bad if m not in seg.bad and self._bad_still_there(key, m, listing))
+                if not used.all() or (seg.dev < 0).any() or not np.array_equal(old.dev, seg.dev):
+                    any_change = True
+            elif listing.n:
+                any_change = True
+            todo = np.nonzero(seg.dev < 0)[0]
+            if len(todo):
+                new_entries.append((key, todo))
+        if not any_change:                                             # only directory timestamps moved
+            for key, seg in fresh.items():
+                self.segs[key].mtime_ns = seg.mtime_ns
+            self.files_read = 0
+            self.windows_packed = 0
+            return
+        # renames: a new entry whose (inode, size, mtime) equals a removed record's is that record under a new name (move_memory /
+        # update_memory_flags, utils.py:255-297, :354-388): its packed text is taken from the device, the file is not read
+        rem_map = {k: d for k, d in zip(rem_key, rem_dev) if d >= 0}
+        moved_from: List[int] = []
+        moved_to: List[Tuple[Tuple[str, str], int]] = []
+        to_read: List[Tuple[Tuple[str, str], np.ndarray]] = []
+        known_bad = {m for seg in fresh.values() for m in seg.bad}
+        for key, todo in new_entries:
+            L = fresh[key].listing
+            nk_ = L.key()
+            still = []
+            for i in todo.tolist():
+                d = rem_map.pop((int(nk_[i]["ino"]), int(nk_[i]["size"]), int(nk_[i]["mtime"])), None)
+                if d is not None:
+                    moved_from.append(d); moved_to.append((key, i))
+                elif any(m.startswith(f"Error processing {L.name(i)}: ") for m in known_bad):
+                    fresh[key].dev[i] = -2                             # a file already known to be undecodable, unchanged
+                else:
+                    still.append(i)
+            if still:
+                to_read.append((key, np.array(still, dtype=np.int64)))
+        # contents of the delta after this sync: surviving delta records + moved records + newly read files
+        seg_of = lambda key: fresh.get(key) or self.segs[key]
+        raws: List[bytes] = []
+        metas: List[Tuple] = []
+        place: List[Tuple[Tuple[str, str], int]] = []                  # where each delta record is listed
+        for key in self._order():
+            seg = fresh.get(key) or self.segs.get(key)
+            if seg is None:
+                continue
+            for i in np.nonzero(seg.dev >= self.n_base)[0].tolist():   # records already in the delta keep their text
+                raws.append(self.delta_raw[int(seg.dev[i]) - self.n_base]); metas.append(self._meta_of(seg.listing, i, key)); place.append((key, i))
+        if moved_from:
+            for (key, i), text in zip(moved_to, self._device_texts(np.array(moved_from, dtype=np.int64))):
+                raws.append(text); metas.append(self._meta_of(fresh[key].listing, i, key)); place.append((key, i))
+        files = 0
+        for key, sel in to_read:
+            L = fresh[key].listing
+            raw, off, problems = read_files(self._dir(*key), L, sel)
+            bad_k = {k for k, _m in problems}
+            fresh[key].bad.extend(m for _k, m in problems)
+            for k, i in enumerate(sel.tolist()):
+                if k in bad_k:
+                    fresh[key].dev[i] = -2
+                    continue
+                raws.append(raw[int(off[k]):int(off[k + 1])].tobytes()); metas.append(self._meta_of(L, i, key)); place.append((key, i))
+                files += 1
+        self.files_read = files
+        delta, keep = self._pack_delta(raws, metas)                    # validates the new files; undecodable ones are reported and dropped
+        kept = []
+        for j, ok in enumerate(keep):
+            key, i = place[j]
+            seg = seg_of(key)
+            if ok:
+                seg.dev[i] = self.n_base + len(kept)
+                kept.append(j)
+            else:
+                seg.bad.append(f"Error processing {seg.listing.name(i)}: {_decode_error(raws[j])}")
+                seg.dev[i] = -2
+        for key in self._order():                                      # entries that could not be packed leave the listing
+            seg = fresh.get(key) or self.segs.get(key)
+            if seg is not None and (seg.dev < 0).any():
+                sel = np.nonzero(seg.dev >= 0)[0]
+                seg.listing = _subset(seg.listing, sel); seg.dev = seg.dev[sel]
+            if key in fresh:
+                self.segs[key] = fresh[key]
+        old_delta = self.delta
+        self.delta, self.n_delta = delta, (delta.n if delta is not None else 0)
+        self.delta_raw = [raws[j] for j in kept]
+        self.windows_packed = (self.n_delta + 4095) // 4096
+        if old_delta is not None:
+            old_delta.close()
+        self._rebuild_listing()
+        n_dead = self.n_base - int((self.dev < self.n_base).sum())
+        if self.n_delta > max(8192, self.n_base // 16) or n_dead > max(8192, self.n_base // 4):
+            self._full_pack(self.folders)                              # the delta / the tombstones outgrew their welcome: repack
+
+    def _bad_still_there(self, key, msg: str, listing: DirListing) -> bool:
+        m = re.match(r"Error processing (.*?): ", msg)
+        return bool(m) and os.path.exists(os.path.join(self._dir(*key), m.group(1)))
+
+    def _meta_of(self, L: DirListing, i: int, key) -> Tuple:
+        return (L.name_bytes(i), int(L.ts[i]), int(L.wall[i]), int(L.flags8[i]), tuple(int(x) for x in L.spans[i]), self._fsb_of(key))
+
+    def _device_texts(self, dev: np.ndarray) -> List[bytes]:
+        """The packed text of device records as file contents that pack to the same record again (header + '---' + body)."""
+        out: List[bytes] = [b""] * len(dev)
+        for corpus, lo in self._corpora():
+            sel = np.nonzero((dev >= lo) & (dev < lo + corpus.n))[0]
+            if not len(sel):
+                continue
+            hdr, ho, body, bo = corpus.fetch_records(dev[sel] - lo)
+            bits = corpus.fetch_meta()["fsb"] >> 24
+            for k, j in enumerate(sel.tolist()):
+                h, b = hdr[int(ho[k]):int(ho[k + 1])], body[int(bo[k]):int(bo[k + 1])]
+                out[j] = b if int(bits[int(dev[j]) - lo]) & REC_NO_SEPARATOR else h + b"---" + b
+        return out
+
+    def _pack_delta(self, raws: List[bytes], metas: List[Tuple]):
+        from .corpus import Corpus
+        keep = [True] * len(raws)
+        delta = None
+        while any(keep):
+            idx = [j for j, k in enumerate(keep) if k]
+            off = np.zeros(len(idx) + 1, dtype=np.uint64)
+            np.cumsum([len(raws[j]) for j in idx], out=off[1:])
+            raw = np.frombuffer(b"".join(raws[j] for j in idx), dtype=np.uint8).copy() if off[-1] else np.zeros(1, dtype=np.uint8)
+            names = [metas[j][0] for j in idx]
+            name_off = np.zeros(len(idx) + 1, dtype=np.uint64); np.cumsum([len(x) for x in names], out=name_off[1:])
+            arrays = {"n": len(idx), "global_base": 0, "raw": raw, "raw_off": off,
+                      "name": np.frombuffer(b"".join(names), dtype=np.uint8).copy(), "name_off": name_off,
+                      "name_spans": np.array([metas[j][4] for j in idx], dtype=np.uint16).reshape(-1),
+                      "ts": np.array([metas[j][1] for j in idx], dtype=np.int64), "wall": np.array([metas[j][2] for j in idx], dtype=np.int64),
+                      "flags8": np.array([metas[j][3] for j in idx], dtype=np.uint64), "fsb": np.array([metas[j][5] for j in idx], dtype=np.uint32)}
+            if delta is None:
+                delta = Corpus()
+            valid = delta.load_raw(arrays)
+            if valid.all():
+                return delta, keep
+            for j, ok in zip(idx, valid.tolist()):
+                if not ok:
+                    keep[j] = False
+        if delta is not None:
+            delta.close()
+        return None, keep
+
+    # ---- listing order
+    def _rebuild_listing(self) -> None:
+        self.segments = {}
+        pos = 0
+        devs: List[np.ndarray] = []
+        cols: Dict[str, List[np.ndarray]] = {k: [] for k in ("ts", "wall", "flags8", "fsb")}
+        for key in self._order():
+            seg = self.segs[key]
+            k = seg.listing.n
+            self.segments[key] = (pos, pos + k)
+            pos += k
+            if k:
+                devs.append(seg.dev)
+                cols["ts"].append(seg.listing.ts); cols["wall"].append(seg.listing.wall); cols["flags8"].append(seg.listing.flags8)
+                cols["fsb"].append(np.full(k, self._fsb_of(key), dtype=np.uint32))
+        self.n = pos
+        self.dev = np.concatenate(devs) if devs else np.zeros(0, dtype=np.int64)
+        self.pos_of_dev = np.full(self.n_base + self.n_delta, -1, dtype=np.int64)
+        self.pos_of_dev[self.dev] = np.arange(self.n, dtype=np.int64)
+        self.identity = self.n == self.n_base and self.n_delta == 0 and bool((self.dev == np.arange(self.n)).all())
+        dts = {"ts": np.int64, "wall": np.int64, "flags8": np.uint64, "fsb": np.uint32}
+        self.arrays = {k: (np.concatenate(v) if v else np.zeros(0, dtype=dts[k])) for k, v in cols.items()}
+        bits = np.zeros(self.n_base + self.n_delta, dtype=np.uint8)
+        for corpus, lo in self._corpora():
+            if corpus.n:
+                bits[lo:lo + corpus.n] = (corpus.fetch_meta()["fsb"] >> 24).astype(np.uint8)
+        self.arrays["rec_bits"] = bits[self.dev] if self.n else np.zeros(0, dtype=np.uint8)
+        if self.n:
+            self.arrays["fsb"] = self.arrays["fsb"] | (self.arrays["rec_bits"].astype(np.uint32) << 24)
+        self._field_values = {}
+        self._seg_index = None
+
+    @property
+    def bad(self) -> Dict[Tuple[str, str], List[str]]:
+        return {k: s.bad for k, s in self.segs.items() if s.bad}
+
+    # ---- scanning in listing order
+    def _corpora(self):
+        out = []
+        if self.corpus is not None:
+            out.append((self.corpus, 0))
+        if self.delta is not None and self.delta.n:
+            out.append((self.delta, self.n_base))
+        return out
+
+    def scan_hits(self, prog: bytes, nq: int) -> List[np.ndarray]:
+        """Per query, the listing positions of the hits, ascending (= the reference's result order inside the tree)."""
+        per: List[List[np.ndarray]] = [[] for _ in range(nq)]
+        for corpus, lo in self._corpora():
+            for q, h in enumerate(corpus.scan_hits(prog, nq)):
+                per[q].append(h.astype(np.int64) + lo)
+        out = []
+        for q in range(nq):
+            ids = np.concatenate(per[q]) if per[q] else np.zeros(0, dtype=np.int64)
+            if not self.identity:
+                ids = self.pos_of_dev[ids]
+                ids = ids[ids >= 0]
+                ids.sort()
+            out.append(ids)
+        return out
+
+    def scan_masks(self, prog: bytes) -> np.ndarray:
+        """mask[p] bit q = the record at listing position p satisfies query q."""
+        if self.identity:
+            return self.corpus.scan_masks(prog)
+        dev_masks = np.zeros(self.n_base + self.n_delta, dtype=np.uint32)
+        for corpus, lo in self._corpora():
+            dev_masks[lo:lo + corpus.n] = corpus.scan_masks(prog)
+        return dev_masks[self.dev]
+
+    def compact(self) -> None:
+        """Fold delta and tombstones back into one base corpus in listing order (whole-corpus passes such as the tag statistics want that)."""
+        if not self.identity:
+            self._full_pack(self.folders)
+
+    def _segment_index(self):
+        if self._seg_index is None:
+            keys = [k for k in self._order() if self.segments[k][1] > self.segments[k][0]]
+            self._seg_index = (keys, np.array([self.segments[k][0] for k in keys], dtype=np.int64))
+        return self._seg_index
+
+    def materialize(self, positions: Sequence[int], include_content: bool) -> List[Dict[str, Any]]:
+        """The dicts list_memories yields (utils.py:234-243) for these listing positions; header text and body come from the device."""
+        positions = np.asarray(positions, dtype=np.int64)
+        m = len(positions)
+        if m == 0:
+            return []
+        dev = self.dev[positions]
+        hdr_text: List[str] = [""] * m
+        body_text: List[str] = [""] * m
+        for corpus, lo in self._corpora():
+            sel = np.nonzero((dev >= lo) & (dev < lo + corpus.n))[0]
+            if not len(sel):
+                continue
+            hdr, ho, body, bo = corpus.fetch_records(dev[sel] - lo, want_body=include_content)
+            for k, j in enumerate(sel.tolist()):
+                hdr_text[j] = hdr[int(ho[k]):int(ho[k + 1])].decode("utf-8")
+                if include_content:
+                    body_text[j] = body[int(bo[k]):int(bo[k + 1])].decode("utf-8")
+        keys, starts = self._segment_index()
+        which = np.searchsorted(starts, positions, side="right") - 1
+        out = []
+        for j, p in enumerate(positions.tolist()):
+            key = keys[int(which[j])]
+            L = self.segs[key].listing
+            i = p - self.segments[key][0]
+            nb = L.name_bytes(i)
+            sp = L.spans[i]
+            flags = int(L.flags8[i])
+            mem = {"filename": os.fsdecode(nb), "folder": key[0], "status": key[1], "headers": _headers_of(hdr_text[j]),
+                   "metadata": {"timestamp": int(L.ts[i]), "unique_id": os.fsdecode(nb[int(sp[0]):int(sp[0]) + int(sp[1])]),
+                                "hostname": os.fsdecode(nb[int(sp[2]):int(sp[2]) + int(sp[3])]),
+                                "flags": [chr((flags >> (8 * k)) & 0xFF) for k in range(flags >> 56)], "date": datetime.fromtimestamp(int(L.ts[i]))}}
+            if include_content:
+                mem["content"] = body_text[j]
+            out.append(mem)
+        return out
+
+    # ---- per-record header values for conditions only Python can judge (search.py:126-130)
+    def header_values(self, field: str) -> Tuple[np.ndarray, np.ndarray, List[str]]:
+        """(present[n], inv[n], distinct), listing order: the value _get_field_value would read for `field` (first key whose lower()
+        equals field.lower(), last line of that exact key) as an index into the list of distinct values (len(distinct) = absent)."""
+        key = field.lower()
+        got = self._field_values.get(key)
+        if got is None:
+            from .program import C_SLOT, Cond, ProgramBuilder
+            from .regexc import Pattern
+            pb = ProgramBuilder()
+            pb.add_query([Cond(C_SLOT, pattern=Pattern("regex", "", re.IGNORECASE), field=field, mode=0)])
+            prog = pb.build()
+            index: Dict[bytes, int] = {}
+            inv_dev = np.full(self.n_base + self.n_delta, -1, dtype=np.int64)
+            for corpus, lo in self._corpora():
+                present, off, blob = corpus.slot_values(prog)
+                raw = blob.tobytes()
+                o = off.astype(np.int64)
+                for i in np.nonzero(present)[0].tolist():
+                    inv_dev[lo + i] = index.setdefault(raw[o[i]:o[i + 1]], len(index))
+            distinct = [b.decode("utf-8") for b in index]
+            inv = inv_dev[self.dev] if self.n else np.zeros(0, dtype=np.int64)
+            present = inv >= 0
+            inv = np.where(present, inv, len(distinct))
+            got = self._field_values[key] = (present, inv, distinct)
+        return got
+
+    def begin_query(self) -> None:
+        self._aux_next = 0
+
+    def new_aux(self, verdicts: np.ndarray) -> int:
+        """Uploads one per-record verdict column (listing order) for the query being compiled; returns its index (C_RECBITS.which)."""
+        from .program import MAX_AUX
+        if self._aux_next >= MAX_AUX:
+            raise NotImplementedError(f"more than {MAX_AUX} host-judged header conditions in one query")
+        k = self._aux_next
+        self._aux_next += 1
+        dev_v = np.zeros(self.n_base + self.n_delta, dtype=np.uint8)
+        dev_v[self.dev] = np.asarray(verdicts, dtype=np.uint8)
+        for corpus, lo in self._corpora():
+            corpus.set_aux(k, dev_v[lo:lo + corpus.n])
+        return k
+
+    def sigma_in(self, ranges: Sequence[Tuple[int, int]]) -> bool:
+        """Does a record of these listing ranges hold U+03A3 (the one character whose str.lower() the automata do not model)?"""
+        bits = self.arrays.get("rec_bits")
+        if bits is None or not len(bits):
+            return False
+        return any(bool((bits[a:b] & REC_HAS_SIGMA).any()) for a, b in ranges)
+
+    def report_skipped(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> None:
+        """The reference prints `Error processing <file>: <error>` each time a directory is listed (utils.py:247-248)."""
+        for f in (self.folders if folders is None else folders):
+            for st in (U.STANDARD_FOLDERS if statuses is None else statuses):
+                seg = self.segs.get((f, st))
+                if seg is not None:
+                    for msg in seg.bad:
+                        print(msg)
+
+    def ranges(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> List[Tuple[int, int]]:
+        """Listing ranges of the requested (folder, status) pairs in the caller's order (search.py:361-363)."""
+        if folders is None:
+            folders = self.folders
+        if statuses is None:
+            statuses = U.STANDARD_FOLDERS
+        out = []
+        for f in folders:
+            for st in statuses:
+                if st not in U.STANDARD_FOLDERS:
+                    raise ValueError(f"Invalid status: {st}. Must be one of {U.STANDARD_FOLDERS}")
+                r = self.segments.get((f, st))
+                if r and r[1] > r[0]:
+                    out.append(r)
+        return out
+
+    # ---- snapshot
+    def save_snapshot(self, path: str) -> None:
+        """The packed corpus (device buffers) + the listings, so a restart restores instead of re-packing; the next sync() diffs
+        the tree against the restored listings and reads only what changed since."""
+        with self.lock:
+            self.compact()
+            self.corpus.save(path + ".corpus")
+            blob: Dict[str, Any] = {"folders": np.array(self.folders, dtype=object)}
+            for k, key in enumerate(self._order()):
+                seg = self.segs[key]
+                L = seg.listing
+                blob[f"s{k}_names"] = np.frombuffer(L.names, dtype=np.uint8) if L.names else np.zeros(0, dtype=np.uint8)
+                for a in ("name_off", "ts", "wall", "flags8", "spans", "ino", "size", "mtime_ns"):
+                    blob[f"s{k}_{a}"] = getattr(L, a)
+                blob[f"s{k}_mt"] = np.array([seg.mtime_ns], dtype=np.int64)
+                blob[f"s{k}_bad"] = np.array(seg.bad, dtype=object)
+            np.savez(path + ".dirs.npz", **blob)
+
+    @classmethod
+    def from_snapshot(cls, base: str, path: str) -> "PackedMemdir":
+        from .corpus import Corpus
+        z = np.load(path + ".dirs.npz", allow_pickle=True)
+        pm = cls(base)
+        pm.folders = [str(x) for x in z["folders"]]
+        pm.folder_ids = {f: i for i, f in enumerate(pm.folders)}
+        pos = 0
+        for k, key in enumerate(pm._order()):
+            L = DirListing()
+            L.names = z[f"s{k}_names"].tobytes()
+            for a in ("name_off", "ts", "wall", "flags8", "spans", "ino", "size", "mtime_ns"):
+                setattr(L, a, z[f"s{k}_{a}"])
+            L.n = len(L.ts); L.bad = []
+            seg = _Seg(); seg.listing = L; seg.dev = np.arange(pos, pos + L.n, dtype=np.int64); seg.mtime_ns = -2; seg.bad = [str(x) for x in z[f"s{k}_bad"]]
+            pos += L.n
+            pm.segs[key] = seg
+        pm.corpus = Corpus()
+        pm.snapshot_gbs = pm.corpus.load_snapshot(path + ".corpus")
+        pm.n_base = pm.corpus.n
+        pm._rebuild_listing()
+        return pm
+
+    def close(self) -> None:
+        with self.lock:
+            for c in (self.corpus, self.delta):
+                if c is not None:
+                    c.close()
+            self.corpus = self.delta = None
+            self.watcher.close()
+
+
+def _subset(L: DirListing, sel: np.ndarray) -> DirListing:
+    d = DirListing()
+    d.names = b"".join(L.name_bytes(i) for i in sel.tolist())
+    d.name_off = np.zeros(len(sel) + 1, dtype=np.uint64)
+    np.cumsum((L.name_off[1:] - L.name_off[:-1])[sel], out=d.name_off[1:])
+    for k in ("ts", "wall", "flags8", "spans", "ino", "size", "mtime_ns"):
+        setattr(d, k, getattr(L, k)[sel])
+    d.n = len(sel)
+    d.bad = L.bad
+    return d
+
+
+# ----------------------------------------------------------------------------- host-side listing of one directory (no GPU)
 def read_segment(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
+    """utils.list_memories for callers that want plain dicts of one directory (host only: the reference-shaped helper, and the
+    one-record corpora of MemoryFilter.matches)."""
     path = os.path.join(base, folder, status) if folder else os.path.join(base, status)
     if not os.path.exists(path):
         return []
@@ -41,98 +901,29 @@ def read_segment(base: str, folder: str, status: str) -> List[Dict[str, Any]]:
                 text = f.read()
             head, sep, rest = text.partition("---")
             ts = int(m.group(1))
-            out.append({
-                "filename": name, "folder": folder, "status": status, "ts": ts,
-                "uid": m.group(2), "host": m.group(3), "flags": m.group(4),
-                "uid_span": (m.start(2), m.end(2)), "host_span": (m.start(3), m.end(3)),
-                "hdr_text": head if sep else "", "body_text": (rest if sep else text).strip(), "has_sep": bool(sep),
-                "date": datetime.fromtimestamp(ts),
-            })
+            out.append({"filename": name, "folder": folder, "status": status, "ts": ts, "uid": m.group(2), "host": m.group(3), "flags": m.group(4),
+                        "uid_span": (m.start(2), m.end(2)), "host_span": (m.start(3), m.end(3)),
+                        "hdr_text": head if sep else "", "body_text": (rest if sep else text).strip(), "has_sep": bool(sep),
+                        "date": datetime.fromtimestamp(ts)})
         except Exception as e:
             print(f"Error processing {name}: {e}")
     out.sort(key=lambda r: r["ts"], reverse=True)
     return out
-
-
-def read_segment_raw(base: str, folder: str, status: str, file_cache: Optional[Dict[Tuple, bytes]] = None) -> List[Dict[str, Any]]:
-    """Like read_segment but leaves the file *text* work (decode, newline folding, '---' split, strip) to the
-    GPU ingest kernels (fei_corpus_load_raw): files are read as bytes; only the file-name grammar and the
-    listing order are handled here.  `file_cache` maps (inode, size, mtime_ns) to content: a memory file is
-    immutable, and moves / flag changes are renames (utils.py:255-297, :354-388), so an incremental re-pack
-    re-reads only files it has never seen."""
-    path = os.path.join(base, folder, status) if folder else os.path.join(base, status)
-    if not os.path.exists(path):
-        return []
-    out = []
-    for name in os.listdir(path):
-        try:
-            if not _LIST_RE.match(name):
-                continue
-            m = U.FILENAME_RE.match(name)
-            if not m:
-                raise ValueError(f"Invalid memory filename: {name}")
-            full = os.path.join(path, name)
-            raw = None
-            if file_cache is not None:
-                st = os.stat(full)
-                key = (st.st_ino, st.st_size, st.st_mtime_ns)
-                raw = file_cache.get(key)
-            if raw is None:
-                with open(full, "rb") as f:
-                    raw = f.read()
-                if file_cache is not None:
-                    file_cache[key] = raw
-            ts = int(m.group(1))
-            out.append({"filename": name, "folder": folder, "status": status, "ts": ts, "uid": m.group(2), "host": m.group(3),
-                        "flags": m.group(4), "uid_span": (m.start(2), m.end(2)), "host_span": (m.start(3), m.end(3)),
-                        "raw": raw, "date": datetime.fromtimestamp(ts)})
-        except Exception as e:
-            print(f"Error processing {name}: {e}")
-    out.sort(key=lambda r: r["ts"], reverse=True)
-    return out
-
-
-def _ensure_text(rec: Dict[str, Any]) -> None:
-    """Host-side text of one record (hits only): what open(path, "r").read() + parse_memory_content see."""
-    if "hdr_text" in rec:
-        return
-    text = rec["raw"].decode("utf-8").replace("\r\n", "\n").replace("\r", "\n")
-    head, sep, rest = text.partition("---")
-    rec["hdr_text"] = head if sep else ""
-    rec["body_text"] = (rest if sep else text).strip()
-    rec["has_sep"] = bool(sep)
 
 
 def memory_dict(rec: Dict[str, Any], include_content: bool) -> Dict[str, Any]:
-    """The dict list_memories yields (utils.py:234-243); headers parsed on the host for materialisation."""
-    _ensure_text(rec)
-    headers = rec.get("_headers")                       # parsed once per record; callers get their own copy (they may mutate it)
-    if headers is None:
-        headers = {}
-        if rec["has_sep"]:
-            for line in rec["hdr_text"].strip().split("\n"):
-                k, colon, v = line.partition(":")
-                if colon:
-                    headers[k.strip()] = v.strip()
-        rec["_headers"] = headers
-    mem = {"filename": rec["filename"], "folder": rec["folder"], "status": rec["status"], "headers": dict(headers),
-           "metadata": {"timestamp": rec["ts"], "unique_id": rec["uid"], "hostname": rec["host"], "flags": list(rec["flags"]),
-                        "date": rec["date"]}}
+    """The dict list_memories yields (utils.py:234-243) from a read_segment record."""
+    headers = _headers_of(rec["hdr_text"]) if rec["has_sep"] else {}
+    mem = {"filename": rec["filename"], "folder": rec["folder"], "status": rec["status"], "headers": headers,
+           "metadata": {"timestamp": rec["ts"], "unique_id": rec["uid"], "hostname": rec["host"], "flags": list(rec["flags"]), "date": rec["date"]}}
     if include_content:
         mem["content"] = rec["body_text"]
     return mem
 
 
-def _flags8(flags: str, name: str) -> int:
-    if len(flags) > 7:
-        raise NotImplementedError(f"{name}: more than 7 flag letters are not supported by the packed layout")
-    v = len(flags) << 56
-    for k, ch in enumerate(flags):
-        v |= ord(ch) << (8 * k)
-    return v
-
-
 def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, int], global_base: int = 0) -> Dict[str, Any]:
+    """Canonical host arrays (fei_corpus_load) from read_segment records: the host-text path, used for one-record corpora
+    (MemoryFilter.matches) and tests."""
     n = len(recs)
     hdr_parts = [r["hdr_text"].encode("utf-8") for r in recs]
     body_parts = [r["body_text"].encode("utf-8") for r in recs]
@@ -152,7 +943,6 @@ def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, i
     bits = np.zeros(max(n, 1), dtype=np.uint32)
     for i, r in enumerate(recs):
         fname = r["filename"]
-        # spans are character offsets; convert to byte offsets when the name has non-ASCII characters
         (a0, a1), (b0, b1) = r["uid_span"], r["host_span"]
         if len(name_parts[i]) != len(fname):
             a0, a1, b0, b1 = (len(os.fsencode(fname[:x])) for x in (a0, a1, b0, b1))
@@ -176,245 +966,36 @@ def arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, i
             "rec_bits": bits[:n].astype(np.uint8)}
 
 
-def raw_arrays_from_segments(recs: Sequence[Dict[str, Any]], folder_ids: Dict[str, int], global_base: int = 0) -> Dict[str, Any]:
-    """Host arrays for fei_corpus_load_raw: raw file bytes + meta columns + names (no text processing)."""
-    n = len(recs)
-    name_parts = [os.fsencode(r["filename"]) for r in recs]
-
-    def blob(parts):
-        off = np.zeros(n + 1, dtype=np.uint64)
-        if n:
-            np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=n), out=off[1:])
-        data = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if n and off[n] else np.zeros(1, dtype=np.uint8)
-        return data, off
-
-    raw, raw_off = blob([r["raw"] for r in recs])
-    name, name_off = blob(name_parts)
-    spans = np.zeros((max(n, 1), 4), dtype=np.uint16)
-    for i, r in enumerate(recs):
-        fname = r["filename"]
-        (a0, a1), (b0, b1) = r["uid_span"], r["host_span"]
-        if len(name_parts[i]) != len(fname):
-            a0, a1, b0, b1 = (len(os.fsencode(fname[:x])) for x in (a0, a1, b0, b1))
-        spans[i] = (a0, a1 - a0, b0, b1 - b0)
-    ts = np.array([r["ts"] for r in recs], dtype=np.int64)
-    wall = np.array([calendar.timegm(r["date"].timetuple()) for r in recs], dtype=np.int64)
-    f8 = np.array([_flags8(r["flags"], r["filename"]) for r in recs], dtype=np.uint64)
-    fsb = np.array([(folder_ids[r["folder"]] & 0xFFFF) | (U.STANDARD_FOLDERS.index(r["status"]) << 16) for r in recs], dtype=np.uint32)
-    return {"n": n, "global_base": global_base, "raw": raw, "raw_off": raw_off, "name": name, "name_off": name_off,
-            "name_spans": spans.reshape(-1), "ts": ts, "wall": wall, "flags8": f8, "fsb": fsb}
+def _flags8(flags: str, name: str) -> int:
+    if len(flags) > 7:
+        raise NotImplementedError(f"{name}: more than 7 flag letters are not supported by the packed layout")
+    v = len(flags) << 56
+    for k, ch in enumerate(flags):
+        v |= ord(ch) << (8 * k)
+    return v
 
 
-class PackedMemdir:
-    """Host bookkeeping for one packed tree: records in listing order + the device corpus."""
-
-    def __init__(self, base: str):
-        self.base = base
-        self.folders: List[str] = []
-        self.segments: Dict[Tuple[str, str], Tuple[int, int]] = {}
-        self.recs: List[Dict[str, Any]] = []
-        self.arrays: Dict[str, Any] = {}
-        self.corpus = None
-        self.signature: Tuple = ()
-        self.seg_cache: Dict[Tuple[str, str], Tuple[int, List[Dict[str, Any]]]] = {}   # (folder, status) -> (dir mtime, records)
-        self.file_cache: Dict[Tuple, bytes] = {}
-        self.files_read = 0          # files whose content was read from disk by the last build (incremental-sync telemetry)
-        self.bad: Dict[Tuple[str, str], List[str]] = {}      # undecodable files per directory, reported on every listing
-        self.lock = threading.RLock()                        # one query at a time plans aux columns / scans this corpus state
-        self._field_values: Dict[str, Tuple[np.ndarray, np.ndarray, List[str]]] = {}
-        self.parsed_dates: Dict[str, Tuple[Any, bool]] = {}  # header value -> (dateutil result | None, depends on today's date)
-        self._aux_next = 0
-
-    @staticmethod
-    def tree_signature(base: str) -> Tuple:
-        sig = []
-        for root, dirs, _ in os.walk(base):
-            for st in U.STANDARD_FOLDERS:
-                if st in dirs:
-                    p = os.path.join(root, st)
-                    s = os.stat(p)
-                    sig.append((p, s.st_mtime_ns))
-        return tuple(sig)
-
-    def build(self, upload: bool = True, gpu_text: Optional[bool] = None) -> "PackedMemdir":
-        """gpu_text (default on; FEI_PACK_HOST_TEXT=1 turns it off): decode / newline folding / '---' split / strip run in the
-        ingest kernels (fei_corpus_load_raw) instead of Python."""
-        if gpu_text is None:
-            gpu_text = os.environ.get("FEI_PACK_HOST_TEXT", "0") != "1"
-        if gpu_text and upload:
-            return self._build_raw()
-        self.signature = self.tree_signature(self.base)
-        self.folders = []
-        for root, dirs, _ in os.walk(self.base):
-            if any(st in dirs for st in U.STANDARD_FOLDERS):
-                rel = os.path.relpath(root, self.base)
-                self.folders.append("" if rel == "." else rel)
-        if len(self.folders) > 65535:
-            raise NotImplementedError("more than 65535 folders")
-        self.folder_ids = {f: i for i, f in enumerate(self.folders)}
-        self.recs = []
-        self.segments = {}
-        for folder in self.folders:
-            for st in U.STANDARD_FOLDERS:
-                seg = read_segment(self.base, folder, st)
-                self.segments[(folder, st)] = (len(self.recs), len(self.recs) + len(seg))
-                self.recs.extend(seg)
-        self.arrays = arrays_from_segments(self.recs, self.folder_ids)
-        if upload:
-            from .corpus import Corpus
-            self.corpus = Corpus().load(self.arrays)
-            self._field_values = {}
-        return self
-
-    def _build_raw(self) -> "PackedMemdir":
-        from .corpus import Corpus
-        self.signature = self.tree_signature(self.base)
-        self.folders = []
-        for root, dirs, _ in os.walk(self.base):
-            if any(st in dirs for st in U.STANDARD_FOLDERS):
-                rel = os.path.relpath(root, self.base)
-                self.folders.append("" if rel == "." else rel)
-        if len(self.folders) > 65535:
-            raise NotImplementedError("more than 65535 folders")
-        self.folder_ids = {f: i for i, f in enumerate(self.folders)}
-        segs: Dict[Tuple[str, str], List[Dict[str, Any]]] = {}
-        self.bad = {}
-        skipped_raw = set()
-        before = len(self.file_cache)
-        new_seg_cache = {}
-        for folder in self.folders:
-            for st in U.STANDARD_FOLDERS:
-                path = os.path.join(self.base, folder, st) if folder else os.path.join(self.base, st)
-                mt = os.stat(path).st_mtime_ns if os.path.exists(path) else -1
-                cached = self.seg_cache.get((folder, st))
-                if cached is not None and cached[0] == mt:
-                    segs[(folder, st)] = list(cached[1])                 # directory untouched since the last pack
-                else:
-                    segs[(folder, st)] = read_segment_raw(self.base, folder, st, self.file_cache)
-                new_seg_cache[(folder, st)] = (mt, segs[(folder, st)])
-        self.files_read = len(self.file_cache) - before
-        corpus = Corpus()
-        while True:
-            recs = [r for folder in self.folders for st in U.STANDARD_FOLDERS for r in segs[(folder, st)]]
-            arrays = raw_arrays_from_segments(recs, self.folder_ids)
-            valid = corpus.load_raw(arrays)
-            if valid.all():
-                break
-            for r, ok in zip(recs, valid.tolist()):            # undecodable files: reported and skipped (utils.py:247-248)
-                if not ok:
-                    try:
-                        r["raw"].decode("utf-8")
-                        msg = "invalid UTF-8"
-                    except UnicodeDecodeError as e:
-                        msg = str(e)
-                    self.bad.setdefault((r["folder"], r["status"]), []).append(f"Error processing {r['filename']}: {msg}")
-                    skipped_raw.add(id(r["raw"]))
-                    segs[(r["folder"], r["status"])].remove(r)
-        self.recs = recs
-        self.seg_cache = {k: (mt, list(segs[k])) for k, (mt, _r) in new_seg_cache.items()}
-        live = {id(r["raw"]) for r in recs} | skipped_raw
-        self.file_cache = {k: v for k, v in self.file_cache.items() if id(v) in live}   # forget deleted files
-        self.segments = {}
-        pos = 0
-        for folder in self.folders:
-            for st in U.STANDARD_FOLDERS:
-                k = len(segs[(folder, st)])
-                self.segments[(folder, st)] = (pos, pos + k)
-                pos += k
-        self.corpus = corpus
-        self._field_values = {}
-        fsb = corpus.fetch_meta()["fsb"] if corpus.n else np.zeros(0, dtype=np.uint32)
-        arrays["rec_bits"] = (fsb >> 24).astype(np.uint8)
-        self.arrays = arrays
-        return self
-
-    # ---- per-record header values for conditions only Python can judge (search.py:126-130)
-    def header_values(self, field: str) -> Tuple[np.ndarray, np.ndarray, List[str]]:
-        """(present[n], inv[n], distinct): the value _get_field_value would read for `field` (first key whose lower() equals
-        field.lower(), last line of that exact key), record by record, as an index into the list of distinct values
-        (len(distinct) for records without the header).  Extracted by the GPU once per packed corpus state."""
-        key = field.lower()
-        got = self._field_values.get(key)
-        if got is None:
-            from .program import C_SLOT, Cond, ProgramBuilder
-            from .regexc import Pattern
-            pb = ProgramBuilder()
-            pb.add_query([Cond(C_SLOT, pattern=Pattern("regex", "", re.IGNORECASE), field=field, mode=0)])
-            present, off, blob = self.corpus.slot_values(pb.build())
-            n = self.corpus.n
-            raw = blob.tobytes()
-            index: Dict[bytes, int] = {}
-            inv = np.empty(n, dtype=np.int64)
-            o = off.astype(np.int64)
-            for i in range(n):
-                if not present[i]:
-                    inv[i] = -1
-                    continue
-                inv[i] = index.setdefault(raw[o[i]:o[i + 1]], len(index))
-            distinct = [b.decode("utf-8") for b in index]
-            inv[inv < 0] = len(distinct)
-            got = self._field_values[key] = (present, inv, distinct)
-        return got
-
-    def sigma_in(self, ranges: Sequence[Tuple[int, int]]) -> bool:
-        """Does a record of these index ranges hold U+03A3 (the one character whose str.lower() the automata do not model)?"""
-        bits = self.arrays.get("rec_bits")
-        if bits is None or not len(bits):
-            return False
-        return any(bool((bits[a:b] & REC_HAS_SIGMA).any()) for a, b in ranges)
-
-    def begin_query(self) -> None:
-        self._aux_next = 0
-
-    def new_aux(self, verdicts: np.ndarray) -> int:
-        """Uploads one per-record verdict column for the query being compiled; returns its index (C_RECBITS.which)."""
-        from .program import MAX_AUX
-        if self._aux_next >= MAX_AUX:
-            raise NotImplementedError(f"more than {MAX_AUX} host-judged header conditions in one query")
-        k = self._aux_next
-        self._aux_next += 1
-        self.corpus.set_aux(k, verdicts)
-        return k
-
-    def report_skipped(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> None:
-        """The reference prints `Error processing <file>: <error>` each time a directory is listed (utils.py:247-248)."""
-        for f in (self.folders if folders is None else folders):
-            for st in (U.STANDARD_FOLDERS if statuses is None else statuses):
-                for msg in self.bad.get((f, st), []):
-                    print(msg)
-
-    def ranges(self, folders: Optional[Sequence[str]], statuses: Optional[Sequence[str]]) -> List[Tuple[int, int]]:
-        """Index ranges of the requested (folder, status) pairs in the caller's order (search.py:361-363)."""
-        if folders is None:
-            folders = self.folders
-        if statuses is None:
-            statuses = U.STANDARD_FOLDERS
-        out = []
-        for f in folders:
-            for st in statuses:
-                if st not in U.STANDARD_FOLDERS:
-                    raise ValueError(f"Invalid status: {st}. Must be one of {U.STANDARD_FOLDERS}")
-                r = self.segments.get((f, st))
-                if r and r[1] > r[0]:
-                    out.append(r)
-        return out
-
-
+# ----------------------------------------------------------------------------- process-wide cache
 _cache: Dict[str, PackedMemdir] = {}
+_cache_lock = threading.Lock()
 
 
 def packed(base: Optional[str] = None) -> PackedMemdir:
-    """The packed corpus for a tree, rebuilt when any cur/new/tmp directory changed."""
+    """The packed corpus for a tree, synced with the tree (see PackedMemdir.sync).  Callers hold `pm.lock` while they compile
+    conditions against it and scan, so a request sees one consistent state."""
     base = base or U.MEMDIR_BASE
-    pm = _cache.get(base)
-    if pm is None:
-        pm = PackedMemdir(base).build()
-        _cache[base] = pm
-    elif pm.signature != PackedMemdir.tree_signature(base):
-        # incremental sync: unchanged directories and already-seen files come from the host cache; the packed
-        # arrays are rebuilt and re-uploaded (H2D + tiling are cheap next to file I/O)
-        old = pm.corpus
-        pm.build()
-        if old is not None and old is not pm.corpus:
-            old.close()
-    return pm
+    with _cache_lock:
+        pm = _cache.get(base)
+        if pm is None:
+            pm = _cache[base] = PackedMemdir(base)
+    return pm.sync()
+
+
+def drop(base: Optional[str] = None) -> None:
+    """Forget (and free) the packed corpus of a tree, or of every tree."""
+    with _cache_lock:
+        keys = [base] if base else list(_cache)
+        for k in keys:
+            pm = _cache.pop(k, None)
+            if pm is not None:
+                pm.close()

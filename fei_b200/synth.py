@@ -99,6 +99,17 @@ def write_memdir(base: str, recs: List[Dict[str, Any]]) -> None:
             f.write(raw if raw is not None else file_text(r).encode("utf-8"))
 
 
+def write_memdir_native(base: str, seed: int, first: int, n: int, threads: int = 0) -> None:
+    """The same tree as write_memdir([record(seed, first + k) for k in range(n)]), written by native threads
+    (fei_synth_write_tree): a million files in seconds."""
+    for folder in FOLDERS + [".Trash", ".Archive"]:
+        for st in STATUSES:
+            os.makedirs(os.path.join(base, folder, st) if folder else os.path.join(base, st), exist_ok=True)
+    if not threads:
+        threads = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+    _abi.check(_abi.lib().fei_synth_write_tree(os.fsencode(base), HOSTNAME.encode(), seed, first, n, threads))
+
+
 def block(seed: int, i: int) -> Dict[str, Any]:
     l = _abi.lib()
     ts = C.c_double(); mid = C.create_string_buffer(8)

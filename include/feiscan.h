@@ -299,6 +299,9 @@ int fei_synth_record_host(uint64_t seed, uint64_t i,
 int fei_synth_block_host(uint64_t seed, uint64_t i, double* timestamp, char* memory_id8,
                          uint8_t* task_state, uint8_t* difficulty, uint8_t* is_task);
 
+/* tooling: records [first, first+n) of the synthetic Memdir written as Maildir files under base (directories must exist).          */
+int fei_synth_write_tree(const char* base, const char* hostname, uint64_t seed, uint64_t first, uint64_t n, int threads);
+
 /* ---- multi-GPU (one process per GPU; NCCL is dlopen()ed at first use) ------------- */
 #define FEI_NCCL_ID_BYTES 128
 int fei_comm_unique_id(uint8_t* id /*[FEI_NCCL_ID_BYTES]*/);

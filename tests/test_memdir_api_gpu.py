@@ -211,6 +211,126 @@ def test_incremental_sync_after_flag_and_move(gpu, tmp_path, capsys):
         U.set_memdir_base(old)
 
 
+def _oracle_keys(base, conds, include_content=False):
+    mems = mo.listing(base, None, None, include_content)
+    return [key_of(mems[i]) for i in mo.run_search(mems, [{"field": f, "operator": op, "value": v} for f, op, v in conds])]
+
+
+def test_in_place_rewrite_delete_and_bad_file_reporting(gpu, tmp_path, capsys):
+    """The reference rewrites memory files in place (folders.py:575, archiver.py:591): the directory's mtime does not move, the
+    packed corpus must still notice.  Deleted files disappear; an undecodable file in an untouched directory keeps being
+    reported on every listing (utils.py:247-248) without being read again."""
+    import os, time
+    from fei_b200 import packer, synth
+    from fei_b200.memdir_tools import utils as U
+    from fei_b200.memdir_tools.search import search_memories
+    base = str(tmp_path / "Memdir")
+    synth.write_memdir(base, [synth.record(33, i) for i in range(300)])
+    with open(os.path.join(base, ".Projects/AI", "cur", "1700009999.badbad02.host:2,"), "wb") as f:
+        f.write(b"Subject: x\n---\n\xff\xfe")
+    old = U.MEMDIR_BASE
+    U.set_memdir_base(base)
+    try:
+        conds = [("Tags", "has_tag", "zznewtag")]
+        assert search_memories(_query(conds, False)) == []
+        pm = packer.packed()
+        assert "badbad02" in capsys.readouterr().out
+        victim = search_memories(_query([("flags", "has_flag", "F")], False))[0]
+        path = os.path.join(U.get_memory_path(victim["folder"], victim["status"]), victim["filename"])
+        text = open(path).read()
+        with open(path, "w") as f:                                        # same name, same directory entry: an in-place rewrite
+            f.write(text.replace("Tags: ", "Tags: zznewtag,", 1))
+        got = search_memories(_query(conds, False))
+        assert [key_of(m) for m in got] == [key_of(victim)] == _oracle_keys(base, conds)
+        assert pm.files_read == 1 and pm.windows_packed == 1 and packer.packed() is pm
+        assert "badbad02" in capsys.readouterr().out                    # reported again, though its directory was not touched
+        os.remove(path)
+        assert search_memories(_query(conds, False)) == []
+        assert pm.files_read == 0
+        every = search_memories(_query([], False))
+        capsys.readouterr()
+        assert [key_of(m) for m in every] == _oracle_keys(base, [])
+        for env in ("0", "1"):                                           # the same through the no-inotify path (periodic native re-listing)
+            os.environ["FEI_INOTIFY"] = env; os.environ["FEI_REVALIDATE_S"] = "0"
+            packer.drop()
+            search_memories(_query(conds, False))
+            p2 = os.path.join(base, "cur", [n for n in os.listdir(os.path.join(base, "cur"))][0])
+            t2 = open(p2).read()
+            with open(p2, "w") as f:
+                f.write(t2.replace("---", "Tags: zznewtag\n---", 1) if "Tags: " not in t2 else t2.replace("Tags: ", "Tags: zznewtag,", 1))
+            assert [key_of(m) for m in search_memories(_query(conds, False))] == _oracle_keys(base, conds) != []
+            with open(p2, "w") as f:
+                f.write(t2)
+    finally:
+        os.environ.pop("FEI_INOTIFY", None); os.environ.pop("FEI_REVALIDATE_S", None)
+        packer.drop()
+        U.set_memdir_base(old)
+
+
+def test_one_changed_file_in_100k_repacks_one_window(gpu, tmp_path, capsys):
+    """Incremental sync at scale: 100 k files packed once; one new file, one rewritten file and one flag change later at most one
+    4096-record window is (re)packed and exactly the files whose content is new are read.  Results equal a fresh listing by the oracle."""
+    import os
+    from fei_b200 import packer, synth
+    from fei_b200.memdir_tools import utils as U
+    from fei_b200.memdir_tools.search import search_memories
+    base = str(tmp_path / "Memdir")
+    synth.write_memdir_native(base, 0xFE1, 0, 100_000)
+    old = U.MEMDIR_BASE
+    U.set_memdir_base(base)
+    try:
+        conds = [("Tags", "has_tag", "kubernetes"), ("flags", "has_flag", "P"), ("content", "matches", "terraform")]
+        r1 = search_memories(_query(conds, True))
+        pm = packer.packed()
+        assert pm.files_read == 100_000 and pm.full_packs == 1 and pm.n == 100_000
+        U.save_memory(".Projects/AI", "terraform notes", {"Tags": "kubernetes,new", "Subject": "fresh"}, "P")
+        r2 = search_memories(_query(conds, True))
+        assert pm.files_read == 1 and pm.windows_packed == 1 and pm.full_packs == 1 and len(r2) == len(r1) + 1
+        m = r1[len(r1) // 2]
+        assert U.update_memory_flags(m["filename"], m["folder"], m["status"], "FS")          # drops P: leaves the result
+        r3 = search_memories(_query(conds, True))
+        assert pm.files_read == 0 and pm.windows_packed == 1 and pm.full_packs == 1 and len(r3) == len(r2) - 1
+        capsys.readouterr()
+        assert [key_of(x) for x in r3] == _oracle_keys(base, conds, True)
+        want = {tuple(key_of(m)): m for m in mo.listing(base, None, None, True)}
+        capsys.readouterr()
+        assert all(x["content"] == want[tuple(key_of(x))]["content"] and x["headers"] == want[tuple(key_of(x))]["headers"] for x in r3[:200])
+    finally:
+        packer.drop()
+        U.set_memdir_base(old)
+
+
+def test_snapshot_restore_and_resync(gpu, tmp_path, capsys):
+    """save_snapshot / from_snapshot: the restored corpus answers like the packed one, and the first sync after the restore reads
+    only what changed on disk since the snapshot."""
+    import os
+    from fei_b200 import packer, synth
+    from fei_b200.memdir_tools import utils as U
+    from fei_b200.memdir_tools.search import search_memories
+    base = str(tmp_path / "Memdir")
+    synth.write_memdir_native(base, 5, 0, 6000)
+    old = U.MEMDIR_BASE
+    U.set_memdir_base(base)
+    try:
+        conds = [("content", "matches", "docker|rust"), ("Tags", "has_tag", "python")]
+        r1 = search_memories(_query(conds, True))
+        snap = str(tmp_path / "snap")
+        packer.packed().save_snapshot(snap)
+        packer.drop()
+        U.save_memory("", "rust and python after the snapshot", {"Tags": "python", "Subject": "late"}, "")
+        pm = packer.PackedMemdir.from_snapshot(base, snap)
+        assert pm.snapshot_gbs is not None and pm.n == 6000
+        packer._cache[base] = pm
+        r2 = search_memories(_query(conds, True))
+        assert pm.files_read == 1 and pm.full_packs == 0
+        capsys.readouterr()
+        assert [key_of(x) for x in r2] == _oracle_keys(base, conds, True) and len(r2) == len(r1) + 1
+        assert [(x["headers"], x["content"]) for x in r2 if x["headers"].get("Subject") != "late"] == [(x["headers"], x["content"]) for x in r1]
+    finally:
+        packer.drop()
+        U.set_memdir_base(old)
+
+
 def test_legacy_substring_search(api):
     """memdir_tools.utils.search_memories (utils.py:299-352): any header value / content substring, previews."""
     from fei_b200.memdir_tools import utils as U
