@@ -108,6 +108,7 @@ _SIGS = {
     "fei_chain_create": (C.c_int, [_P]),
     "fei_chain_destroy": (C.c_int, [_P]),
     "fei_chain_load_msgs": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _U64, _U64]),
+    "fei_chain_load_cols": (C.c_int, [_P, _P, _P, _P, _U64, _U64]),
     "fei_chain_synth": (C.c_int, [_P, _U64, _U64, _U64, C.c_int64]),
     "fei_chain_validate": (C.c_int, [_P, _P, _P, _P, _P]),
     "fei_chain_fetch": (C.c_int, [_P, _U64, _U64, _P, _U64, _P, _P, _P]),

@@ -16,6 +16,7 @@
 // bound (about 1.4k integer ops per compression), not HBM bound: see DESIGN.md.
 #include "common.h"
 #include "chain_json.h"
+#include "jsonfmt.cuh"
 #include <vector>
 #include <string.h>
 #include <mutex>
@@ -238,6 +239,7 @@ struct fei_chain {
   fei::DevBuf padded, blk_off;        // SHA-ready
   fei::DevBuf hash, hash_off, prev, prev_off;
   fei::DevBuf stored_bin, flags, digests, verdict, nblk, scan_tmp;
+  fei::DevBuf col_tag[FEI_CHAIN_NCOLS], col_num[FEI_CHAIN_NCOLS], col_str[FEI_CHAIN_NCOLS], col_off[FEI_CHAIN_NCOLS], json_len, json_err;   // column form (fei_chain_load_cols)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -488,6 +490,84 @@ extern "C" int fei_chain_validate_cols(const fei_json_col* cols, const uint8_t* 
     prev_ptr += prev_off_ptr[0]; prev_off_ptr = prev_rebased.data();
   }
   return fei_chain_validate_msgs(msgs.data(), off.data(), hash, hash_off, prev_ptr, prev_off_ptr, n, first_index, first_bad, bad_kind, digests);
+}
+
+// ---------------------------------------------------------------- canonical JSON of the column form on the GPU
+// One thread per block serialises the ten hashed fields (jsonfmt.cuh: json.dumps(..., sort_keys=True) incl. the shortest
+// round-trip float repr) -- a counting pass, a prefix sum, a writing pass -- straight into the resident chain's message blob: the
+// host ships typed columns (~100 B per block) instead of building and copying 360-byte texts (memorychain.py:117-128).
+namespace fei {
+struct DevCols { fei_json_col c[FEI_CHAIN_NCOLS]; };
+
+__global__ void __launch_bounds__(128) k_json_size(DevCols cols, uint64_t n, uint32_t* __restrict__ len, int* __restrict__ err) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  feijson::CountSink s;
+  if (feijson::put_block(s, cols.c, i) != 0) atomicExch(err, 1);
+  len[i] = s.n;
+}
+__global__ void __launch_bounds__(128) k_json_write(DevCols cols, uint64_t n, const uint64_t* __restrict__ off, uint8_t* __restrict__ out) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  feijson::WriteSink s{out + off[i]};
+  feijson::put_block(s, cols.c, i);
+}
+}  // namespace fei
+
+/* Resident chain from the column form (fei_chain_validate_cols' layout): typed columns are uploaded, the canonical JSON texts are
+ * produced on the GPU, then padded and linked like fei_chain_load_msgs does.  previous_hash must be all strings (column 4).      */
+extern "C" int fei_chain_load_cols(fei_chain* ch, const fei_json_col* cols, const uint8_t* hash, const uint64_t* hash_off, uint64_t n, uint64_t first_index) {
+  FEI_TRY(require_ready());
+  if (!ch || !cols || !hash_off) { set_error("null argument"); return FEI_E_BADARG; }
+  Context& c = ctx();
+  cudaStream_t s = c.stream;
+  ch->n = n; ch->first_index = first_index; ch->msg_bytes = 0;
+  if (n == 0) return FEI_OK;
+  const fei_json_col& pc = cols[4];
+  if (pc.tag || pc.uniform_tag != FEI_J_STR) { set_error("previous_hash column must hold strings only for the resident column form"); return FEI_E_UNSUPPORTED; }
+  DevCols dc;
+  std::vector<std::vector<uint64_t>> rebased(FEI_CHAIN_NCOLS);
+  for (int k = 0; k < FEI_CHAIN_NCOLS; ++k) {
+    const fei_json_col& h = cols[k];
+    fei_json_col d; d.tag = nullptr; d.uniform_tag = h.uniform_tag; d.num = nullptr; d.str = nullptr; d.str_off = nullptr;
+    if (!h.tag && (h.uniform_tag < FEI_J_NULL || h.uniform_tag > FEI_J_BIGINT)) { set_error("column %d: bad uniform tag %d", k, h.uniform_tag); return FEI_E_BADARG; }
+    if (h.tag) { FEI_TRY(upload(ch->col_tag[k], h.tag, n, s)); d.tag = ch->col_tag[k].as<uint8_t>(); }
+    if (h.num) { FEI_TRY(upload(ch->col_num[k], h.num, n * 8, s)); d.num = ch->col_num[k].as<uint64_t>(); }
+    if (h.str_off) {
+      const uint64_t base = h.str_off[0];
+      const uint64_t* off = h.str_off;
+      if (base) { rebased[k].resize(n + 1); for (uint64_t i = 0; i <= n; ++i) rebased[k][i] = h.str_off[i] - base; off = rebased[k].data(); }
+      FEI_TRY(upload(ch->col_off[k], off, (n + 1) * 8, s));
+      FEI_TRY(upload(ch->col_str[k], h.str ? h.str + base : nullptr, h.str ? h.str_off[n] - base : 0, s));
+      d.str = ch->col_str[k].as<uint8_t>(); d.str_off = ch->col_off[k].as<uint64_t>();
+    }
+    dc.c[k] = d;
+  }
+  FEI_TRY(ch->json_len.ensure(n * 4));
+  FEI_TRY(ch->json_err.ensure(16));
+  FEI_CUDA(cudaMemsetAsync(ch->json_err.p, 0, 4, s));
+  FEI_TRY(ch->msg_off.ensure((n + 1) * 8));
+  const unsigned g = (unsigned)((n + 127) / 128);
+  k_json_size<<<g, 128, 0, s>>>(dc, n, ch->json_len.as<uint32_t>(), ch->json_err.as<int>());
+  FEI_TRY(exclusive_scan_u32_u64(ch->json_len.as<uint32_t>(), n, ch->msg_off.as<uint64_t>(), ch->scan_tmp, s));
+  uint64_t total = 0; int err = 0;
+  FEI_CUDA(cudaMemcpyAsync(&total, ch->msg_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaMemcpyAsync(&err, ch->json_err.p, 4, cudaMemcpyDeviceToHost, s));
+  FEI_CUDA(cudaStreamSynchronize(s));                               // (also: the rebased offset vectors may go now)
+  if (err) { set_error("unsupported JSON tag in chain columns"); return FEI_E_BADARG; }
+  ch->msg_bytes = total;
+  FEI_TRY(ch->msgs.ensure(total + 16));
+  k_json_write<<<g, 128, 0, s>>>(dc, n, ch->msg_off.as<uint64_t>(), ch->msgs.as<uint8_t>());
+  FEI_CUDA(cudaGetLastError());
+  FEI_TRY(upload(ch->hash, hash, hash_off[n], s));
+  FEI_TRY(upload(ch->hash_off, hash_off, (n + 1) * 8, s));
+  // previous_hash strings = column 4, already on the device
+  FEI_TRY(ch->prev.ensure(ch->col_str[4].bytes ? ch->col_str[4].bytes : 16));
+  FEI_TRY(ch->prev_off.ensure((n + 1) * 8));
+  const uint64_t pbytes = cols[4].str_off[n] - cols[4].str_off[0];
+  if (pbytes) FEI_CUDA(cudaMemcpyAsync(ch->prev.p, ch->col_str[4].p, pbytes, cudaMemcpyDeviceToDevice, s));
+  FEI_CUDA(cudaMemcpyAsync(ch->prev_off.p, ch->col_off[4].p, (n + 1) * 8, cudaMemcpyDeviceToDevice, s));
+  return chain_prepare(ch);
 }
 
 extern "C" int fei_chain_fetch(fei_chain* ch, uint64_t first, uint64_t n, uint8_t* msgs, uint64_t msgs_cap, uint64_t* msg_off,

@@ -20,6 +20,7 @@ import json
 import logging
 import os
 import threading
+import weakref
 import time
 from operator import attrgetter, itemgetter
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
@@ -154,7 +155,7 @@ def _extract(blocks: Sequence[Any]) -> Optional[List[tuple]]:
     cls = kinds.pop()
     hash_key = "hash"
     if isinstance(getattr(cls, "hash", None), property):
-        if cls is not MemoryBlock:
+        if cls is not MemoryBlock and cls is not _TrackedBlock:
             return None
         hash_key = "_hash"                       # our lazy-hash block keeps the value there (None until first use)
     elif hasattr(cls, "hash"):
@@ -201,7 +202,7 @@ def chain_columns_native(blocks: Sequence[Any]) -> Optional[Tuple[List[_Col], np
     cls = kinds.pop()
     hash_key = "hash"
     if isinstance(getattr(cls, "hash", None), property):
-        if cls is not MemoryBlock:
+        if cls is not MemoryBlock and cls is not _TrackedBlock:
             return None
         hash_key = "_hash"
     elif hasattr(cls, "hash"):
@@ -412,6 +413,154 @@ class _HashProbe:
                 setattr(self, k, getattr(b, k))
 
 
+
+# --------------------------------------------------------------------------- resident chain
+_WATCHED = frozenset(_DIRECT + _OPTIONAL + ("hash", "_hash"))
+
+
+class _TrackedBlock(MemoryBlock):
+    """A MemoryBlock that sits in a MemoryChain: assigning one of its hashed attributes (or its stored hash) tells the chain that
+    its device image is stale from that block on.  Blocks are switched to this class when they enter a chain (same layout), so
+    building blocks stays as cheap as a plain class."""
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name in _WATCHED:
+            for ref, pos in self.__dict__.get("_fei_owners", ()):
+                chain = ref()
+                if chain is not None:
+                    chain._touch(pos)
+
+
+def _track(block: Any, chain: "MemoryChain", pos: int) -> None:
+    if type(block) is MemoryBlock:
+        object.__setattr__(block, "__class__", _TrackedBlock)
+    if type(block) is _TrackedBlock:
+        owners = [(r, p) for r, p in block.__dict__.get("_fei_owners", ()) if r() is not None and r() is not chain]
+        owners.append((weakref.ref(chain), pos))
+        block.__dict__["_fei_owners"] = owners
+
+
+class _TrackedList(list):
+    """`MemoryChain.chain`: a list whose structural changes (append, item assignment, insert, delete, sort ...) mark the chain's
+    device image stale from the lowest index they can affect."""
+
+    def __init__(self, owner: "MemoryChain", items=()):
+        super().__init__(items)
+        self._owner = weakref.ref(owner)
+
+    def _dirty(self, k: int) -> None:
+        o = self._owner()
+        if o is not None:
+            o._touch(max(0, k))
+
+    def append(self, x): self._dirty(len(self)); super().append(x)
+    def extend(self, xs): self._dirty(len(self)); super().extend(xs)
+    def insert(self, i, x): self._dirty(i if i >= 0 else len(self) + i); super().insert(i, x)
+    def pop(self, i=-1): self._dirty(i if i >= 0 else len(self) + i); return super().pop(i)
+    def remove(self, x): self._dirty(0); super().remove(x)
+    def clear(self): self._dirty(0); super().clear()
+    def sort(self, *a, **k): self._dirty(0); super().sort(*a, **k)
+    def reverse(self): self._dirty(0); super().reverse()
+    def __iadd__(self, xs): self._dirty(len(self)); return super().__iadd__(xs)
+    def __imul__(self, k): self._dirty(0); return super().__imul__(k)
+
+    def __setitem__(self, i, x):
+        self._dirty(0 if isinstance(i, slice) else (i if i >= 0 else len(self) + i))
+        super().__setitem__(i, x)
+
+    def __delitem__(self, i):
+        self._dirty(0 if isinstance(i, slice) else (i if i >= 0 else len(self) + i))
+        super().__delitem__(i)
+
+
+class _Resident:
+    """Device image of a chain (fei_chain*): the hashed fields as typed columns, turned into canonical JSON and SHA-ready blocks
+    by GPU kernels once (fei_chain_load_cols); every validate_chain() after that re-hashes what is resident (fei_chain_validate)."""
+
+    def __init__(self):
+        _abi.init()
+        self.h = C.c_void_p()
+        _abi.check(_abi.lib().fei_chain_create(C.byref(self.h)))
+        self.n = 0
+        self.cols: Optional[List[_Col]] = None           # host copy of the columns: a changed tail is re-marshalled, the rest reused
+        self.hash_blob: Optional[np.ndarray] = None
+        self.hash_off: Optional[np.ndarray] = None
+        self.uploads = 0
+        self.marshalled = 0
+
+    def close(self) -> None:
+        if self.h:
+            _abi.lib().fei_chain_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _marshal(blocks: Sequence[Any]):
+        native = chain_columns_native(blocks)
+        if native is not None:
+            return native
+        cols, stored = chain_columns(blocks)
+        if not all(isinstance(h, str) for h in stored):
+            raise NotImplementedError("block.hash must be a str for GPU validation")
+        hb, ho = _str_blob(stored)
+        return cols, hb, ho
+
+    @staticmethod
+    def _concat(a: _Col, b: _Col, na: int) -> Optional[_Col]:
+        """Column a (first na entries) followed by column b; None when their representations differ (then everything is re-marshalled)."""
+        if a.tag is not None or b.tag is not None or a.uniform != b.uniform:
+            return None
+        c = _Col()
+        c.uniform = a.uniform
+        if a.uniform in (_abi.J_INT, _abi.J_FLOAT):
+            c.num = np.concatenate([a.num[:na], b.num])
+        elif a.uniform == _abi.J_STR:
+            end = int(a.off[na])
+            c.blob = np.concatenate([a.blob[:end], b.blob]) if end or len(b.blob) else np.zeros(1, dtype=np.uint8)
+            c.off = np.concatenate([a.off[:na + 1], b.off[1:] + np.uint64(end)])
+        return c
+
+    def sync(self, blocks: Sequence[Any], dirty_from: Optional[int]) -> bool:
+        """Bring the device image in line with `blocks`; False when this chain cannot be resident (falls back to one-shot calls)."""
+        n = len(blocks)
+        keep = 0
+        if self.cols is not None and dirty_from is not None:
+            keep = min(dirty_from, self.n, n)
+        elif self.cols is not None and dirty_from is None and self.n == n:
+            return True
+        tail = blocks[keep:]
+        cols = hb = ho = None
+        if keep and tail:
+            tcols, thb, tho = self._marshal(tail)
+            merged = [self._concat(a, b, keep) for a, b in zip(self.cols, tcols)]
+            if all(m is not None for m in merged):
+                cols = merged
+                end = int(self.hash_off[keep])
+                hb = np.concatenate([self.hash_blob[:end], thb]); ho = np.concatenate([self.hash_off[:keep + 1], tho[1:] + np.uint64(end)])
+                self.marshalled = len(tail)
+        if cols is None:
+            cols, hb, ho = self._marshal(blocks)
+            self.marshalled = n
+        if cols[4].tag is not None or cols[4].uniform != _abi.J_STR:
+            return False                                    # previous_hash values that are not strings: not resident
+        arr = _cols_struct(cols)
+        _abi.check(_abi.lib().fei_chain_load_cols(self.h, arr, _abi.ptr(np.ascontiguousarray(hb)), _abi.ptr(np.ascontiguousarray(ho)), n, 0))
+        self.cols, self.hash_blob, self.hash_off, self.n = cols, hb, ho, n
+        self.uploads += 1
+        return True
+
+    def validate(self) -> Tuple[int, int]:
+        fb, kind = C.c_int64(-1), C.c_int32(0)
+        _abi.check(_abi.lib().fei_chain_validate(self.h, C.byref(fb), C.byref(kind), None, None))
+        return fb.value, kind.value
+
+
 class MemoryChain:
     """The ledger slice of the reference's ``MemoryChain``: building (genesis, add_memory with GPU proof of work), validating
     (:596-618), syncing (receive_chain_update) and persisting (serialize / save / load) a chain.
@@ -422,14 +571,62 @@ class MemoryChain:
 
     def __init__(self, node_id: str = "validator", difficulty: int = 2, blocks: Optional[Iterable[Any]] = None,
                  chain_file: Optional[str] = None):
-        self.chain: List[Any] = list(blocks) if blocks is not None else []
+        self.lock = threading.RLock()
+        self._res: Optional[_Resident] = None
+        self._dirty_from: Optional[int] = 0
+        self.chain = list(blocks) if blocks is not None else []
         self.node_id = node_id
         self.difficulty = difficulty
-        self.lock = threading.RLock()
         self.chain_file = chain_file      # None: nothing is written behind the caller's back; save_chain() then uses CHAIN_FILE
+        if len(self._chain) > 1:
+            self._sync_resident()         # the device image is built when blocks arrive, not when they are first validated
+
+    # `chain` stays a list for every caller; assignments and in-place edits are noticed
+    @property
+    def chain(self) -> List[Any]:
+        return self._chain
+
+    @chain.setter
+    def chain(self, blocks: Iterable[Any]) -> None:
+        self._chain = _TrackedList(self, blocks)
+        self._dirty_from = 0
+
+    def _touch(self, pos: int) -> None:
+        self._dirty_from = pos if self._dirty_from is None else min(self._dirty_from, pos)
+
+    def _sync_resident(self) -> bool:
+        """Marshal what changed (blocks from the lowest touched index on), hand the columns to the GPU, start watching the blocks."""
+        with self.lock:
+            if os.environ.get("FEI_CHAIN_RESIDENT", "1") == "0":
+                return False
+            if self._res is None:
+                self._res = _Resident()
+            start = self._dirty_from
+            try:
+                ok = self._res.sync(self._chain, start)
+            except NotImplementedError:
+                ok = False
+            if not ok:
+                return False
+            if start is not None:
+                for pos in range(min(start, len(self._chain)), len(self._chain)):
+                    _track(self._chain[pos], self, pos)
+            self._dirty_from = None
+            return True
 
     def validate_chain(self) -> bool:
-        return validate_chain_blocks(self.chain, lock=self.lock, log=logger)
+        """Reference :596-618.  The blocks' hashed fields live on the device as typed columns -> canonical JSON -> SHA-ready blocks
+        (built when the blocks arrived; only blocks touched since are marshalled again), so a call is one GPU pass over resident data."""
+        with self.lock:
+            if len(self._chain) < 2:
+                return True
+            if not self._sync_resident():
+                return validate_chain_blocks(self._chain, lock=self.lock, log=logger)
+            first_bad, kind = self._res.validate()
+        if first_bad < 0:
+            return True
+        logger.error(f"Block {first_bad} has invalid hash" if kind == 1 else f"Block {first_bad} has broken link to previous block")
+        return False
 
     # ---- building and persisting the ledger (reference :528-594, :1130-1172); proof of work runs on the GPU (mine_block)
     def create_genesis_block(self) -> None:
@@ -461,6 +658,8 @@ class MemoryChain:
             self.chain.append(new_block)
             if self.chain_file:
                 self.save_chain()
+            if len(self._chain) > 1:
+                self._sync_resident()     # the new block joins the device image now (one block marshalled)
         return new_block.hash
 
     def serialize_chain(self) -> List[Dict[str, Any]]:
@@ -486,6 +685,8 @@ class MemoryChain:
                 chain_data = json.load(f)
             with self.lock:
                 self.chain = [MemoryBlock.from_dict(block_data) for block_data in chain_data]
+                if len(self._chain) > 1:
+                    self._sync_resident()
             return len(self.chain) > 0
         except (json.JSONDecodeError, KeyError, FileNotFoundError) as e:
             logger.error(f"Error loading chain: {e}")
@@ -511,6 +712,7 @@ class MemoryChain:
                     logger.warning("Rejecting chain update: Chains have diverged")
                     return False
             self.chain = new_chain
+            self._sync_resident()
         logger.info(f"Chain updated to {len(self.chain)} blocks")
         return True
 

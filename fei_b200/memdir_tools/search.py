@@ -218,12 +218,13 @@ def _compile_one(field: Any, op: str, v2: Any, include_content: bool, pm) -> Lis
         return [Cond(C_NAME, pattern=pat, negate=neg, which=NAME_ID if low == "id" else NAME_FILENAME)]
     if low in ("folder", "status", "maildir_status"):
         names = pm.folders if low == "folder" else U.STANDARD_FOLDERS
-        if len(names) > 64:
+        ids = [pm.folder_ids[f] for f in names] if low == "folder" else list(range(len(names)))      # packed folder ids are stable, not positions
+        if ids and max(ids) >= 64:
             raise NotImplementedError("folder predicates on more than 64 folders")
         verdicts = _eval_on_strings(names, op, v2)
         if any(isinstance(v, Exception) for v in verdicts):
             return [_Raises(next(v for v in verdicts if isinstance(v, Exception)), None)]
-        bits = sum(1 << i for i, v in enumerate(verdicts) if v)
+        bits = sum(1 << i for i, v in zip(ids, verdicts) if v)
         return [Cond(C_FOLDER_SET if low == "folder" else C_STATUS_SET, set64=bits)]
     if low in _DATE_HEADERS:
         return _compile_date_header(field, op, v2, pm)

@@ -326,7 +326,7 @@ class PackedMemdir:
             dirty_paths = self.watcher.drain()
             now = time.monotonic()
             recheck = float(os.environ.get("FEI_REVALIDATE_S", "1.0"))
-            full_check = self.corpus is None or folders != self.folders or (dirty_paths is None and now - self.last_full_check >= recheck)
+            full_check = self.corpus is None or (dirty_paths is None and now - self.last_full_check >= recheck)
             changed: List[Tuple[str, str]] = []
             for folder in folders:
                 for st in U.STANDARD_FOLDERS:
@@ -343,9 +343,10 @@ class PackedMemdir:
                         changed.append((folder, st))
             if full_check or changed:
                 self.last_full_check = now
-            if self.corpus is None or folders != self.folders:
+            if self.corpus is None:
                 self._full_pack(folders)
-            elif changed:
+            elif folders != self.folders or changed:
+                self._set_folders(folders)
                 self._incremental(changed)
             return self
 
@@ -360,10 +361,23 @@ class PackedMemdir:
     def _fsb_of(self, key: Tuple[str, str]) -> int:
         return (self.folder_ids[key[0]] & 0xFFFF) | (U.STANDARD_FOLDERS.index(key[1]) << 16)
 
+    def _set_folders(self, folders: List[str]) -> None:
+        """The folder list in os.walk order (= listing order); packed folder ids are handed out once and never change, so records
+        already on the device keep theirs when folders appear or disappear."""
+        for f in folders:
+            if f not in self.folder_ids:
+                self.folder_ids[f] = len(self.folder_ids)
+        if len(self.folder_ids) > 65535:
+            raise NotImplementedError("more than 65535 folders")
+        gone = [k for k in self.segs if k[0] not in folders]
+        for key in gone:                                               # a folder that vanished: its records become tombstones
+            del self.segs[key]
+        self.folders = folders
+
     def _full_pack(self, folders: List[str]) -> None:
         from .corpus import Corpus
-        self.folders = folders
-        self.folder_ids = {f: i for i, f in enumerate(folders)}
+        self.folder_ids = {}
+        self._set_folders(folders)
         order = self._order()
         segs: Dict[Tuple[str, str], _Seg] = {}
         raws: List[np.ndarray] = []
@@ -495,11 +509,17 @@ class PackedMemdir:
             todo = np.nonzero(seg.dev < 0)[0]
             if len(todo):
                 new_entries.append((key, todo))
-        if not any_change:                                             # only directory timestamps moved
+        if not any_change:                                             # only directory timestamps moved (or empty directories appeared)
             for key, seg in fresh.items():
-                self.segs[key].mtime_ns = seg.mtime_ns
+                if key in self.segs:
+                    self.segs[key].mtime_ns = seg.mtime_ns
+                    self.segs[key].bad = seg.bad
+                else:
+                    self.segs[key] = seg
             self.files_read = 0
             self.windows_packed = 0
+            if list(self.segments) != self._order() or self.n != sum(s_.listing.n for s_ in self.segs.values()):
+                self._rebuild_listing()                                # the folder set changed
             return
         # renames: a new entry whose (inode, size, mtime) equals a removed record's is that record under a new name (move_memory /
         # update_memory_flags, utils.py:255-297, :354-388): its packed text is taken from the device, the file is not read

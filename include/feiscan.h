@@ -272,6 +272,10 @@ int fei_chain_destroy(fei_chain* ch);
 int fei_chain_load_msgs(fei_chain* ch, const uint8_t* msgs, const uint64_t* msg_off,
                         const uint8_t* hash, const uint64_t* hash_off,
                         const uint8_t* prev, const uint64_t* prev_off, uint64_t n, uint64_t first_index);
+/* The same from the column form: typed columns go up (~100 B per block), the canonical JSON texts (incl. Python's shortest
+ * round-trip float repr) are produced by a GPU kernel, then hashed in place.  previous_hash must be all strings.                 */
+int fei_chain_load_cols(fei_chain* ch, const fei_json_col* cols /*[FEI_CHAIN_NCOLS]*/, const uint8_t* hash, const uint64_t* hash_off,
+                        uint64_t n, uint64_t first_index);
 /* Synthetic chain blocks [first, first+n) (synth.cuh gen_block): canonical JSON and
  * the SHA-256 links are produced on the GPU; `corrupt_at` >= 0 flips one stored digest. */
 int fei_chain_synth(fei_chain* ch, uint64_t seed, uint64_t first, uint64_t n, int64_t corrupt_at);
