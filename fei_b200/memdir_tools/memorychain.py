@@ -574,6 +574,7 @@ class MemoryChain:
         self.lock = threading.RLock()
         self._res: Optional[_Resident] = None
         self._dirty_from: Optional[int] = 0
+        self._all_tracked = False
         self.chain = list(blocks) if blocks is not None else []
         self.node_id = node_id
         self.difficulty = difficulty
@@ -593,6 +594,8 @@ class MemoryChain:
 
     def _touch(self, pos: int) -> None:
         self._dirty_from = pos if self._dirty_from is None else min(self._dirty_from, pos)
+        if pos == 0:
+            self._all_tracked = False
 
     def _sync_resident(self) -> bool:
         """Marshal what changed (blocks from the lowest touched index on), hand the columns to the GPU, start watching the blocks."""
@@ -611,7 +614,9 @@ class MemoryChain:
             if start is not None:
                 for pos in range(min(start, len(self._chain)), len(self._chain)):
                     _track(self._chain[pos], self, pos)
-            self._dirty_from = None
+                self._all_tracked = (self._all_tracked or start == 0) and all(type(b) is _TrackedBlock for b in self._chain[start:])
+            # blocks of other classes cannot report their own mutations: such a chain is marshalled afresh on every call
+            self._dirty_from = None if self._all_tracked else 0
             return True
 
     def validate_chain(self) -> bool:

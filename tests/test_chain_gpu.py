@@ -191,3 +191,84 @@ def test_build_persist_and_reload_a_chain(gpu, tmp_path):
     assert mc.MemoryChain(chain_file=str(tmp_path / "missing.json")).load_chain() is False
     (tmp_path / "bad.json").write_text("{not json")
     assert mc.MemoryChain(chain_file=str(tmp_path / "bad.json")).load_chain() is False
+
+
+def _our_chain(n, seed=0xC4A1):
+    from fei_b200 import synth
+    from fei_b200.memdir_tools import memorychain as mc
+    blocks = []
+    for ob in co.build_chain(synth.chain_specs(seed, 0, n)):
+        b = mc.MemoryBlock(ob.index, ob.timestamp, ob.memory_data, ob.previous_hash, ob.responsible_node, ob.proposer_node)
+        b.nonce = ob.nonce; b.hash = ob.hash
+        blocks.append(b)
+    return blocks
+
+
+def test_resident_chain_tracks_mutations(gpu, caplog):
+    """MemoryChain keeps a device image of its blocks: a second validate_chain() re-hashes resident data without marshalling a
+    block, and every kind of edit (attribute assignment, item assignment, append / pop, a new list) is seen -- the verdict and the
+    log line stay the reference's (memorychain.py:596-618)."""
+    import ctypes as C
+    from fei_b200 import _abi
+    from fei_b200.memdir_tools import memorychain as mc
+    n = 3000
+    ch = mc.MemoryChain(blocks=_our_chain(n))
+    r = ch._res
+    assert r is not None and r.uploads == 1 and r.marshalled == n          # built when the blocks arrived
+    assert ch.validate_chain() and ch.validate_chain() and r.uploads == 1   # resident: nothing marshalled, nothing uploaded
+    # the GPU-made canonical JSON equals json.dumps(..., sort_keys=True) of the reference
+    off = np.zeros(n + 1, dtype=np.uint64); buf = np.zeros(600 * n, dtype=np.uint8)
+    _abi.check(_abi.lib().fei_chain_fetch(r.h, 0, n, _abi.ptr(buf), buf.size, _abi.ptr(off), None, None))
+    texts = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(n)]
+    assert texts == [co.block_text(b).encode() for b in ch.chain]
+    with caplog.at_level(logging.ERROR, logger="memorychain"):
+        ch.chain[1234].nonce = 5                                            # attribute assignment on a block of the chain
+        assert ch.validate_chain() is False and r.uploads == 2 and r.marshalled == n - 1234
+        assert caplog.records[-1].getMessage() == "Block 1234 has invalid hash"
+        ch.chain[1234].nonce = 0
+        assert ch.validate_chain() is True and r.uploads == 3
+        ch.chain[2000].memory_data = {"metadata": {"unique_id": "someone-else"}}
+        assert ch.validate_chain() is False and caplog.records[-1].getMessage() == "Block 2000 has invalid hash"
+        good = _our_chain(n)[2000]
+        ch.chain[2000] = good                                               # item assignment
+        assert ch.validate_chain() is True
+        last = ch.chain.pop()
+        assert ch.validate_chain() is True and r.n == n - 1
+        last.previous_hash = "0" * 64
+        ch.chain.append(last)
+        assert ch.validate_chain() is False and caplog.records[-1].getMessage() == f"Block {n - 1} has invalid hash"
+        ch.chain = _our_chain(500)                                          # a new list
+        assert ch.validate_chain() is True and r.n == 500
+        ch.chain[77].hash = "f" * 64                                        # stored hash edited: block 77 invalid, and 78 would have a broken link
+        assert ch.validate_chain() is False and caplog.records[-1].getMessage() == "Block 77 has invalid hash"
+    # blocks of a foreign class cannot report their mutations: such a chain is marshalled again on every call, never stale
+    foreign = co.build_chain(__import__("fei_b200.synth", fromlist=["x"]).chain_specs(0xC4A1, 0, 300))
+    ch2 = mc.MemoryChain(blocks=foreign)
+    assert ch2.validate_chain() is True
+    foreign[100].nonce = 9
+    assert ch2.validate_chain() is False and co.validate(foreign) == (False, 100, 1)
+
+
+def test_gpu_canonical_json_matches_reference_kats(gpu, chain_golden):
+    """fei_chain_load_cols: the column form serialised on the GPU (incl. Python's shortest round-trip float repr, ensure_ascii
+    escapes, big ints) gives the reference's digests for every golden single-block vector."""
+    import ctypes as C
+    from fei_b200 import _abi
+    from fei_b200.memdir_tools import memorychain as mc
+    blocks = [single_block(s) for s in chain_golden["single"]]
+    for b in blocks:
+        if not isinstance(b.previous_hash, str):
+            b.previous_hash = str(b.previous_hash)
+    cols, stored = mc.chain_columns(blocks)
+    hb, ho = mc._str_blob([s if isinstance(s, str) else "" for s in stored])
+    h = C.c_void_p(); _abi.check(_abi.lib().fei_chain_create(C.byref(h)))
+    n = len(blocks)
+    _abi.check(_abi.lib().fei_chain_load_cols(h, mc._cols_struct(cols), _abi.ptr(hb), _abi.ptr(ho), n, 0))
+    dig = np.zeros((n, 32), dtype=np.uint8); fb, kind = C.c_int64(), C.c_int32()
+    _abi.check(_abi.lib().fei_chain_validate(h, C.byref(fb), C.byref(kind), _abi.ptr(dig), None))
+    off = np.zeros(n + 1, dtype=np.uint64); buf = np.zeros(4096 * n, dtype=np.uint8)
+    _abi.check(_abi.lib().fei_chain_fetch(h, 0, n, _abi.ptr(buf), buf.size, _abi.ptr(off), None, None))
+    _abi.lib().fei_chain_destroy(h)
+    for i, b in enumerate(blocks):
+        assert bytes(buf[int(off[i]):int(off[i + 1])]) == mc.canonical_texts([b])[0], chain_golden["single"][i]["name"]
+        assert bytes(dig[i]).hex() == co.block_hash(b), chain_golden["single"][i]["name"]
