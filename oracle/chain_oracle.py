@@ -181,3 +181,38 @@ def c_validate(chain: Sequence[Any]) -> Tuple[bool, int, int]:
     fb, kind = C.c_int64(), C.c_int()
     ok = c_lib().co_validate(vals, harr, hlen, len(chain), C.byref(fb), C.byref(kind))
     return bool(ok), fb.value, kind.value
+
+
+# --------------------------------------------------------------------------- chain-memory search ("next" row 4)
+def search_chain_memories(chain: Sequence[Any], query: str, search_content: bool = True, search_subject: bool = True,
+                          search_tags: bool = True) -> List[int]:
+    """Indices of the blocks MemorychainConnector.search_memories returns (fei/tools/memorychain_connector.py:273-324)."""
+    q = query.lower()
+    out = []
+    for i, block in enumerate(chain):
+        memory = block["memory_data"] if isinstance(block, dict) else block.memory_data
+        if memory.get("metadata", {}).get("unique_id", "") == "genesis":          # :304-305
+            continue
+        headers = memory.get("headers", {})
+        found = search_subject and q in headers.get("Subject", "").lower()         # :310
+        found = found or (search_tags and q in headers.get("Tags", "").lower())    # :314
+        found = found or (search_content and q in memory.get("content", "").lower())   # :318
+        if found:
+            out.append(i)
+    return out
+
+
+def search_chain_by_tag(chain: Sequence[Any], tag: str) -> List[int]:
+    """Indices of the blocks MemorychainConnector.search_by_tag returns (memorychain_connector.py:326-362)."""
+    if tag.startswith("#"):
+        tag = tag[1:]
+    tag = tag.lower()
+    out = []
+    for i, block in enumerate(chain):
+        memory = block["memory_data"] if isinstance(block, dict) else block.memory_data
+        tags = [t.strip() for t in memory.get("headers", {}).get("Tags", "").lower().split(",")]
+        if memory.get("metadata", {}).get("unique_id", "") == "genesis":
+            continue
+        if tag in tags:
+            out.append(i)
+    return out

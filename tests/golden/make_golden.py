@@ -4,7 +4,7 @@
 Only runs in the build container (the reference tree does not travel to the GPU box);
 the JSON fixtures it writes are committed.  Usage:
 
-    TZ=UTC python tests/golden/make_golden.py [chain] [memdir]
+    TZ=UTC python tests/golden/make_golden.py [chain] [memdir] [chainsearch]
 
 The reference is imported with cwd = a scratch directory (memdir_tools.utils binds
 MEMDIR_BASE to os.getcwd() at import, utils.py:16) and HOME = scratch (memorychain.py:49-52).
@@ -179,7 +179,7 @@ def make_chain(scratch: str):
 
 
 def main():
-    what = sys.argv[1:] or ["chain", "memdir"]
+    what = sys.argv[1:] or ["chain", "memdir", "chainsearch"]
     scratch = tempfile.mkdtemp(prefix="fei_golden_")
     try:
         if "chain" in what:
@@ -187,6 +187,9 @@ def main():
         if "memdir" in what:
             from make_golden_memdir import make_memdir
             make_memdir(scratch, import_reference)
+        if "chainsearch" in what:
+            from make_golden_chainsearch import make_chainsearch
+            make_chainsearch()
     finally:
         os.chdir(REPO)
         shutil.rmtree(scratch, ignore_errors=True)

@@ -272,3 +272,18 @@ def test_gpu_canonical_json_matches_reference_kats(gpu, chain_golden):
     for i, b in enumerate(blocks):
         assert bytes(buf[int(off[i]):int(off[i + 1])]) == mc.canonical_texts([b])[0], chain_golden["single"][i]["name"]
         assert bytes(dig[i]).hex() == co.block_hash(b), chain_golden["single"][i]["name"]
+
+
+def test_chain_memory_search_matches_reference(gpu):
+    """ChainMemorySearch (GPU) vs the reference's MemorychainConnector.search_memories / search_by_tag goldens and the oracle."""
+    from tests.conftest import load_golden
+    from fei_b200.memdir_tools.chain_search import ChainMemorySearch
+    g = load_golden("chainsearch_golden.json")
+    idx = {id(b["memory_data"]): i for i, b in enumerate(g["blocks"])}
+    cs = ChainMemorySearch(g["blocks"])
+    for q in g["queries"]:
+        got = [idx[id(m)] for m in cs.search_memories(q["query"], q["search_content"], q["search_subject"], q["search_tags"])]
+        assert got == q["result"] == co.search_chain_memories(g["blocks"], q["query"], q["search_content"], q["search_subject"], q["search_tags"]), q["query"]
+    for t in g["tags"]:
+        assert [idx[id(m)] for m in cs.search_by_tag(t["tag"])] == t["result"], t["tag"]
+    cs.close()
