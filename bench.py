@@ -380,7 +380,11 @@ def main():
                                 "sample": f"{args.cpu_sample} synthetic records x 32 single-pattern passes (oracle port of search.py:244-335, match-only), {dt:.1f} s",
                                 "host_cores_available": usable_cores(), "host_cores_reported": os.cpu_count()}
         if not args.no_extra:
-            line["extra"] = run_extra(args, corpus, st, peak, lib, _abi)
+            try:
+                line["extra"] = run_extra(args, corpus, st, peak, lib, _abi)
+            except Exception as e:                                 # an extra must not cost the headline line
+                import traceback
+                line["extra"] = {"error": f"{type(e).__name__}: {e}", "traceback": traceback.format_exc()[-1500:]}
     if dist:
         lib.fei_comm_destroy()
         dist.destroy_process_group()
@@ -809,14 +813,14 @@ def run_extra(args, corpus, st, peak, lib, _abi):
     ch2 = C.c_void_p()
     _abi.check(lib.fei_chain_create(C.byref(ch2)))
     _abi.check(lib.fei_chain_synth(ch2, CHAIN_SEED, 0, nb_api, -1))
-    hh = np.zeros(64 * nb_api, dtype=np.uint8); ph = np.zeros(64 * nb_api, dtype=np.uint8); moff = np.zeros(nb_api + 1, dtype=np.uint64)
-    _abi.check(lib.fei_chain_fetch(ch2, 0, nb_api, None, 0, _abi.ptr(moff), _abi.ptr(hh), _abi.ptr(ph)))
+    hh = np.zeros(64 * nb_api, dtype=np.uint8); moff = np.zeros(nb_api + 1, dtype=np.uint64)
+    _abi.check(lib.fei_chain_fetch(ch2, 0, nb_api, None, 0, _abi.ptr(moff), _abi.ptr(hh), None))
     lib.fei_chain_destroy(ch2)
-    hashes = hh.tobytes().decode(); prevs = ph.tobytes().decode()
+    hashes = hh.tobytes().decode()
     t0 = time.perf_counter()
     blocks = []                                                            # reference-shaped MemoryBlock objects (plain instance attributes)
     for i, sp in enumerate(synth.chain_specs(CHAIN_SEED, 0, nb_api)):
-        b = mc.MemoryBlock(sp["index"], sp["timestamp"], sp["memory_data"], "0" if i == 0 else prevs[64 * i:64 * i + 64], sp["responsible_node"], sp["proposer_node"])
+        b = mc.MemoryBlock(sp["index"], sp["timestamp"], sp["memory_data"], "0" if i == 0 else hashes[64 * i - 64:64 * i], sp["responsible_node"], sp["proposer_node"])
         b.hash = hashes[64 * i:64 * i + 64]
         blocks.append(b)
     objects_s = time.perf_counter() - t0
