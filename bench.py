@@ -620,6 +620,7 @@ def api_on_disk(n_files: int):
         with contextlib.redirect_stdout(sink):
             t0 = time.perf_counter(); cold = gsearch.search_memories(q); cold_s = time.perf_counter() - t0
             pm = packer.packed()
+            cold_stages = dict(pm.timing)
             warm, warm0 = [], []
             for _ in range(5):
                 t0 = time.perf_counter(); res = gsearch.search_memories(q); warm.append(time.perf_counter() - t0)
@@ -648,7 +649,7 @@ def api_on_disk(n_files: int):
         assert len(cold) == len(res) and len(res2) == len(res) + 1 and len(res3) == len(res2)
         assert [m["filename"] for m in sub] == [mems[i]["filename"] for i in want], "API result differs from the oracle on the sub-tree"
         return {"files": n_files, "write_tree_s": write_s, "query": "content matches kubernetes.*docker|docker.*kubernetes AND Tags has_tag python (with_content)",
-                "search_memories_cold_s": cold_s, "search_memories_warm_ms": float(np.median(warm)) * 1e3, "hits": len(res),
+                "search_memories_cold_s": cold_s, "cold_stages": cold_stages, "search_memories_warm_ms": float(np.median(warm)) * 1e3, "hits": len(res),
                 "search_memories_warm_no_hits_ms": float(np.median(warm0)) * 1e3,
                 "materialisation_ms_per_1k_hits": (float(np.median(warm)) - float(np.median(warm0))) * 1e3 / max(1, len(res)) * 1000,
                 "apply_filters_default_dry_run_first_ms": filt_first_s * 1e3, "apply_filters_default_dry_run_warm_ms": filt_s * 1e3,

@@ -82,21 +82,42 @@ extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
   while (struct dirent* de = readdir(d)) {
     const char* nm = de->d_name;
     if (nm[0] == '.' && (nm[1] == 0 || (nm[1] == '.' && nm[2] == 0))) continue;
-    Ent e; e.ts = 0; e.f8 = 0; e.nf = 0; memset(e.sp, 0, sizeof(e.sp));
+    Ent e; e.ts = 0; e.f8 = 0; e.nf = 0; e.wall = 0; e.ino = 0; e.size = 0; e.mtime = -1; memset(e.sp, 0, sizeof(e.sp));
     const size_t len = strlen(nm);
     const int st = parse_name(nm, len, &e.ts, e.sp, &e.f8, &e.nf);
     if (st == 0) continue;
     e.st = (uint8_t)st; e.name.assign(nm, len);
-    struct stat sb;
-    if (fstatat(dfd, nm, &sb, 0) != 0) { e.ino = 0; e.size = 0; e.mtime = -1; e.st = 2; }          // vanished / unreadable: Python reports it
-    else { e.ino = sb.st_ino; e.size = (uint64_t)sb.st_size; e.mtime = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec; }
-    e.wall = 0;
-    if (e.st == 1) {                                               // datetime.fromtimestamp(ts): naive local wall clock (utils.py:94)
-      time_t tt = (time_t)e.ts; struct tm tmv;
-      if (!localtime_r(&tt, &tmv) || tmv.tm_year + 1900 > 9999) e.st = 2;
-      else e.wall = (int64_t)timegm(&tmv);
-    }
     ents.push_back(std::move(e));
+  }
+  {
+    // stat + local-time conversion of every entry, in parallel (a million fstatat calls are the cold listing's cost)
+    const size_t total = ents.size();
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 32) nt = 32;
+    if (nt < 1 || total < 4096) nt = 1;
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        const size_t i0 = next.fetch_add(512);
+        if (i0 >= total) break;
+        const size_t i1 = i0 + 512 < total ? i0 + 512 : total;
+        for (size_t i = i0; i < i1; ++i) {
+          Ent& e = ents[i];
+          struct stat sb;
+          if (fstatat(dfd, e.name.c_str(), &sb, 0) != 0) { e.st = 2; }                   // vanished / unreadable: Python reports it
+          else { e.ino = sb.st_ino; e.size = (uint64_t)sb.st_size; e.mtime = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec; }
+          if (e.st == 1) {                                           // datetime.fromtimestamp(ts): naive local wall clock (utils.py:94)
+            time_t tt = (time_t)e.ts; struct tm tmv;
+            if (!localtime_r(&tt, &tmv) || tmv.tm_year + 1900 > 9999) e.st = 2;
+            else e.wall = (int64_t)timegm(&tmv);
+          }
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
   }
   closedir(d);
   // newest first, ties in readdir order (utils.py:251: sort(key=timestamp, reverse=True) is stable); entries Python must judge go last
@@ -126,7 +147,8 @@ extern "C" int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v) {
 extern "C" void fei_dirlist_free(fei_dirlist* l) { delete l; }
 
 // Reads n files of one directory into dst at dst_off[i] (capacity dst_off[i+1] - dst_off[i]): `threads` workers, open + pread +
-// close each.  got[i] = bytes read (a file that grew is cut at its capacity and flagged), err[i] = errno or 0.
+// close each.  got[i] = bytes read (a file that grew since it was listed is cut at the listed size: its new (size, mtime) makes the
+// next sync read it again), err[i] = errno or 0.
 extern "C" int fei_read_files(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* dst, const uint64_t* dst_off,
                               int threads, uint64_t* got, int32_t* err) {
   if (!dir || (n && (!names || !name_off || !dst || !dst_off || !got || !err))) { set_error("null argument"); return FEI_E_BADARG; }
@@ -154,7 +176,6 @@ extern "C" int fei_read_files(const char* dir, const uint8_t* names, const uint6
           if (r == 0) break;
           done += (uint64_t)r;
         }
-        if (!err[i] && done == cap) { char probe; if (pread(fd, &probe, 1, (off_t)done) == 1) err[i] = EFBIG; }      // grew since it was listed
         got[i] = done;
         close(fd);
       }

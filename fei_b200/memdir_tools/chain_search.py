@@ -33,17 +33,14 @@ class ChainMemorySearch:
         n = len(self.memories)
         vals: List[bytes] = []
         self.genesis = np.zeros(n, dtype=bool)
-        sigma = False
         for i, m in enumerate(self.memories):
             headers = m.get("headers", {})
             trio = (headers.get("Subject", ""), headers.get("Tags", ""), m.get("content", ""))
             for name, v in zip(_FIELDS, trio):
                 if not isinstance(v, str):
                     raise NotImplementedError(f"block {i}: {name} is a {type(v).__name__}; the reference calls .lower() on it (str only)")
-                sigma = sigma or "Σ" in v
                 vals.append(v.encode("utf-8", "surrogatepass"))
             self.genesis[i] = m.get("metadata", {}).get("unique_id", "") == "genesis"
-        self.has_sigma = sigma
         k = 3 * n
         body_off = np.zeros(k + 1, dtype=np.uint64)
         if k:
@@ -61,9 +58,6 @@ class ChainMemorySearch:
 
     def _field_hits(self, pattern: Pattern) -> np.ndarray:
         """bool[n, 3]: which of (Subject, Tags, content) of each block satisfies the pattern."""
-        if self.has_sigma and ("σ" in pattern.text or "ς" in pattern.text):
-            raise NotImplementedError("the chain's memories hold a capital sigma and the query contains a sigma: str.lower() picks the "
-                                      "final or medial form from the context; refused rather than answered inexactly")
         if self.n == 0:
             return np.zeros((0, 3), dtype=bool)
         pb = ProgramBuilder()

@@ -414,22 +414,8 @@ def _compile_date_header(field: str, op: str, v2: Any, pm) -> List[Any]:
 
 
 # ----------------------------------------------------------------------------- search
-_LOWER_KINDS = ("contains", "startswith", "endswith", "equals", "has_tag")
-
-
-def check_sigma(pm, conds: Sequence[Cond], ranges) -> None:
-    """str.lower() maps U+03A3 to a final or a medial sigma depending on its neighbours (search.py:148-163 read values through
-    lower()); every other character, U+0130's two-character expansion included, is modelled exactly by the automata.  A needle
-    without any sigma cannot tell the two forms apart, so only a sigma-bearing needle over records that hold U+03A3 is refused."""
-    risky = [c for c in conds if c.pattern is not None and c.pattern.kind in _LOWER_KINDS and ("σ" in c.pattern.text or "ς" in c.pattern.text)]
-    if risky and pm.sigma_in(ranges):
-        raise NotImplementedError("the searched records hold a capital sigma and the operand contains a sigma: str.lower() picks the "
-                                  "final or medial form from the context; refused rather than answered inexactly")
-
-
 def _scan_ranges(pm, conds: List[Cond], ranges: List[Tuple[int, int]]) -> np.ndarray:
     """Ordered hit indices (pack order restricted / re-ordered to the requested segments)."""
-    check_sigma(pm, conds, ranges)
     pb = ProgramBuilder()
     pb.add_query(conds)
     hits = pm.scan_hits(pb.build(), 1)[0]

@@ -146,9 +146,6 @@ def search_memories(query: str, folders: List[str] = None, statuses: List[str] =
     with pm.lock:                                        # ranges, scan and materialisation from one corpus state
         ranges = pm.ranges(folders, statuses)
         pm.report_skipped(folders, statuses)
-        if ("σ" in low or "ς" in low) and pm.sigma_in(ranges):
-            raise NotImplementedError("the searched records hold a capital sigma and the query contains a sigma: str.lower() picks the "
-                                      "final or medial form from the context; refused rather than answered inexactly")
         pb = ProgramBuilder()
         pb.add_query([Cond(C_SLOT, pattern=Pattern("contains", low), field="", mode=2)])
         if not headers_only:

@@ -138,8 +138,10 @@ def list_dir(path: str) -> DirListing:
     return d
 
 
-def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray, List[Tuple[int, str]]]:
-    """Contents of the selected entries (all when sel is None): (raw blob, offsets[k+1], [(k, error message)])."""
+def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None, out: Optional[np.ndarray] = None, out_base: int = 0
+               ) -> Tuple[np.ndarray, np.ndarray, List[Tuple[int, str]]]:
+    """Contents of the selected entries (all when sel is None): (raw blob, offsets[k+1], [(k, error message)]).  With `out`, the
+    bytes land in out[out_base : out_base + sum(sizes)] (one buffer for a whole tree, no concatenation afterwards)."""
     if sel is None:
         names, name_off, sizes = d.names, d.name_off, d.size
     else:
@@ -151,15 +153,18 @@ def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None) -> Tu
     k = len(sizes)
     off = np.zeros(k + 1, dtype=np.uint64)
     np.cumsum(sizes, out=off[1:])
-    raw = np.empty(max(1, int(off[k])), dtype=np.uint8)
+    if out is None:
+        raw = np.empty(max(1, int(off[k])), dtype=np.uint8)
+    else:
+        raw = out[out_base:out_base + max(1, int(off[k]))]
     got = np.zeros(max(1, k), dtype=np.uint64)
     err = np.zeros(max(1, k), dtype=np.int32)
     nbuf = np.frombuffer(names, dtype=np.uint8) if names else np.zeros(1, dtype=np.uint8)
-    _abi.check(_abi.lib().fei_read_files(os.fsencode(path), _abi.ptr(nbuf), _abi.ptr(np.ascontiguousarray(name_off)), k, _abi.ptr(raw), _abi.ptr(off),
+    _abi.check(_abi.lib().fei_read_files(os.fsencode(path), _abi.ptr(nbuf), _abi.ptr(np.ascontiguousarray(name_off)), k, raw.ctypes.data, _abi.ptr(off),
                                         READ_THREADS, _abi.ptr(got), _abi.ptr(err)))
     problems: List[Tuple[int, str]] = []
     short = np.nonzero((err[:k] != 0) | (got[:k] != sizes))[0]
-    if len(short):                                                    # shrunk, grew or vanished between stat and read: read those again, one by one
+    if len(short):                                                    # shrunk or vanished between stat and read: read those again, one by one
         parts = [raw[int(off[i]):int(off[i + 1])].tobytes() for i in range(k)]
         for i in short.tolist():
             name = os.fsdecode(names[int(name_off[i]):int(name_off[i + 1])])
@@ -172,6 +177,9 @@ def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None) -> Tu
         off = np.zeros(k + 1, dtype=np.uint64)
         np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=k), out=off[1:])
         raw = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if off[k] else np.zeros(1, dtype=np.uint8)
+        if out is not None and int(off[k]) <= len(out) - out_base:      # keep the one-buffer layout when it still fits
+            out[out_base:out_base + int(off[k])] = raw[:int(off[k])]
+            raw = out[out_base:out_base + max(1, int(off[k]))]
     return raw, off, problems
 
 
@@ -249,7 +257,7 @@ class _Watcher:
 # ----------------------------------------------------------------------------- packed tree
 class _Seg:
     """Cached state of one (folder, status) directory: its listing + the device record id of every entry."""
-    __slots__ = ("listing", "dev", "mtime_ns", "bad")
+    __slots__ = ("listing", "dev", "mtime_ns", "bad", "bad_files")      # bad_files: name -> (inode, size, mtime) of files that could not be packed
 
 
 def _headers_of(text: str) -> Dict[str, str]:
@@ -293,23 +301,69 @@ class PackedMemdir:
         self.windows_packed = 0                              # 4096-record windows (re)tiled by the last sync
         self.full_packs = 0
         self.snapshot_gbs: Optional[float] = None
+        self.timing: Dict[str, float] = {}               # stage times of the last full pack
         self.watcher = _Watcher()
         self.last_full_check = 0.0
         self._field_values: Dict[str, Tuple[np.ndarray, np.ndarray, List[str]]] = {}
         self.parsed_dates: Dict[str, Tuple[Any, bool]] = {}
         self._aux_next = 0
         self._seg_index: Optional[Tuple[List[Tuple[str, str]], np.ndarray]] = None
+        self._walk_cache: Optional[List[str]] = None
+        self._tree_dirty = True
+        self._tree_dirs: List[str] = []
 
     # ---- tree walk
     def _walk(self) -> List[str]:
-        out = []
-        for root, dirs, _ in os.walk(self.base):
-            if any(st in dirs for st in U.STANDARD_FOLDERS):
-                rel = os.path.relpath(root, self.base)
-                out.append("" if rel == "." else rel)
+        """get_memdir_folders (utils.py:43-57): every directory that directly contains a cur / new / tmp child, in os.walk order
+        (top-down, children in scandir order).  os.walk would also list the million files inside cur / new / tmp on every call;
+        a Maildir status directory without sub-directories (st_nlink == 2) cannot contain a folder and is not descended into.
+        With inotify on every directory of the tree, an unchanged tree is not walked at all."""
+        if self._walk_cache is not None and self.watcher.ok and not self._tree_dirty:
+            return list(self._walk_cache)
+        out: List[str] = []
+        self._tree_dirs: List[str] = []
+        ok_watch = True
+
+        def visit(path: str, rel: str) -> None:
+            nonlocal ok_watch
+            try:
+                with os.scandir(path) as it:
+                    entries = list(it)
+            except OSError:
+                return
+            ok_watch = self.watcher.watch(path) and ok_watch
+            self._tree_dirs.append(path)
+            dirs = []
+            for e in entries:
+                try:
+                    if e.is_dir():                                       # os.walk follows symlinks for the test, not for the descent
+                        dirs.append(e)
+                except OSError:
+                    pass
+            names = {e.name for e in dirs}
+            if any(st in names for st in U.STANDARD_FOLDERS):
+                out.append(rel)
+            for e in dirs:
+                if e.is_symlink():
+                    continue
+                if e.name in U.STANDARD_FOLDERS and names & set(U.STANDARD_FOLDERS):
+                    try:
+                        if os.stat(e.path).st_nlink == 2:                # no sub-directories inside this status directory
+                            continue
+                    except OSError:
+                        continue
+                visit(e.path, e.name if rel == "" else os.path.join(rel, e.name))
+
+        visit(self.base, "")
         if len(out) > 65535:
             raise NotImplementedError("more than 65535 folders")
+        self._walk_cache = list(out) if ok_watch else None
+        self._tree_dirty = False
         return out
+
+    def _tree_dir_set(self) -> set:
+        status_dirs = {self._dir(f, st) for f in self.folders for st in U.STANDARD_FOLDERS}
+        return set(self._tree_dirs) - status_dirs
 
     def _dir(self, folder: str, st: str) -> str:
         return os.path.join(self.base, folder, st) if folder else os.path.join(self.base, st)
@@ -322,8 +376,10 @@ class PackedMemdir:
         """Bring the packed corpus up to date with the tree.  Cheap when nothing changed: one os.walk over the folder tree, one
         stat per cur/new/tmp directory and a drain of the inotify queue."""
         with self.lock:
-            folders = self._walk()
             dirty_paths = self.watcher.drain()
+            if dirty_paths is None or any(p in self._tree_dir_set() for p in dirty_paths):
+                self._tree_dirty = True                                # a directory was created / removed / renamed somewhere in the folder tree
+            folders = self._walk()
             now = time.monotonic()
             recheck = float(os.environ.get("FEI_REVALIDATE_S", "1.0"))
             full_check = self.corpus is None or (dirty_paths is None and now - self.last_full_check >= recheck)
@@ -380,26 +436,39 @@ class PackedMemdir:
         self._set_folders(folders)
         order = self._order()
         segs: Dict[Tuple[str, str], _Seg] = {}
-        raws: List[np.ndarray] = []
-        sizes: List[np.ndarray] = []
-        files = total = 0
-        for key in order:
+        t0 = time.perf_counter()
+        total = 0
+        for key in order:                                              # 1. list every directory (readdir + parallel stat, native)
             listing, mt = self._list(*key)
-            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.dev = np.zeros(listing.n, dtype=np.int64)
+            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.zeros(listing.n, dtype=np.int64)
             segs[key] = seg
-            if listing.n:
-                raw, off, problems = read_files(self._dir(*key), listing)
-                seg.bad.extend(msg for _i, msg in problems)
-                raws.append(raw[:int(off[-1])]); sizes.append((off[1:] - off[:-1]).astype(np.int64)); files += listing.n
-                total += int(off[-1])
-                if total > MAX_RAW_BATCH:
-                    raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
-        self.files_read = files
-        n = files
-        raw = np.concatenate(raws) if raws else np.zeros(1, dtype=np.uint8)
+            total += int(listing.size.sum())
+        if total > MAX_RAW_BATCH:
+            raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
+        t1 = time.perf_counter()
+        n = sum(segs[k].listing.n for k in order)
+        raw = np.empty(max(1, total), dtype=np.uint8)                  # 2. read every file into ONE buffer (native threads), directory by directory
         raw_off = np.zeros(n + 1, dtype=np.uint64)
-        if n:
-            np.cumsum(np.concatenate(sizes), out=raw_off[1:])
+        pos = base_off = 0
+        exact = True
+        for key in order:
+            L = segs[key].listing
+            if not L.n:
+                continue
+            r, off, problems = read_files(self._dir(*key), L, out=raw if exact else None, out_base=base_off)
+            segs[key].bad.extend(msg for _i, msg in problems)
+            if exact and r.base is not raw and r is not raw and int(off[-1]) and not np.shares_memory(r, raw):
+                exact = False                                          # a file changed size under us: fall back to pieces
+                pieces = [raw[:base_off].copy()]
+            if not exact:
+                pieces.append(r[:int(off[-1])].copy())
+            raw_off[pos + 1:pos + L.n + 1] = off[1:] + np.uint64(base_off)
+            pos += L.n; base_off += int(off[-1])
+        if not exact:
+            raw = np.concatenate(pieces) if pieces else np.zeros(1, dtype=np.uint8)
+        self.files_read = n
+        t2 = time.perf_counter()
+        self.timing = {"list_s": t1 - t0, "read_s": t2 - t1}
         corpus = Corpus()
         keep = np.ones(n, dtype=bool)
         while True:
@@ -411,7 +480,9 @@ class PackedMemdir:
             for j in alive[~valid].tolist():                           # undecodable files: reported and skipped (utils.py:247-248)
                 keep[j] = False
                 key, i = self._locate(segs, order, j)
-                segs[key].bad.append(f"Error processing {segs[key].listing.name(i)}: {_decode_error(raw[int(raw_off[j]):int(raw_off[j + 1])].tobytes())}")
+                L = segs[key].listing
+                segs[key].bad.append(f"Error processing {L.name(i)}: {_decode_error(raw[int(raw_off[j]):int(raw_off[j + 1])].tobytes())}")
+                segs[key].bad_files[L.name_bytes(i)] = (int(L.ino[i]), int(L.size[i]), int(L.mtime_ns[i]))
         pos = start = 0
         for key in order:                                              # drop the skipped entries from the listings; device id = listing position
             seg = segs[key]
@@ -428,7 +499,9 @@ class PackedMemdir:
         self.delta_raw = []
         self.windows_packed = (corpus.n + 4095) // 4096
         self.full_packs += 1
+        t3 = time.perf_counter()
         self._rebuild_listing()
+        self.timing.update({"pack_s": t3 - t2, "listing_arrays_s": time.perf_counter() - t3, "files": n, "raw_bytes": int(raw_off[n])})
         for c in (old, old_delta):
             if c is not None:
                 c.close()
@@ -488,9 +561,14 @@ class PackedMemdir:
         for key in changed:
             old = self.segs.get(key)
             listing, mt = self._list(*key)
-            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.dev = np.full(listing.n, -1, dtype=np.int64)
+            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.full(listing.n, -1, dtype=np.int64)
             fresh[key] = seg
-            if old is not None and old.listing.n:
+            if (old is not None and old.listing.n == listing.n and old.listing.names == listing.names
+                    and np.array_equal(old.listing.key(), listing.key())):
+                seg.dev = old.dev                                      # same names, same (inode, size, mtime): nothing to do here
+                if old.bad:
+                    seg.bad.extend(m for m in old.bad if m not in seg.bad and self._bad_still_there(key, m, listing))
+            elif old is not None and old.listing.n:
                 old_names = {old.listing.name_bytes(i): i for i in range(old.listing.n)}
                 ok_, nk_ = old.listing.key(), listing.key()
                 used = np.zeros(old.listing.n, dtype=bool)
@@ -498,15 +576,19 @@ class PackedMemdir:
                     j = old_names.get(listing.name_bytes(i))
                     if j is not None and ok_[j] == nk_[i]:
                         seg.dev[i] = old.dev[j]; used[j] = True
+                for i in np.nonzero(seg.dev < 0)[0].tolist():          # a file already known to be unpackable, unchanged: stays out, stays reported
+                    nb = listing.name_bytes(i)
+                    if old.bad_files.get(nb) == (int(nk_[i]["ino"]), int(nk_[i]["size"]), int(nk_[i]["mtime"])):
+                        seg.dev[i] = -2; seg.bad_files[nb] = old.bad_files[nb]
                 for j in np.nonzero(~used)[0].tolist():
                     rem_dev.append(int(old.dev[j])); rem_key.append((int(ok_[j]["ino"]), int(ok_[j]["size"]), int(ok_[j]["mtime"])))
                 if old.bad:                                            # undecodable files that did not change stay reported without being read again
                     seg.bad.extend(m for m in old.bad if m not in seg.bad and self._bad_still_there(key, m, listing))
-                if not used.all() or (seg.dev < 0).any() or not np.array_equal(old.dev, seg.dev):
+                if not used.all() or (seg.dev == -1).any() or not np.array_equal(old.dev, seg.dev[seg.dev != -2]):
                     any_change = True
             elif listing.n:
                 any_change = True
-            todo = np.nonzero(seg.dev < 0)[0]
+            todo = np.nonzero(seg.dev == -1)[0]
             if len(todo):
                 new_entries.append((key, todo))
         if not any_change:                                             # only directory timestamps moved (or empty directories appeared)
@@ -515,6 +597,9 @@ class PackedMemdir:
                     self.segs[key].mtime_ns = seg.mtime_ns
                     self.segs[key].bad = seg.bad
                 else:
+                    if (seg.dev < 0).any():
+                        sel = np.nonzero(seg.dev >= 0)[0]
+                        seg.listing = _subset(seg.listing, sel); seg.dev = seg.dev[sel]
                     self.segs[key] = seg
             self.files_read = 0
             self.windows_packed = 0
@@ -527,7 +612,6 @@ class PackedMemdir:
         moved_from: List[int] = []
         moved_to: List[Tuple[Tuple[str, str], int]] = []
         to_read: List[Tuple[Tuple[str, str], np.ndarray]] = []
-        known_bad = {m for seg in fresh.values() for m in seg.bad}
         for key, todo in new_entries:
             L = fresh[key].listing
             nk_ = L.key()
@@ -536,8 +620,6 @@ class PackedMemdir:
                 d = rem_map.pop((int(nk_[i]["ino"]), int(nk_[i]["size"]), int(nk_[i]["mtime"])), None)
                 if d is not None:
                     moved_from.append(d); moved_to.append((key, i))
-                elif any(m.startswith(f"Error processing {L.name(i)}: ") for m in known_bad):
-                    fresh[key].dev[i] = -2                             # a file already known to be undecodable, unchanged
                 else:
                     still.append(i)
             if still:
@@ -579,6 +661,7 @@ class PackedMemdir:
                 kept.append(j)
             else:
                 seg.bad.append(f"Error processing {seg.listing.name(i)}: {_decode_error(raws[j])}")
+                seg.bad_files[seg.listing.name_bytes(i)] = (int(seg.listing.ino[i]), int(seg.listing.size[i]), int(seg.listing.mtime_ns[i]))
                 seg.dev[i] = -2
         for key in self._order():                                      # entries that could not be packed leave the listing
             seg = fresh.get(key) or self.segs.get(key)
@@ -872,7 +955,7 @@ class PackedMemdir:
             for a in ("name_off", "ts", "wall", "flags8", "spans", "ino", "size", "mtime_ns"):
                 setattr(L, a, z[f"s{k}_{a}"])
             L.n = len(L.ts); L.bad = []
-            seg = _Seg(); seg.listing = L; seg.dev = np.arange(pos, pos + L.n, dtype=np.int64); seg.mtime_ns = -2; seg.bad = [str(x) for x in z[f"s{k}_bad"]]
+            seg = _Seg(); seg.listing = L; seg.dev = np.arange(pos, pos + L.n, dtype=np.int64); seg.mtime_ns = -2; seg.bad = [str(x) for x in z[f"s{k}_bad"]]; seg.bad_files = {}
             pos += L.n
             pm.segs[key] = seg
         pm.corpus = Corpus()

@@ -323,9 +323,165 @@ def _lit_chain(n: Nfa, a: int, text: str, lowered: bool, end_half: bool = False,
     return states[-1]
 
 
-def add_pattern(n: Nfa, pid: int, pat: Pattern) -> None:
+_SIGMA = 0x3A3
+_PH = "\U0010FFFE"        # placeholder (a noncharacter) that marks a needle sigma inside the plain fragment
+_case_classes: Optional[Tuple[RangeSet, RangeSet]] = None
+
+
+def _case_class_sets() -> Tuple[RangeSet, RangeSet]:
+    """(case-ignorable, cased-and-not-ignorable) code point sets exactly as str.lower()'s final-sigma rule sees them
+    (Objects/unicodeobject.c handle_capital_sigma), obtained by asking str.lower() itself:
+    'A' + c + 'Σ' lowers to a final sigma iff c is case-ignorable or cased; c + 'Σ' iff c is cased and not ignorable."""
+    global _case_classes
+    if _case_classes is None:
+        ign, cased = [], []
+        for x in range(0x110000):
+            if 0xD800 <= x <= 0xDFFF:
+                continue
+            ch = chr(x)
+            alone = (ch + "Σ").lower()[-1] == "ς"
+            after = ("A" + ch + "Σ").lower()[-1] == "ς"
+            if alone:
+                cased.append(x)
+            elif after:
+                ign.append(x)
+        _case_classes = (_ranges_from_sorted(np.array(ign, dtype=np.int64)), _ranges_from_sorted(np.array(cased, dtype=np.int64)))
+    return _case_classes
+
+
+def _rs_and(a: RangeSet, b: RangeSet) -> RangeSet:
+    out = []
+    i = j = 0
+    while i < len(a) and j < len(b):
+        lo, hi = max(a[i][0], b[j][0]), min(a[i][1], b[j][1])
+        if lo <= hi:
+            out.append((lo, hi))
+        if a[i][1] < b[j][1]:
+            i += 1
+        else:
+            j += 1
+    return tuple(out)
+
+
+def _rs_not(a: RangeSet) -> RangeSet:
+    out = []
+    prev = 0
+    for lo, hi in a:
+        if lo > prev:
+            out.append((prev, lo - 1))
+        prev = hi + 1
+    if prev <= MAX_CP:
+        out.append((prev, MAX_CP))
+    return tuple(out)
+
+
+def _add_sigma_exact(n: Nfa, pid: int, pat: Pattern) -> None:
+    """Lower-casing pattern whose needle holds a sigma, exact over text with capital sigmas.  str.lower() turns U+03A3 into the
+    final form (U+03C2) iff it is preceded by a cased letter and not followed by one, case-ignorable characters skipped on both
+    sides.  The pattern's plain automaton is multiplied with that rule: every thread carries B = 'the text so far ends in a cased
+    letter (+ ignorables)' and a pending obligation about what must follow a capital sigma it consumed -- F (read as final: no cased
+    letter may follow) or M (read as medial: one must).  Reading a capital sigma as a needle character forks the two readings; the
+    wrong one dies when the following characters contradict it."""
+    f = Nfa()
+    add_pattern(f, 0, Pattern(pat.kind, pat.text.replace("σ", _PH + "s").replace("ς", _PH + "f"), pat.flags), _plain=True)   # placeholders, replaced below
+    ign, cased = _case_class_sets()
+    sig: RangeSet = ((_SIGMA, _SIGMA),)
+    not_sig = _rs_not(sig)
+    classes = {"I": _rs_and(ign, not_sig), "C": _rs_and(cased, not_sig), "O": _rs_and(_rs_and(_rs_not(ign), _rs_not(cased)), not_sig)}
+    prod: Dict[Tuple[int, int, str], int] = {}
+
+    def P(q: int, b: int, ob: str) -> int:
+        k = (q, b, ob)
+        v = prod.get(k)
+        if v is None:
+            v = prod[k] = n.new()
+        return v
+
+    def resolve(ob: str, cls: str) -> Optional[str]:
+        if ob == "F":
+            return {"I": "F", "C": None, "O": ""}[cls]
+        if ob == "M":
+            return {"I": "M", "C": "", "O": None}[cls]
+        return ""
+
+    def next_b(b: int, cls: str) -> int:
+        return b if cls == "I" else 1 if cls == "C" else 0
+
+    # the fragment was built with two-character placeholders for the sigmas: (_PH, 's') = medial sigma, (_PH, 'f') = final sigma.
+    # Collapse each placeholder pair into one edge with a marker.
+    nul: RangeSet = ((ord(_PH), ord(_PH)),)
+    edges: Dict[int, List[Tuple[Any, int]]] = {q: [] for q in range(len(f.chars))}
+    for q in range(len(f.chars)):
+        for leaf_id, d in f.chars[q]:
+            S = f.leaves[leaf_id]
+            if S == nul:                                          # first half of a placeholder: look through to its second half
+                for leaf2, d2 in f.chars[d]:
+                    S2 = f.leaves[leaf2]
+                    edges[q].append(("sigma_medial" if any(lo <= ord("s") <= hi for lo, hi in S2) else "sigma_final", d2))
+            else:
+                edges[q].append((S, d))
+    mid_states = {d for q in range(len(f.chars)) for leaf_id, d in f.chars[q] if f.leaves[leaf_id] == nul}
+    terminal = {a for a in f.accept if not f.chars[a]}
+    for q in range(len(f.chars)):
+        if q in mid_states:
+            continue
+        for b in (0, 1):
+            for ob in ("", "F", "M"):
+                src = None
+                for S, d in edges[q]:
+                    if src is None:
+                        src = P(q, b, ob)
+                    if isinstance(S, str):                        # a needle sigma
+                        want_final = S == "sigma_final"
+                        lit: RangeSet = ((0x3C2, 0x3C2),) if want_final else ((0x3C3, 0x3C3),)       # the lower-case letter itself (cased, not ignorable)
+                        r = resolve(ob, "C")
+                        if r is not None:
+                            n.c(src, lit, P(d, 1, r))
+                            if want_final and b:                  # capital sigma read as final
+                                n.c(src, sig, P(d, 1, "F"))
+                            if not want_final:                    # capital sigma read as medial (certainly medial without a cased letter before it)
+                                n.c(src, sig, P(d, 1, "M" if b else ""))
+                        continue
+                    for cls, cset in classes.items():
+                        part = _rs_and(S, cset)
+                        r = resolve(ob, cls)
+                        if part and r is not None:
+                            n.c(src, part, P(d, next_b(b, cls), r))
+                    if any(lo <= _SIGMA <= hi for lo, hi in S):    # a capital sigma whose lowered form this edge does not care about
+                        r = resolve(ob, "C")
+                        if r is not None:
+                            n.c(src, sig, P(d, 1, r))
+                for d, cond in f.eps[q]:
+                    if src is None:
+                        src = P(q, b, ob)
+                    n.e(src, P(d, b, ob), cond)
+                    if cond:
+                        n.uses.add(cond)
+                if q in f.accept:
+                    here = P(q, b, ob)
+                    if ob == "":
+                        n.accept[here] = pid
+                        if q in f.end_only:
+                            n.end_only.add(here)
+                    elif ob == "F":                               # fine if the text ends here
+                        n.accept[here] = pid; n.end_only.add(here)
+                    if q in terminal and ob:                      # matched, the last sigma's reading still to be confirmed by what follows
+                        for cls, cset in classes.items():
+                            r = resolve(ob, cls)
+                            if r is not None:
+                                n.c(here, cset, P(q, next_b(b, cls), r))
+                        r = resolve(ob, "C")
+                        if r is not None:
+                            n.c(here, sig, P(q, 1, r))
+    n.e(n.start, P(f.start, 0, ""))
+
+
+def add_pattern(n: Nfa, pid: int, pat: Pattern, _plain: bool = False) -> None:
     """Attach pattern `pid` to the union NFA.  `n.start` is the global start (position 0 only)."""
     k = pat.kind
+    if not _plain and k in ("contains", "startswith", "endswith", "equals", "has_tag") and ("\u03c3" in pat.text or "\u03c2" in pat.text):
+        _add_sigma_exact(n, pid, pat)
+        return
     if k == "regex":
         ast = _P.parse(pat.text, pat.flags)           # re.error propagates to the caller
         flags = ast.state.flags

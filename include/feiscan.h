@@ -130,7 +130,7 @@ int fei_dir_list(const char* path, fei_dirlist** out);
 int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v);
 void fei_dirlist_free(fei_dirlist* l);
 /* n files of one directory read by `threads` workers into dst[dst_off[i] .. dst_off[i+1]) (capacities from the listing's sizes);
- * got[i] = bytes read, err[i] = errno (EFBIG: the file grew since it was listed).  dst may be pinned (fei_host_register).     */
+ * got[i] = bytes read (at most the listed size), err[i] = errno.  dst may be pinned (fei_host_register).                          */
 int fei_read_files(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* dst, const uint64_t* dst_off,
                    int threads, uint64_t* got, int32_t* err);
 /* tooling: write n files into an existing directory with `threads` workers (synthetic trees for tests and the bench).          */

@@ -113,6 +113,12 @@ QUERIES = [
     ("idot_tag", [("Tags", "has_tag", "\u0130zmir")], False, None, None),
     ("idot_content", [("content", "contains", "i\u0307 in")], True, None, None),
     ("sigma_free_needle", [("Subject", "contains", "\u03bf\u03c6\u03b9\u03b1")], False, None, None),
+    # capital sigma lowers to the final form only after a cased letter and before a non-cased one (case-ignorables skipped)
+    ("sigma_medial_at_word_start", [("Subject", "contains", "\u03c3\u03bf\u03c6\u03b9\u03b1")], False, None, None),
+    ("sigma_final_needle_start", [("Subject", "contains", "\u03c2\u03bf\u03c6")], False, None, None),
+    ("sigma_final_in_body", [("content", "contains", "\u03b5\u03c5\u03c2")], True, None, None),
+    ("sigma_medial_not_final", [("content", "contains", "\u03b5\u03c5\u03c3")], True, None, None),
+    ("sigma_double", [("content", "endswith", "\u03c3\u03c3\u03b5\u03c5\u03c2 too\nreact")], True, None, None),
 ]
 
 RAISING = [

@@ -68,16 +68,18 @@ def test_raising_query_raises_the_first_reached_records_error(api):
     assert str(got.value) == str(want.value)
 
 
-def test_sigma_needle_over_capital_sigma_records_is_refused_not_guessed(api):
-    """str.lower() turns U+03A3 into a final or medial sigma depending on its neighbours: the one case the automata do not model.
-    Only a needle that itself holds a sigma can see the difference, and only where such records are searched."""
+def test_capital_sigma_lowers_by_context(api):
+    """str.lower() turns U+03A3 into a final or a medial sigma depending on its neighbours; the automata of sigma-bearing needles
+    carry that rule (regexc._add_sigma_exact), so nothing is refused and nothing is guessed."""
     from fei_b200.memdir_tools.search import search_memories
-    q = _query([("Subject", "contains", "\u03c3\u03bf\u03c6\u03b9\u03b1")], False)
-    with pytest.raises(NotImplementedError):
-        search_memories(q)
-    assert search_memories(q, folders=[".Projects/Python"]) == []          # no capital sigma in the searched records: answered
-    hit = search_memories(_query([("Subject", "contains", "\u03bf\u03c6\u03b9\u03b1")], False))
-    assert [m["metadata"]["unique_id"] for m in hit] == ["adv00020"]      # sigma-free needle over the same record: exact
+    base, g = api
+    mems = mo.listing(base, None, None, True)
+    for field, needle in (("Subject", "σοφια"), ("Subject", "ςοφια"), ("content", "ευς"), ("content", "ευσ"), ("content", "σσ"), ("content", "σς")):
+        for op in ("contains", "endswith", "startswith", "="):
+            conds = [(field, op, needle)]
+            want = [key_of(mems[i]) for i in mo.run_search(mems, [{"field": f, "operator": o, "value": v} for f, o, v in conds])]
+            got = [key_of(m) for m in search_memories(_query(conds, True))]
+            assert got == want, (field, op, needle)
 
 
 def test_sort_and_pagination(api):

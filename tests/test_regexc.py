@@ -60,7 +60,7 @@ def test_unsupported_constructs_raise():
         compile_patterns([Pattern("regex", r"(unclosed", re.IGNORECASE)])
 
 
-LOWER_OK = lambda s: "Σ" not in s        # capital sigma: its lower() depends on the neighbours; every other character is modelled exactly
+LOWER_OK = lambda s: True               # capital sigma and dotted capital I included: both are modelled exactly
 
 
 def test_lowercase_string_operators():
@@ -70,7 +70,7 @@ def test_lowercase_string_operators():
         d = compile_patterns([Pattern("contains", nl), Pattern("startswith", nl), Pattern("endswith", nl), Pattern("equals", nl), Pattern("has_tag", nl)])
         for v in VALUES:
             if not LOWER_OK(v):
-                continue                     # capital sigma: flagged at pack time (FEI_REC_HAS_SIGMA), refused only for needles that hold a sigma
+                continue
             m = d.run(v.encode("utf-8"))
             vl = v.lower()
             assert bool(m & 1) == (nl in vl), ("contains", nd, v)
@@ -98,6 +98,26 @@ def test_dotted_capital_i_lowers_to_two_characters():
             assert bool(m & 4) == vl.endswith(nl), ("endswith", nl, v)
             assert bool(m & 8) == (vl == nl), ("equals", nl, v)
             assert bool(m & 16) == (nl in [t.strip() for t in vl.split(",")]), ("has_tag", nl, v)
+
+
+def test_capital_sigma_final_form_rule():
+    """'Σ'.lower() is 'ς' after a cased letter and before a non-cased one (case-ignorable characters skipped), else 'σ':
+    needles that hold a sigma get the product automaton of regexc._add_sigma_exact."""
+    import random
+    rnd = random.Random(11)
+    alpha = ["σ", "ς", "Σ", "a", "A", "'", "\u0307", ".", " ", ",", "\u0130", "ο", "Ο", "1", "i"]
+    for kind in ("contains", "startswith", "endswith", "equals", "has_tag"):
+        for _ in range(40):
+            nl = "".join(rnd.choice(alpha) for _ in range(rnd.randint(1, 4))).lower()
+            if "σ" not in nl and "ς" not in nl:
+                nl += rnd.choice("σς")
+            d = compile_patterns([Pattern(kind, nl)])
+            for _ in range(40):
+                v = "".join(rnd.choice(alpha) for _ in range(rnd.randint(0, 8)))
+                vl = v.lower()
+                want = {"contains": nl in vl, "startswith": vl.startswith(nl), "endswith": vl.endswith(nl), "equals": vl == nl,
+                        "has_tag": nl in [t.strip() for t in vl.split(",")]}[kind]
+                assert bool(d.run(v.encode("utf-8")) & 1) == want, (kind, nl, v)
 
 
 def test_exact_and_ordering_operators():
