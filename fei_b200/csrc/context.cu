@@ -24,6 +24,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 int DevBuf::alloc(size_t n) {
+  (void)ctx();
   release();
   if (n == 0) return FEI_OK;
   cudaError_t e = cudaMalloc(&p, n);
@@ -42,7 +43,14 @@ void DevBuf::release() {
 }
 size_t total_device_bytes() { return g_dev_bytes.load(); }
 
-Context& ctx() { static Context c; return c; }
+/* The CUDA "current device" is per host thread: a worker thread of the caller (a thread pool loading batches, Flask's request
+ * threads) starts on device 0 whatever fei_init bound.  Every path that touches the device goes through ctx() or DevBuf::alloc, so
+ * this is where the calling thread is put on the bound device. */
+static inline void bind_thread(const Context& c) {
+  int d = -1;
+  if (c.ready && (cudaGetDevice(&d) != cudaSuccess || d != c.device)) cudaSetDevice(c.device);
+}
+Context& ctx() { static Context c; bind_thread(c); return c; }
 
 int require_ready() {
   if (!ctx().ready) { set_error("fei_init() has not been called (or failed): no CUDA device bound; there is no CPU path"); return FEI_E_CUDA; }

@@ -120,6 +120,26 @@ def main():
         print(f"[multi_gpu_check] flags + content query: scan+gather ok ({len(want)} hits)", flush=True)
     dist.barrier()
 
+    # the library is called from a worker thread of the caller (CUDA's current device is per thread: it must follow fei_init's)
+    import threading
+    box = {}
+
+    def worker():
+        try:
+            c2 = Corpus().synth(0xFE1, a, b - a)
+            pb2 = ProgramBuilder(); pb2.add_query([Cond(C_BODY, pattern=Pattern("regex", "python", re.IGNORECASE))])
+            box["got"] = c2.scan_hits(pb2.build(), 1)[0]
+            c2.close()
+        except Exception as e:  # noqa: BLE001
+            box["err"] = e
+    th = threading.Thread(target=worker); th.start(); th.join()
+    assert "err" not in box, box.get("err")
+    pb2 = ProgramBuilder(); pb2.add_query([Cond(C_BODY, pattern=Pattern("regex", "python", re.IGNORECASE))])
+    assert np.array_equal(box["got"], corpus.scan_hits(pb2.build(), 1)[0]), "scan from a worker thread"
+    if rank == 0:
+        print("[multi_gpu_check] calls from a worker thread land on the bound device: ok", flush=True)
+    dist.barrier()
+
     # range-sharded chain with a one-block halo; first failure = min over ranks
     nb, bad_at = 4000, 2777
     ch = C.c_void_p(); _abi.check(lib.fei_chain_create(C.byref(ch)))
