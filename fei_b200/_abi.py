@@ -90,6 +90,7 @@ _SIGS = {
     "fei_corpus_destroy": (C.c_int, [_P]),
     "fei_corpus_load": (C.c_int, [_P, _P]),
     "fei_corpus_load_raw": (C.c_int, [_P, _P, _P, _P, _P]),
+    "fei_corpus_last_load_timing": (C.c_int, [_P, _P]),
     "fei_corpus_synth": (C.c_int, [_P, _U64, _U64, _U64]),
     "fei_corpus_stats_get": (C.c_int, [_P, _P]),
     "fei_corpus_fetch": (C.c_int, [_P, _U64, _U64, _P, _U64, _P, _P, _U64, _P, _P, _P, _P, _P]),

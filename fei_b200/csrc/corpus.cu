@@ -121,6 +121,10 @@ __global__ void k_untile(const uint8_t* __restrict__ tiles, const uint64_t* __re
   }
 }
 
+int corpus_load_events(fei_corpus* c) {
+  for (auto& e : c->ev_load) if (!e) FEI_CUDA(cudaEventCreate(&e));
+  return FEI_OK;
+}
 cudaStream_t corpus_load_stream(fei_corpus* c) {
   if (!c->load_stream && cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->load_stream = nullptr; }
   return c->load_stream ? c->load_stream : ctx().copy_stream;
@@ -207,6 +211,7 @@ extern "C" int fei_corpus_destroy(fei_corpus* c) {
   cudaStreamSynchronize(ctx().stream);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->load_stream) { cudaStreamSynchronize(c->load_stream); cudaStreamDestroy(c->load_stream); }
+  for (auto& e : c->ev_load) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_chunk) if (e) cudaEventDestroy(e);
   if (c->ev_side) cudaEventDestroy(c->ev_side);

@@ -71,6 +71,8 @@ struct fei_corpus {
   cudaEvent_t ev[8] = {nullptr};
   // chunked scans: compaction / all-gather of a finished chunk run on `side` under the next chunk's scan (scan.cu)
   cudaStream_t side = nullptr;
+  cudaEvent_t ev_load[3] = {nullptr, nullptr, nullptr};   // load_raw: before / after the text copy, end of the pack kernels
+  bool load_timed = false; uint64_t load_raw_bytes = 0;
   cudaStream_t load_stream = nullptr;    // loads of this handle (H2D + pack kernels): own stream, so that batches streamed through several handles overlap
   cudaEvent_t ev_chunk[16] = {nullptr};
   cudaEvent_t ev_side = nullptr;
@@ -78,6 +80,7 @@ struct fei_corpus {
 
 namespace fei {
 // builds tiles from a canonical body blob already on the device (body has >= 32 bytes of slack)
+int corpus_load_events(fei_corpus* c);              // ev_load[], created on first use
 cudaStream_t corpus_load_stream(fei_corpus* c);   // created on first use; falls back to the context's copy stream
 int build_tiles(fei_corpus* c, const uint8_t* d_body, const uint64_t* d_body_off, cudaStream_t s);
 // builds the header directory from hdr / hdr_off already on the device (hdir.cu)

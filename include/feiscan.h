@@ -106,6 +106,10 @@ int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h);
  * nothing is loaded and FEI_E_BADARG is returned so the caller can drop them (the reference reports and skips
  * such files, utils.py:247-248) and call again.                                                                */
 int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out);
+/* Device-side stage times (ms) of the last fei_corpus_load_raw on this handle, CUDA events on its load stream:
+ * out[0] = host-to-device copy of the file text, out[1] = the pack kernels after it (measure, offsets, normalise, tiling,
+ * header directory), out[2] = that copy's rate in GB/s.  Waits for the load to finish on the device. */
+int fei_corpus_last_load_timing(fei_corpus* c, float* out);
 /* Fills the corpus with records [first, first+n) of the deterministic synthetic
  * Memdir (fei_b200/csrc/synth.cuh), generated on the GPU.                           */
 int fei_corpus_synth(fei_corpus* c, uint64_t seed, uint64_t first, uint64_t n);

@@ -318,7 +318,70 @@ def test_raw_ingest_matches_python_text_semantics(gpu):
         h = bytes(got["hdr"][int(got["hdr_off"][i]):int(got["hdr_off"][i + 1])])
         b = bytes(got["body"][int(got["body_off"][i]):int(got["body_off"][i + 1])])
         assert (h, b) == (want_h, want_b), raw
-        assert bool(bits[i] & 1) == (not sep) and bool(bits[i] & 2) == (not text.isascii()) and bool(bits[i] & 4) == ("İ" in text or "Σ" in text), raw
+        assert bool(bits[i] & 1) == (not sep) and bool(bits[i] & 2) == (not text.isascii()), raw
+        assert bool(bits[i] & 4) == ("Σ" in text) and bool(bits[i] & 8) == ("İ" in text), raw
+
+
+def test_raw_ingest_fuzz_long_records(gpu):
+    """Seeded fuzz of the warp-per-file ingest kernels on files long enough to span many 512-byte rows: multi-byte characters,
+    separators, "\r\n" pairs and whitespace runs land on every 16-byte / 512-byte boundary; a third of the files are then
+    corrupted (one byte overwritten, or cut inside a character) and must be reported exactly as bytes.decode("utf-8") would."""
+    import random
+    from fei_b200.corpus import Corpus
+    rng = random.Random(20260921)
+    toks = ["a", "word ", "--", "---", "-", "\r\n", "\r", "\n", " ", "\t", "\u00a0", "\u2003", "\u3000", "\x85", "é", "日本", "\U0001F409", "Σ", "ς", "İ", "x" * 37,
+            "Tags: a,b\n", "\r\n\r\n", " \r\n ", "\x1c", "ß", "-\r\n-"]
+    raws = []
+    for i in range(400):
+        target = rng.choice([0, 1, 15, 16, 17, 31, 33, 100, 511, 512, 513, 700, 1500, 3000, 6000])
+        parts, size = [], 0
+        if rng.random() < 0.3:
+            parts.append(rng.choice([" \r\n\t", "\r\n" * rng.randrange(1, 40), "\u2003" * rng.randrange(1, 200)]))
+        while size < target:
+            t = rng.choice(toks); parts.append(t); size += len(t.encode())
+        if rng.random() < 0.3:
+            parts.append(rng.choice(["\r\n" * rng.randrange(1, 300), " \u3000\r", "\n"]))
+        raw = "".join(parts).encode()
+        k = rng.random()
+        if raw and k < 0.2:
+            j = rng.randrange(len(raw)); raw = raw[:j] + bytes([rng.choice([0x80, 0xBF, 0xC0, 0xC1, 0xE0, 0xED, 0xF0, 0xF4, 0xF5, 0xFF, 0xA0, 0x9F])]) + raw[j + 1:]
+        elif raw and k < 0.33:
+            raw = raw[:rng.randrange(len(raw))]
+        raws.append(raw)
+    recs = []
+    for i, raw in enumerate(raws):
+        r = synth.record(11, i); r["raw"] = raw
+        recs.append(r)
+
+    def arrays(rs):
+        off = np.zeros(len(rs) + 1, dtype=np.uint64); np.cumsum([len(r["raw"]) for r in rs], out=off[1:])
+        base = synth.arrays_from_records(rs)
+        return {"n": len(rs), "raw": np.frombuffer(b"".join(r["raw"] for r in rs) or b"\0", dtype=np.uint8).copy(), "raw_off": off,
+                "ts": base["ts"], "wall": base["wall"], "flags8": base["flags8"], "fsb": base["fsb"]}
+
+    def decodes(raw):
+        try:
+            raw.decode("utf-8"); return True
+        except UnicodeDecodeError:
+            return False
+    c = Corpus()
+    valid = c.load_raw(arrays(recs)).tolist()
+    want_valid = [decodes(r) for r in raws]
+    assert valid == want_valid, [i for i in range(len(raws)) if valid[i] != want_valid[i]][:10]
+    assert 40 < sum(not v for v in want_valid) < 200
+    good = [r for r, v in zip(recs, want_valid) if v]
+    assert c.load_raw(arrays(good)).all()
+    got = c.fetch(0, len(good))
+    bits = (got["fsb"] >> 24).tolist()
+    for i, r in enumerate(good):
+        text = r["raw"].decode("utf-8").replace("\r\n", "\n").replace("\r", "\n")
+        head, sep, rest = text.partition("---")
+        want_h = (head if sep else "").encode(); want_b = (rest if sep else text).strip().encode()
+        h = bytes(got["hdr"][int(got["hdr_off"][i]):int(got["hdr_off"][i + 1])])
+        b = bytes(got["body"][int(got["body_off"][i]):int(got["body_off"][i + 1])])
+        assert (h, b) == (want_h, want_b), (i, r["raw"][:80])
+        assert bool(bits[i] & 1) == (not sep) and bool(bits[i] & 2) == (not text.isascii()), i
+        assert bool(bits[i] & 4) == ("Σ" in text) and bool(bits[i] & 8) == ("İ" in text), i
 
 
 def test_random_headers_differential(gpu):
