@@ -53,12 +53,16 @@ class Corpus:
             v = a.get(k)
             setattr(h, k, _abi.ptr(np.ascontiguousarray(v)) if v is not None else None)
         valid = np.zeros(max(1, h.n), dtype=np.uint8)
-        rc = _abi.lib().fei_corpus_load_raw(self._h, C.byref(h), _abi.ptr(a["raw"]), _abi.ptr(a["raw_off"]), _abi.ptr(valid))
+        if "raw_begin" in a:                                            # files anywhere in the buffer (fei_read_dir_packed's arena)
+            rc = _abi.lib().fei_corpus_load_raw_spans(self._h, C.byref(h), _abi.ptr(a["raw"]), int(a["raw_bytes"]), _abi.ptr(a["raw_begin"]),
+                                                      _abi.ptr(a["raw_len"]), _abi.ptr(valid))
+        else:
+            rc = _abi.lib().fei_corpus_load_raw(self._h, C.byref(h), _abi.ptr(a["raw"]), _abi.ptr(a["raw_off"]), _abi.ptr(valid))
         valid = valid[:h.n].astype(bool)
         if rc != 0 and valid.all():
             _abi.check(rc)
         if rc == 0:
-            self._keep = a
+            self._keep = None                  # every host array was consumed before the call returned (the text may be a transient arena)
             self.n, self.global_base = h.n, h.global_base
         return valid
 

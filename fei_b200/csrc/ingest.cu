@@ -70,13 +70,14 @@ struct Utf8State {
 };
 
 constexpr int kIngestThreads = 256;
-__global__ void __launch_bounds__(kIngestThreads) k_raw_measure(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, uint64_t n,
-                                                                 RawMeasure* __restrict__ out, uint32_t* __restrict__ hdr_len, uint32_t* __restrict__ body_len,
+// raw_len == nullptr: file i = raw[raw_off[i], raw_off[i+1]); else raw[raw_off[i], raw_off[i] + raw_len[i])
+__global__ void __launch_bounds__(kIngestThreads) k_raw_measure(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off,
+                                                                 const uint64_t* __restrict__ raw_len, uint64_t n, RawMeasure* __restrict__ out, uint32_t* __restrict__ hdr_len, uint32_t* __restrict__ body_len,
                                                                  unsigned long long* __restrict__ summary) {
   const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
-  const long long o0 = (long long)raw_off[i], o1 = (long long)raw_off[i + 1];
+  const long long o0 = (long long)raw_off[i], o1 = raw_len ? o0 + (long long)raw_len[i] : (long long)raw_off[i + 1];
   const long long a0 = o0 & ~15ll;
   bool bad = false, nonascii = false, sigma = false, idot = false, any_cr = false;
   long long sep = -1;                                  // offset of the first "---", warp-uniform
@@ -217,8 +218,8 @@ __device__ __forceinline__ void warp_copy_translated(uint8_t* __restrict__ dst, 
   }
 }
 
-__global__ void __launch_bounds__(kIngestThreads) k_raw_write(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off, uint64_t n,
-                                                               const RawMeasure* __restrict__ ms, const uint64_t* __restrict__ hdr_off,
+__global__ void __launch_bounds__(kIngestThreads) k_raw_write(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off,
+                                                               const uint64_t* __restrict__ raw_len, uint64_t n, const RawMeasure* __restrict__ ms, const uint64_t* __restrict__ hdr_off,
                                                                const uint64_t* __restrict__ body_off, uint8_t* __restrict__ hdr, uint8_t* __restrict__ body) {
   const uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kIngestThreads) k_raw_write(const uint8_t* __r
   const RawMeasure m = ms[i];
   if (!(m.flags & 1u)) return;
   const uint8_t* p = raw + raw_off[i];
-  const uint8_t* end = raw + raw_off[i + 1];
+  const uint8_t* end = raw_len ? p + raw_len[i] : raw + raw_off[i + 1];
   if (m.flags & 32u) {
     warp_copy_translated(hdr + hdr_off[i], p, m.hdr_raw_len, end, lane);
     warp_copy_translated(body + body_off[i], p + m.body_raw_begin, m.body_raw_end - m.body_raw_begin, end, lane);
@@ -250,7 +251,8 @@ using namespace fei;
 
 // All n files must be valid records to be loaded; the call first reports validity so the host can drop the
 // undecodable ones (and print the reference's message) and call again with the survivors.
-extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out) {
+static int load_raw_impl(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, uint64_t raw_bytes_in, const uint64_t* raw_off,
+                         const uint64_t* raw_len, uint8_t* valid_out) {
   if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
   std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(require_ready());
@@ -263,11 +265,14 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   cudaStream_t s = corpus_load_stream(c);
   uint64_t n = h->n;
   c->loaded = false;
-  uint64_t raw_bytes = n ? raw_off[n] : 0;
+  uint64_t raw_bytes = raw_len ? raw_bytes_in : (n ? raw_off[n] : 0);
+  if (raw_len)
+    for (uint64_t i = 0; i < n; ++i)
+      if (raw_off[i] > raw_bytes || raw_len[i] > raw_bytes - raw_off[i]) { set_error("record %llu: span outside the %llu raw bytes", (unsigned long long)i, (unsigned long long)raw_bytes); return FEI_E_BADARG; }
   c->load_raw_bytes = raw_bytes;
   FEI_TRY(corpus_load_events(c));
   DevBuf& d_raw = c->stage_raw; DevBuf& d_raw_off = c->stage_raw_off; DevBuf& d_ms = c->stage_ms; DevBuf& d_hlen = c->stage_hlen; DevBuf& d_blen = c->stage_blen;
-  FEI_TRY(d_raw.ensure(raw_bytes + 64)); FEI_TRY(d_raw_off.ensure((n + 1) * 8));
+  FEI_TRY(d_raw.ensure(raw_bytes + 64)); FEI_TRY(d_raw_off.ensure((n + 1) * 8 * (raw_len ? 2 : 1)));
   FEI_TRY(d_ms.ensure((n ? n : 1) * sizeof(RawMeasure) + 16)); FEI_TRY(d_hlen.ensure((n ? n : 1) * 4)); FEI_TRY(d_blen.ensure((n ? n : 1) * 4));
   // The small host arrays go first: a second handle's multi-GB text copy may already sit in the copy engine's queue when this load
   // reaches its tail, and anything this load still had to upload then would wait behind it (and the next load behind this one).
@@ -282,7 +287,14 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
     c->name_bytes = h->name_off[n];
     FEI_TRY(up(c->name, h->name, c->name_bytes)); FEI_TRY(up(c->name_off, h->name_off, (n + 1) * 8)); FEI_TRY(up(c->name_spans, h->name_spans, n * 8));
   } else { c->name.release(); c->name_off.release(); c->name_spans.release(); c->name_bytes = 0; }
-  FEI_CUDA(cudaMemcpyAsync(d_raw_off.p, raw_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  const uint64_t* d_len = nullptr;
+  if (raw_len) {                                                        // spans: n begins, then n lengths
+    if (n) FEI_CUDA(cudaMemcpyAsync(d_raw_off.p, raw_off, n * 8, cudaMemcpyHostToDevice, s));
+    if (n) FEI_CUDA(cudaMemcpyAsync(d_raw_off.as<uint64_t>() + n + 1, raw_len, n * 8, cudaMemcpyHostToDevice, s));
+    d_len = d_raw_off.as<uint64_t>() + n + 1;
+  } else {
+    FEI_CUDA(cudaMemcpyAsync(d_raw_off.p, raw_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+  }
   FEI_CUDA(cudaEventRecord(c->ev_load[0], s));
   if (raw_bytes) FEI_CUDA(cudaMemcpyAsync(d_raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, s));
   FEI_CUDA(cudaEventRecord(c->ev_load[1], s));
@@ -291,7 +303,7 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   FEI_CUDA(cudaMemsetAsync(d_summary, 0, 16, s));
   unsigned g = (unsigned)((n + 127) / 128);
   const unsigned gw = (unsigned)((n * 32 + kIngestThreads - 1) / kIngestThreads);       // one warp per file
-  if (n) k_raw_measure<<<gw, kIngestThreads, 0, s>>>(d_raw.as<uint8_t>(), d_raw_off.as<uint64_t>(), n, d_ms.as<RawMeasure>(), d_hlen.as<uint32_t>(), d_blen.as<uint32_t>(), d_summary);
+  if (n) k_raw_measure<<<gw, kIngestThreads, 0, s>>>(d_raw.as<uint8_t>(), d_raw_off.as<uint64_t>(), d_len, n, d_ms.as<RawMeasure>(), d_hlen.as<uint32_t>(), d_blen.as<uint32_t>(), d_summary);
   // offsets of the normalised pieces (computed before the validity verdict is known: one host round trip instead of two)
   FEI_TRY(c->hdr_off.ensure((n + 1) * 8));
   DevBuf& body_off = c->stage_body_off; DevBuf& body = c->stage_body;
@@ -320,7 +332,7 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   FEI_TRY(c->hdr.ensure(hb + 64)); FEI_TRY(body.ensure(bb + 64));
   FEI_CUDA(cudaMemsetAsync((uint8_t*)c->hdr.p + hb, 0, 48, s));
   FEI_CUDA(cudaMemsetAsync((uint8_t*)body.p + bb, 0, 48, s));
-  if (n) k_raw_write<<<gw, kIngestThreads, 0, s>>>(d_raw.as<uint8_t>(), d_raw_off.as<uint64_t>(), n, d_ms.as<RawMeasure>(), c->hdr_off.as<uint64_t>(), body_off.as<uint64_t>(),
+  if (n) k_raw_write<<<gw, kIngestThreads, 0, s>>>(d_raw.as<uint8_t>(), d_raw_off.as<uint64_t>(), d_len, n, d_ms.as<RawMeasure>(), c->hdr_off.as<uint64_t>(), body_off.as<uint64_t>(),
                                        c->hdr.as<uint8_t>(), body.as<uint8_t>());
   if (n) k_fix_fsb<<<g, 128, 0, s>>>(d_ms.as<RawMeasure>(), n, c->fsb.as<uint32_t>());
   FEI_CUDA(cudaGetLastError());
@@ -331,6 +343,16 @@ extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, cons
   c->loaded = true;
   c->load_timed = true;
   return FEI_OK;
+}
+
+extern "C" int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out) {
+  return load_raw_impl(c, h, raw, 0, raw_off, nullptr, valid_out);
+}
+extern "C" int fei_corpus_load_raw_spans(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, uint64_t raw_bytes, const uint64_t* begin,
+                                         const uint64_t* len, uint8_t* valid_out) {
+  if (h && h->n && (!begin || !len)) { set_error("null argument"); return FEI_E_BADARG; }
+  static const uint64_t none = 0;
+  return load_raw_impl(c, h, raw, raw_bytes, begin ? begin : &none, len ? len : &none, valid_out);
 }
 
 /* Device-side stage times of the last fei_corpus_load_raw on this handle (CUDA events on the load stream): out[0] = the text's

@@ -5,6 +5,7 @@
 #include "../../include/feiscan.h"
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cerrno>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +15,7 @@
 #include <vector>
 #include <dirent.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -68,7 +70,37 @@ int parse_name(const char* s, size_t len, int64_t* ts, uint16_t* spans, uint64_t
 
 }  // namespace
 
-extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
+// datetime.fromtimestamp(ts) as a naive wall clock, in seconds (timegm of the local broken-down time); false when Python would raise
+// (year > 9999).  localtime_r takes glibc's tz lock on every call, which serialises the listing threads, so the UTC offset is
+// cached per UTC day: a day whose 25 hourly samples agree has one offset (zone rules change on whole hours at the finest); any
+// other day (a DST switch) goes through localtime_r entry by entry.
+static bool wall_of_slow(int64_t ts, int64_t* wall) {
+  time_t tt = (time_t)ts; struct tm tmv;
+  if (!localtime_r(&tt, &tmv) || tmv.tm_year + 1900 > 9999) return false;
+  *wall = (int64_t)timegm(&tmv);
+  return true;
+}
+static bool wall_of(int64_t ts, int64_t* wall) {
+  struct Slot { int64_t day; int64_t off; int state; };            // state: 0 empty, 1 constant offset, 2 mixed
+  static thread_local Slot cache[64];
+  if (ts < 0 || ts > 253370764800ll) return wall_of_slow(ts, wall);  // before 1970 / the last weeks of year 9999: no shortcut
+  const int64_t day = ts / 86400;
+  Slot& sl = cache[day & 63];
+  if (sl.state == 0 || sl.day != day) {
+    sl.day = day; sl.state = 1; sl.off = 0;
+    for (int h = 0; h <= 24; ++h) {
+      int64_t w;
+      const int64_t t = day * 86400 + h * 3600;
+      if (!wall_of_slow(t, &w)) { sl.state = 2; break; }
+      if (h == 0) sl.off = w - t; else if (w - t != sl.off) { sl.state = 2; break; }
+    }
+  }
+  if (sl.state == 2) return wall_of_slow(ts, wall);
+  *wall = ts + sl.off;
+  return true;
+}
+
+static int dir_list(const char* path, bool want_stat, fei_dirlist** out) {
   if (!path || !out) { set_error("null argument"); return FEI_E_BADARG; }
   *out = nullptr;
   DIR* d = opendir(path);
@@ -77,6 +109,9 @@ extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
     set_error("opendir(%s): %s", path, strerror(errno)); return FEI_E_BADARG;
   }
   const int dfd = dirfd(d);
+  const bool timing = getenv("FEI_LIST_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   struct Ent { std::string name; int64_t ts, wall, mtime; uint64_t ino, size, f8; uint16_t sp[4]; uint8_t st; int64_t nf; };
   std::vector<Ent> ents;
   while (struct dirent* de = readdir(d)) {
@@ -86,9 +121,10 @@ extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
     const size_t len = strlen(nm);
     const int st = parse_name(nm, len, &e.ts, e.sp, &e.f8, &e.nf);
     if (st == 0) continue;
-    e.st = (uint8_t)st; e.name.assign(nm, len);
+    e.st = (uint8_t)st; e.name.assign(nm, len); e.ino = (uint64_t)de->d_ino;
     ents.push_back(std::move(e));
   }
+  const double t1 = now();
   {
     // stat + local-time conversion of every entry, in parallel (a million fstatat calls are the cold listing's cost)
     const size_t total = ents.size();
@@ -104,12 +140,11 @@ extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
         for (size_t i = i0; i < i1; ++i) {
           Ent& e = ents[i];
           struct stat sb;
-          if (fstatat(dfd, e.name.c_str(), &sb, 0) != 0) { e.st = 2; }                   // vanished / unreadable: Python reports it
+          if (!want_stat) {}                                                             // fei_read_dir_packed fills size / mtime from the open file
+          else if (fstatat(dfd, e.name.c_str(), &sb, 0) != 0) { e.st = 2; }              // vanished / unreadable: Python reports it
           else { e.ino = sb.st_ino; e.size = (uint64_t)sb.st_size; e.mtime = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec; }
           if (e.st == 1) {                                           // datetime.fromtimestamp(ts): naive local wall clock (utils.py:94)
-            time_t tt = (time_t)e.ts; struct tm tmv;
-            if (!localtime_r(&tt, &tmv) || tmv.tm_year + 1900 > 9999) e.st = 2;
-            else e.wall = (int64_t)timegm(&tmv);
+            if (!wall_of(e.ts, &e.wall)) e.st = 2;
           }
         }
       }
@@ -120,8 +155,10 @@ extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
     for (auto& t : pool) t.join();
   }
   closedir(d);
+  const double t2 = now();
   // newest first, ties in readdir order (utils.py:251: sort(key=timestamp, reverse=True) is stable); entries Python must judge go last
   std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { if (a.st != b.st) return a.st < b.st; return a.st == 1 && a.ts > b.ts; });
+  const double t3 = now();
   fei_dirlist* l = new fei_dirlist();
   const size_t n = ents.size();
   l->name_off.reserve(n + 1); l->name_off.push_back(0);
@@ -132,8 +169,12 @@ extern "C" int fei_dir_list(const char* path, fei_dirlist** out) {
     for (int k = 0; k < 4; ++k) l->spans.push_back(e.sp[k]);
   }
   *out = l;
+  if (timing) fprintf(stderr, "[fei_dir_list] %zu entries: readdir+parse %.3f s, stat+localtime %.3f s, sort %.3f s, columns %.3f s\n", n, t1 - t0, t2 - t1, t3 - t2, now() - t3);
   return FEI_OK;
 }
+
+extern "C" int fei_dir_list(const char* path, fei_dirlist** out) { return dir_list(path, true, out); }
+extern "C" int fei_dir_list_names(const char* path, fei_dirlist** out) { return dir_list(path, false, out); }
 
 extern "C" int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v) {
   if (!l || !v) { set_error("null argument"); return FEI_E_BADARG; }
@@ -145,6 +186,82 @@ extern "C" int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v) {
 }
 
 extern "C" void fei_dirlist_free(fei_dirlist* l) { delete l; }
+
+// ---- cold read without a stat pass: open, fstat, read, close per file (a path stat costs more than the other three together where
+// system calls are expensive).  Sizes are only known once a file is open, so the bytes go into an ARENA: a worker opens a batch of
+// files, reserves the batch's total with one atomic add on *cursor, and reads them there; begin[i] / len[i] say where file i landed.
+// The arena is a large NORESERVE mapping (only the touched pages become resident), shared by all directories of a tree.
+extern "C" int fei_host_arena_alloc(uint64_t bytes, void** out) {
+  if (!out || !bytes) { set_error("null argument"); return FEI_E_BADARG; }
+  void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+  if (p == MAP_FAILED) { set_error("mmap of a %llu-byte arena: %s", (unsigned long long)bytes, strerror(errno)); return FEI_E_CAPACITY; }
+#ifdef MADV_HUGEPAGE
+  if (getenv("FEI_ARENA_THP")) madvise(p, bytes, MADV_HUGEPAGE);         // opt-in: first touch by 2 MiB instead of 4 KiB (no gain measured)
+#endif
+  *out = p;
+  return FEI_OK;
+}
+extern "C" int fei_host_arena_free(void* p, uint64_t bytes) {
+  if (p && munmap(p, bytes) != 0) { set_error("munmap: %s", strerror(errno)); return FEI_E_BADARG; }
+  return FEI_OK;
+}
+
+extern "C" int fei_read_dir_packed(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* arena, uint64_t arena_cap,
+                                   uint64_t* cursor, uint64_t max_file_bytes, int threads, uint64_t* begin, uint64_t* len, uint64_t* ino,
+                                   int64_t* mtime_ns, int32_t* err) {
+  if (!dir || !cursor || (n && (!names || !name_off || !arena || !begin || !len || !ino || !mtime_ns || !err))) { set_error("null argument"); return FEI_E_BADARG; }
+  if (threads < 1) threads = 1;
+  if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+  const int dfd = open(dir, O_RDONLY | O_DIRECTORY);
+  if (dfd < 0) { set_error("open(%s): %s", dir, strerror(errno)); return FEI_E_BADARG; }
+  std::atomic<uint64_t> next{0};
+  constexpr uint64_t kBatch = 64;
+  auto work = [&]() {
+    std::string nm;
+    int fds[kBatch]; uint64_t sz[kBatch];
+    for (;;) {
+      const uint64_t i0 = next.fetch_add(kBatch);
+      if (i0 >= n) break;
+      const uint64_t k = i0 + kBatch < n ? kBatch : n - i0;
+      uint64_t total = 0;
+      for (uint64_t j = 0; j < k; ++j) {
+        const uint64_t i = i0 + j;
+        begin[i] = 0; len[i] = 0; err[i] = 0; ino[i] = 0; mtime_ns[i] = -1; sz[j] = 0;
+        nm.assign(reinterpret_cast<const char*>(names) + name_off[i], name_off[i + 1] - name_off[i]);
+        fds[j] = openat(dfd, nm.c_str(), O_RDONLY);
+        if (fds[j] < 0) { err[i] = errno; continue; }
+        struct stat sb;
+        if (fstat(fds[j], &sb) != 0) { err[i] = errno; close(fds[j]); fds[j] = -1; continue; }
+        ino[i] = sb.st_ino; mtime_ns[i] = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
+        if (!S_ISREG(sb.st_mode)) { err[i] = S_ISDIR(sb.st_mode) ? EISDIR : EINVAL; close(fds[j]); fds[j] = -1; continue; }
+        if ((uint64_t)sb.st_size > max_file_bytes) { err[i] = EFBIG; len[i] = (uint64_t)sb.st_size; close(fds[j]); fds[j] = -1; continue; }
+        sz[j] = (uint64_t)sb.st_size; total += sz[j];
+      }
+      uint64_t at = __atomic_fetch_add(cursor, total, __ATOMIC_RELAXED);
+      const bool fits = at + total <= arena_cap;
+      for (uint64_t j = 0; j < k; ++j) {
+        const uint64_t i = i0 + j;
+        if (fds[j] < 0) continue;
+        if (!fits) { err[i] = ENOMEM; close(fds[j]); continue; }
+        uint64_t done = 0;
+        while (done < sz[j]) {
+          const ssize_t r = pread(fds[j], arena + at + done, sz[j] - done, (off_t)done);
+          if (r < 0) { if (errno == EINTR) continue; err[i] = errno; break; }
+          if (r == 0) break;                                         // shrank since fstat: what is there is the file
+          done += (uint64_t)r;
+        }
+        begin[i] = at; len[i] = done; at += sz[j];
+        close(fds[j]);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  close(dfd);
+  return FEI_OK;
+}
 
 // Reads n files of one directory into dst at dst_off[i] (capacity dst_off[i+1] - dst_off[i]): `threads` workers, open + pread +
 // close each.  got[i] = bytes read (a file that grew since it was listed is cut at the listed size: its new (size, mtime) makes the

@@ -23,7 +23,9 @@ from __future__ import annotations
 
 import calendar
 import ctypes as C
+import errno
 import os
+import queue
 import re
 import struct
 import threading
@@ -68,10 +70,11 @@ def _arr(p, dt, k):
     return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(k,)).copy()
 
 
-def list_dir(path: str) -> DirListing:
+def list_dir(path: str, want_stat: bool = True) -> DirListing:
+    """want_stat=False: names only (ino from the directory entry, size 0, mtime -1): read_dir_packed fills them from the open files."""
     l = _abi.lib()
     h = C.c_void_p()
-    _abi.check(l.fei_dir_list(os.fsencode(path), C.byref(h)))
+    _abi.check((l.fei_dir_list if want_stat else l.fei_dir_list_names)(os.fsencode(path), C.byref(h)))
     try:
         v = _abi.DirlistView()
         _abi.check(l.fei_dirlist_view_get(h, C.byref(v)))
@@ -181,6 +184,73 @@ def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None, out: 
             out[out_base:out_base + int(off[k])] = raw[:int(off[k])]
             raw = out[out_base:out_base + max(1, int(off[k]))]
     return raw, off, problems
+
+
+class _Arena:
+    """Address space for a cold read whose total size is not known in advance (fei_host_arena_alloc: NORESERVE, only what is read
+    becomes resident).  Finished stretches are page-locked by a background thread while the next directory is being read, so the
+    upload that follows runs at the pinned-memory rate."""
+    _PAGE = 2 << 20
+
+    def __init__(self, cap: int):
+        self.cap = cap
+        p = C.c_void_p()
+        _abi.check(_abi.lib().fei_host_arena_alloc(cap, C.byref(p)))
+        self.addr = p.value
+        self.cursor = C.c_uint64(0)
+        self.buf = np.ctypeslib.as_array(C.cast(self.addr, C.POINTER(C.c_uint8)), shape=(cap,))
+        self._pinned: List[Tuple[int, int]] = []
+        self._pin_to = 0
+        self._jobs: "queue.Queue[Optional[Tuple[int, int]]]" = queue.Queue()
+        self._thread = threading.Thread(target=self._pin_loop, daemon=True)
+        self._thread.start()
+
+    def _pin_loop(self):
+        l = _abi.lib()
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            lo, hi = job
+            if l.fei_host_register(self.addr + lo, hi - lo) == 0:
+                self._pinned.append((lo, hi))
+
+    def pin_finished(self, final: bool = False) -> None:
+        """Everything below the cursor is final once the directory that wrote it has returned."""
+        hi = int(self.cursor.value)
+        hi = min(self.cap, -(-hi // self._PAGE) * self._PAGE) if final else (hi // self._PAGE) * self._PAGE
+        if hi > self._pin_to and os.environ.get("FEI_PIN_COLD", "1") != "0":
+            self._jobs.put((self._pin_to, hi))
+            self._pin_to = hi
+        if final:
+            self._jobs.put(None)
+            self._thread.join()
+
+    def close(self) -> None:
+        if self.addr is None:
+            return
+        if self._thread.is_alive():
+            self._jobs.put(None)
+            self._thread.join()
+        l = _abi.lib()
+        for lo, _hi in self._pinned:
+            l.fei_host_unregister(self.addr + lo)
+        self.buf = None
+        l.fei_host_arena_free(self.addr, self.cap)
+        self.addr = None
+
+
+def read_dir_packed(path: str, d: DirListing, arena: _Arena) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Cold read of every listed entry into the arena (open + fstat + read + close: no stat pass).  Fills d.size / d.ino / d.mtime_ns
+    from the open files; returns (begin, len, errno) per entry."""
+    k = d.n
+    begin = np.zeros(max(1, k), dtype=np.uint64); ln = np.zeros(max(1, k), dtype=np.uint64)
+    ino = np.zeros(max(1, k), dtype=np.uint64); mt = np.zeros(max(1, k), dtype=np.int64); err = np.zeros(max(1, k), dtype=np.int32)
+    nbuf = np.frombuffer(d.names, dtype=np.uint8) if d.names else np.zeros(1, dtype=np.uint8)
+    _abi.check(_abi.lib().fei_read_dir_packed(os.fsencode(path), _abi.ptr(nbuf), _abi.ptr(np.ascontiguousarray(d.name_off)), k, arena.addr, arena.cap,
+                                             C.byref(arena.cursor), MAX_BODY, READ_THREADS, _abi.ptr(begin), _abi.ptr(ln), _abi.ptr(ino), _abi.ptr(mt), _abi.ptr(err)))
+    d.size, d.ino, d.mtime_ns = ln[:k].copy(), ino[:k], mt[:k]
+    return begin[:k], ln[:k], err[:k]
 
 
 # ----------------------------------------------------------------------------- change notification
@@ -406,13 +476,13 @@ class PackedMemdir:
                 self._incremental(changed)
             return self
 
-    def _list(self, folder: str, st: str) -> Tuple[DirListing, int]:
+    def _list(self, folder: str, st: str, want_stat: bool = True) -> Tuple[DirListing, int]:
         path = self._dir(folder, st)
         try:
             mt = os.stat(path).st_mtime_ns
         except OSError:
             mt = -1
-        return list_dir(path), mt
+        return list_dir(path, want_stat), mt
 
     def _fsb_of(self, key: Tuple[str, str]) -> int:
         return (self.folder_ids[key[0]] & 0xFFFF) | (U.STANDARD_FOLDERS.index(key[1]) << 16)
@@ -436,6 +506,96 @@ class PackedMemdir:
         self._set_folders(folders)
         order = self._order()
         segs: Dict[Tuple[str, str], _Seg] = {}
+        arena: Optional[_Arena] = None
+        if os.environ.get("FEI_COLD_STAT", "0") != "1":
+            try:
+                arena = _Arena(MAX_RAW_BATCH + (1 << 30))
+            except _abi.FeiError:
+                arena = None                                           # no address space to spare: list with sizes, read into an exact buffer
+        try:
+            if arena is not None:
+                raw, begin, ln, err = self._cold_read_packed(order, segs, arena)
+            else:
+                raw, begin, ln, err = self._cold_read_listed(order, segs)
+            n = len(begin)
+            self.files_read = n
+            t2 = time.perf_counter()
+            corpus = Corpus()
+            keep = err == 0
+            pos = 0
+            for key in order:                                          # files that could not be read: reported and skipped (utils.py:247-248)
+                seg = segs[key]; L = seg.listing
+                for i in np.nonzero(err[pos:pos + L.n])[0].tolist():
+                    e = int(err[pos + i])
+                    why = "a file over 32 MiB does not fit the packed layout" if e == errno.EFBIG else str(OSError(e, os.strerror(e), os.path.join(self._dir(*key), L.name(i))))
+                    seg.bad.append(f"Error processing {L.name(i)}: {why}")
+                pos += L.n
+            while True:
+                arrays = self._raw_arrays(segs, order, keep, raw, begin, ln)
+                valid = corpus.load_raw(arrays)
+                if valid.all():
+                    break
+                alive = np.nonzero(keep)[0]
+                for j in alive[~valid].tolist():                       # undecodable files: reported and skipped (utils.py:247-248)
+                    keep[j] = False
+                    key, i = self._locate(segs, order, j)
+                    L = segs[key].listing
+                    segs[key].bad.append(f"Error processing {L.name(i)}: {_decode_error(raw[int(begin[j]):int(begin[j] + ln[j])].tobytes())}")
+                    segs[key].bad_files[L.name_bytes(i)] = (int(L.ino[i]), int(L.size[i]), int(L.mtime_ns[i]))
+            raw_bytes = int(ln.sum())
+        finally:
+            raw = None
+            if arena is not None:
+                arena.close()
+        pos = start = 0
+        for key in order:                                              # drop the skipped entries from the listings; device id = listing position
+            seg = segs[key]
+            k = seg.listing.n
+            sel = keep[start:start + k]
+            if not sel.all():
+                seg.listing = _subset(seg.listing, np.nonzero(sel)[0])
+            seg.dev = np.arange(pos, pos + seg.listing.n, dtype=np.int64)
+            pos += seg.listing.n
+            start += k
+        old, old_delta = self.corpus, self.delta
+        self.segs = segs
+        self.corpus, self.delta, self.n_base, self.n_delta = corpus, None, corpus.n, 0
+        self.delta_raw = []
+        self.windows_packed = (corpus.n + 4095) // 4096
+        self.full_packs += 1
+        t3 = time.perf_counter()
+        self._rebuild_listing()
+        self.timing.update({"pack_s": t3 - t2, "listing_arrays_s": time.perf_counter() - t3, "files": n, "raw_bytes": raw_bytes})
+        for c in (old, old_delta):
+            if c is not None:
+                c.close()
+
+    def _cold_read_packed(self, order, segs, arena: "_Arena"):
+        """Names-only listing + open/fstat/read/close into the arena: no stat pass (see fei_read_dir_packed)."""
+        t_list = t_read = 0.0
+        begins, lens, errs = [], [], []
+        for key in order:
+            t = time.perf_counter()
+            listing, mt = self._list(*key, want_stat=False)
+            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.zeros(listing.n, dtype=np.int64)
+            segs[key] = seg
+            t1 = time.perf_counter(); t_list += t1 - t
+            if listing.n:
+                b, l, e = read_dir_packed(self._dir(*key), listing, arena)
+                arena.pin_finished()
+                begins.append(b); lens.append(l); errs.append(e)
+            t_read += time.perf_counter() - t1
+        total = int(arena.cursor.value)
+        if total > MAX_RAW_BATCH:
+            raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
+        t = time.perf_counter()
+        arena.pin_finished(final=True)
+        cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
+        self.timing = {"list_s": t_list, "read_s": t_read, "pin_tail_s": time.perf_counter() - t, "cold_path": "names-only listing, open+fstat+read+close into an arena"}
+        return arena.buf[:max(1, total)], cat(begins, np.uint64), cat(lens, np.uint64), cat(errs, np.int32)
+
+    def _cold_read_listed(self, order, segs):
+        """Listing with a stat of every entry, then reads into one exact buffer (FEI_COLD_STAT=1, or no arena)."""
         t0 = time.perf_counter()
         total = 0
         for key in order:                                              # 1. list every directory (readdir + parallel stat, native)
@@ -466,45 +626,8 @@ class PackedMemdir:
             pos += L.n; base_off += int(off[-1])
         if not exact:
             raw = np.concatenate(pieces) if pieces else np.zeros(1, dtype=np.uint8)
-        self.files_read = n
-        t2 = time.perf_counter()
-        self.timing = {"list_s": t1 - t0, "read_s": t2 - t1}
-        corpus = Corpus()
-        keep = np.ones(n, dtype=bool)
-        while True:
-            arrays = self._raw_arrays(segs, order, keep, raw, raw_off)
-            valid = corpus.load_raw(arrays)
-            if valid.all():
-                break
-            alive = np.nonzero(keep)[0]
-            for j in alive[~valid].tolist():                           # undecodable files: reported and skipped (utils.py:247-248)
-                keep[j] = False
-                key, i = self._locate(segs, order, j)
-                L = segs[key].listing
-                segs[key].bad.append(f"Error processing {L.name(i)}: {_decode_error(raw[int(raw_off[j]):int(raw_off[j + 1])].tobytes())}")
-                segs[key].bad_files[L.name_bytes(i)] = (int(L.ino[i]), int(L.size[i]), int(L.mtime_ns[i]))
-        pos = start = 0
-        for key in order:                                              # drop the skipped entries from the listings; device id = listing position
-            seg = segs[key]
-            k = seg.listing.n
-            sel = keep[start:start + k]
-            if not sel.all():
-                seg.listing = _subset(seg.listing, np.nonzero(sel)[0])
-            seg.dev = np.arange(pos, pos + seg.listing.n, dtype=np.int64)
-            pos += seg.listing.n
-            start += k
-        old, old_delta = self.corpus, self.delta
-        self.segs = segs
-        self.corpus, self.delta, self.n_base, self.n_delta = corpus, None, corpus.n, 0
-        self.delta_raw = []
-        self.windows_packed = (corpus.n + 4095) // 4096
-        self.full_packs += 1
-        t3 = time.perf_counter()
-        self._rebuild_listing()
-        self.timing.update({"pack_s": t3 - t2, "listing_arrays_s": time.perf_counter() - t3, "files": n, "raw_bytes": int(raw_off[n])})
-        for c in (old, old_delta):
-            if c is not None:
-                c.close()
+        self.timing = {"list_s": t1 - t0, "read_s": time.perf_counter() - t1, "cold_path": "listing with stat, reads into one exact buffer"}
+        return raw, raw_off[:-1].copy(), (raw_off[1:] - raw_off[:-1]), np.zeros(n, dtype=np.int32)
 
     @staticmethod
     def _locate(segs, order, j):
@@ -515,7 +638,7 @@ class PackedMemdir:
             j -= k
         raise IndexError(j)
 
-    def _raw_arrays(self, segs, order, keep, raw, raw_off) -> Dict[str, Any]:
+    def _raw_arrays(self, segs, order, keep, raw, begin, ln) -> Dict[str, Any]:
         cols: Dict[str, List[np.ndarray]] = {k: [] for k in ("ts", "wall", "flags8", "spans", "fsb")}
         names, lens = [], []
         for key in order:
@@ -532,21 +655,20 @@ class PackedMemdir:
         nlen = np.concatenate(lens) if lens else np.zeros(0, dtype=np.int64)
         nblob = b"".join(names)
         if keep.all():
-            sel_raw, sel_off = raw, raw_off
+            sel_begin, sel_len = begin, ln
             name = np.frombuffer(nblob, dtype=np.uint8).copy() if nblob else np.zeros(1, dtype=np.uint8)
             name_off = np.zeros(n_all + 1, dtype=np.uint64); np.cumsum(nlen, out=name_off[1:])
         else:
             idx = np.nonzero(keep)[0]
             noff = np.zeros(n_all + 1, dtype=np.int64); np.cumsum(nlen, out=noff[1:])
-            parts = [raw[int(raw_off[j]):int(raw_off[j + 1])].tobytes() for j in idx.tolist()]
-            sel_off = np.zeros(len(idx) + 1, dtype=np.uint64); np.cumsum(np.fromiter(map(len, parts), dtype=np.int64, count=len(idx)), out=sel_off[1:])
-            sel_raw = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if sel_off[-1] else np.zeros(1, dtype=np.uint8)
+            sel_begin, sel_len = begin[idx], ln[idx]
             nm = b"".join(nblob[int(noff[j]):int(noff[j + 1])] for j in idx.tolist())
             name = np.frombuffer(nm, dtype=np.uint8).copy() if nm else np.zeros(1, dtype=np.uint8)
             name_off = np.zeros(len(idx) + 1, dtype=np.uint64); np.cumsum(nlen[idx], out=name_off[1:])
             ts, wall, f8, fsb, spans = ts[idx], wall[idx], f8[idx], fsb[idx], spans[idx]
         n = len(ts)
-        return {"n": n, "global_base": 0, "raw": sel_raw, "raw_off": np.ascontiguousarray(sel_off), "name": name if n else None,
+        return {"n": n, "global_base": 0, "raw": raw, "raw_bytes": len(raw), "raw_begin": np.ascontiguousarray(sel_begin, dtype=np.uint64),
+                "raw_len": np.ascontiguousarray(sel_len, dtype=np.uint64), "name": name if n else None,
                 "name_off": name_off if n else None, "name_spans": np.ascontiguousarray(spans.reshape(-1)) if n else None,
                 "ts": np.ascontiguousarray(ts), "wall": np.ascontiguousarray(wall), "flags8": np.ascontiguousarray(f8), "fsb": np.ascontiguousarray(fsb)}
 

@@ -106,6 +106,10 @@ int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h);
  * nothing is loaded and FEI_E_BADARG is returned so the caller can drop them (the reference reports and skips
  * such files, utils.py:247-248) and call again.                                                                */
 int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out);
+/* The same with file i at raw[begin[i] .. begin[i] + len[i]) (any order, gaps allowed: what fei_read_dir_packed leaves in its arena);
+ * raw_bytes = the extent of raw to upload. */
+int fei_corpus_load_raw_spans(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, uint64_t raw_bytes, const uint64_t* begin,
+                              const uint64_t* len, uint8_t* valid_out);
 /* Device-side stage times (ms) of the last fei_corpus_load_raw on this handle, CUDA events on its load stream:
  * out[0] = host-to-device copy of the file text, out[1] = the pack kernels after it (measure, offsets, normalise, tiling,
  * header directory), out[2] = that copy's rate in GB/s.  Waits for the load to finish on the device. */
@@ -131,12 +135,25 @@ typedef struct fei_dirlist_view {
   const uint8_t* status; const int64_t* flags_len;
 } fei_dirlist_view;
 int fei_dir_list(const char* path, fei_dirlist** out);
+/* The same listing without the per-entry stat: ino comes from the directory entry, size = 0 and mtime_ns = -1 until
+ * fei_read_dir_packed has opened the file. */
+int fei_dir_list_names(const char* path, fei_dirlist** out);
 int fei_dirlist_view_get(const fei_dirlist* l, fei_dirlist_view* v);
 void fei_dirlist_free(fei_dirlist* l);
 /* n files of one directory read by `threads` workers into dst[dst_off[i] .. dst_off[i+1]) (capacities from the listing's sizes);
  * got[i] = bytes read (at most the listed size), err[i] = errno.  dst may be pinned (fei_host_register).                          */
 int fei_read_files(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* dst, const uint64_t* dst_off,
                    int threads, uint64_t* got, int32_t* err);
+/* Cold read without a stat pass (open, fstat, read, close per file): the files' bytes go into a caller arena at positions handed out
+ * by an atomic add on *cursor (start it at 0 and pass the same cursor for every directory of a tree); begin[i] / len[i] locate file
+ * i, ino[i] / mtime_ns[i] come from the open file.  err[i] = errno; EFBIG = larger than max_file_bytes (len[i] = its size, not
+ * read), ENOMEM = the arena is full.  fei_host_arena_alloc maps address space without committing memory (MAP_NORESERVE): size it
+ * for the largest tree, only the bytes read become resident.                                                                  */
+int fei_host_arena_alloc(uint64_t bytes, void** out);
+int fei_host_arena_free(void* p, uint64_t bytes);
+int fei_read_dir_packed(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* arena, uint64_t arena_cap,
+                        uint64_t* cursor, uint64_t max_file_bytes, int threads, uint64_t* begin, uint64_t* len, uint64_t* ino,
+                        int64_t* mtime_ns, int32_t* err);
 /* tooling: write n files into an existing directory with `threads` workers (synthetic trees for tests and the bench).          */
 int fei_write_files(const char* dir, const uint8_t* names, const uint64_t* name_off, const uint8_t* blob, const uint64_t* off, uint64_t n, int threads);
 

@@ -1,0 +1,93 @@
+"""Host side of the cold pack (no GPU): native directory listing and the two read paths of fei_b200.packer give the same files.
+
+Reference behaviour being mirrored: utils.list_memories (memdir_tools/utils.py:202-253) lists a cur/new/tmp directory, keeps the
+names matching the Maildir grammar, reads every file and sorts newest first."""
+import os
+
+import numpy as np
+import pytest
+
+from fei_b200 import packer, synth
+
+
+@pytest.fixture(scope="module")
+def tree(tmp_path_factory):
+    base = str(tmp_path_factory.mktemp("memdir"))
+    synth.write_memdir_native(base, 0xFE1, 0, 3000, 4)
+    d = os.path.join(base, "cur")
+    with open(os.path.join(d, "1700000001.abc.host:2,S"), "wb") as f:          # CRLF + non-ASCII content, read verbatim
+        f.write("Subject: x\r\n---\r\nbödy\r\n".encode())
+    with open(os.path.join(d, "not-a-memory.txt"), "wb") as f:
+        f.write(b"ignored")
+    open(os.path.join(d, "1700000002.empty.host:2,"), "wb").close()
+    return base
+
+
+def test_names_only_listing_matches_stat_listing(tree):
+    d = os.path.join(tree, "cur")
+    a, b = packer.list_dir(d, True), packer.list_dir(d, False)
+    assert a.n == b.n > 100 and a.names == b.names and np.array_equal(a.name_off, b.name_off)
+    for k in ("ts", "wall", "flags8", "ino"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(a.spans, b.spans)
+    assert (b.size == 0).all() and (b.mtime_ns == -1).all()
+    assert (np.diff(a.ts) <= 0).all()                                             # newest first (utils.py:251)
+
+
+def test_packed_read_equals_listed_read(tree):
+    d = os.path.join(tree, "cur")
+    a = packer.list_dir(d, True)
+    raw, off, problems = packer.read_files(d, a)
+    assert not problems
+    b = packer.list_dir(d, False)
+    arena = packer._Arena(64 << 20)
+    try:
+        begin, ln, err = packer.read_dir_packed(d, b, arena)
+        assert not err.any()
+        assert int(arena.cursor.value) == int(off[-1]) == int(ln.sum())
+        for i in range(a.n):
+            want = raw[int(off[i]):int(off[i + 1])].tobytes()
+            assert arena.buf[int(begin[i]):int(begin[i] + ln[i])].tobytes() == want, a.name(i)
+            with open(os.path.join(d, a.name(i)), "rb") as f:
+                assert f.read() == want
+        # size / inode / mtime now come from the open files and equal what stat reports
+        assert np.array_equal(b.size, a.size) and np.array_equal(b.ino, a.ino) and np.array_equal(b.mtime_ns, a.mtime_ns)
+        spans = sorted(zip(begin.tolist(), ln.tolist()))
+        assert all(s0 + l0 <= s1 for (s0, l0), (s1, _l1) in zip(spans, spans[1:]))      # no two files overlap in the arena
+    finally:
+        arena.close()
+
+
+def test_packed_read_reports_vanished_oversized_and_full_arena(tree, monkeypatch):
+    import errno
+    d = os.path.join(tree, "new")
+    b = packer.list_dir(d, False)
+    assert b.n > 10
+    victim = os.path.join(d, b.name(3))
+    keep = open(victim, "rb").read()
+    os.unlink(victim)
+    monkeypatch.setattr(packer, "MAX_BODY", 100)                                  # almost every synthetic file is larger than that
+    arena = packer._Arena(1 << 20)
+    try:
+        begin, ln, err = packer.read_dir_packed(d, b, arena)
+        assert err[3] == errno.ENOENT
+        sizes = np.array([os.stat(os.path.join(d, b.name(i))).st_size if i != 3 else 0 for i in range(b.n)])
+        big = sizes > 100
+        assert big.any() and (err[big] == errno.EFBIG).all() and np.array_equal(ln[big], sizes[big].astype(np.uint64))
+        ok = (~big) & (np.arange(b.n) != 3)
+        assert not err[ok].any()
+    finally:
+        arena.close()
+        with open(victim, "wb") as f:
+            f.write(keep)
+    monkeypatch.setattr(packer, "MAX_BODY", 32 << 20)
+    b = packer.list_dir(d, False)
+    tiny = packer._Arena(4096)
+    try:
+        begin, ln, err = packer.read_dir_packed(d, b, tiny)
+        assert (err == errno.ENOMEM).any() and not ((err != 0) & (err != errno.ENOMEM)).any()
+        for i in np.nonzero(err == 0)[0].tolist():
+            with open(os.path.join(d, b.name(i)), "rb") as f:
+                assert tiny.buf[int(begin[i]):int(begin[i] + ln[i])].tobytes() == f.read()
+    finally:
+        tiny.close()
