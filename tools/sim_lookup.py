@@ -104,6 +104,30 @@ def main():
         report(f"u8 x 32 columns, {k} copies, each confined to {32 // k} banks ({11 * k} KB)", copies(k, 9, 4))
     print("a byte -> class lookup (256-byte table, or one private copy per lane) costs one more wavefront per byte on top of the class-indexed rows")
 
+    # ---- bank-private replicas of the HOT rows only (lane l keeps its copy of the K most visited states' rows in bank l), every other
+    # state in the shared class-indexed table: hot lanes never collide with each other, but cold lanes land on any bank
+    hot_rank = np.full(n, -1, dtype=np.int64)
+    by_occ = np.argsort(-occ, kind="stable")
+    for K in (32, 64, 128):
+        hot_rank[:] = -1
+        hot_rank[by_occ[:K]] = np.arange(K)
+        one = []; two = []; share = []
+        for S, B in traces:
+            hot = hot_rank[S] >= 0
+            shared_word = S * 17 + c32[B] // 2
+            lanes = np.arange(32)
+            for t in range(S.shape[0]):
+                h = hot[t]
+                load = np.zeros(32, dtype=np.int64)
+                load[lanes[h]] += 1                                                # one private word per hot lane, in its own bank
+                cold_words = np.unique(shared_word[t][~h])
+                cold_load = np.bincount(cold_words % 32, minlength=32)
+                one.append((load + cold_load).max())
+                two.append((1 if h.any() else 0) + (cold_load.max() if len(cold_words) else 0))
+            share.append(hot.mean())
+        print(f"  top-{K} rows private per lane ({K * 32 * 2 * 32 // 1024} KB) + shared class-indexed table: {np.mean(share):.2f} of the lanes hot; "
+              f"one mixed LDS {np.mean(one):.2f} wavefronts, hot and cold as two LDS {np.mean(two):.2f} (plus the byte -> class lookup)")
+
 
 if __name__ == "__main__":
     main()
