@@ -328,8 +328,9 @@ def main():
     traffic = ncu_traffic_per_entry()
     roofline = {"bound": "hbm", "kernel": "k_body<direct,acc64>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": body_ms_avg,
-                "kernel_ms_note": "CUDA events around all chunk launches of the kernel within one step (the compaction of finished chunks runs "
-                                  "concurrently on a second stream); kernel launches per step: %d" % (launches // max(1, args.steps)),
+                "kernel_ms_note": "CUDA events on the compute stream around the kernel's one launch per step (a gate kernel on a second stream "
+                                  "releases the compaction of each finished run of windows while it is still scanning); kernel launches per step incl. "
+                                  "gates and compaction: %d" % (launches // max(1, args.steps)),
                 "bytes_per_memory": algo_bytes / max(1, st["n"]),
                 "traffic": int(traffic["bytes_per_entry"] * st["n"]) if traffic else None,
                 "traffic_source": (traffic["source"] + ", scaled linearly with entries") if traffic else "no capture",

@@ -70,6 +70,7 @@ struct Utf8State {
 };
 
 constexpr int kIngestThreads = 256;
+constexpr uint64_t kH2DPiece = 64ull << 20;       // = packer._Arena.BLOCK
 // raw_len == nullptr: file i = raw[raw_off[i], raw_off[i+1]); else raw[raw_off[i], raw_off[i] + raw_len[i])
 __global__ void __launch_bounds__(kIngestThreads) k_raw_measure(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ raw_off,
                                                                  const uint64_t* __restrict__ raw_len, uint64_t n, RawMeasure* __restrict__ out, uint32_t* __restrict__ hdr_len, uint32_t* __restrict__ body_len,
@@ -296,7 +297,12 @@ static int load_raw_impl(fei_corpus* c, const fei_corpus_host* h, const uint8_t*
     FEI_CUDA(cudaMemcpyAsync(d_raw_off.p, raw_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
   }
   FEI_CUDA(cudaEventRecord(c->ev_load[0], s));
-  if (raw_bytes) FEI_CUDA(cudaMemcpyAsync(d_raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, s));
+  // in pieces at fixed offsets: the host buffer may be page-locked block by block (the packer's arena: a copy must not straddle two
+  // registrations), and a failed registration leaves one block pageable without slowing the others
+  for (uint64_t o = 0; o < raw_bytes; o += kH2DPiece) {
+    const uint64_t nb = raw_bytes - o < kH2DPiece ? raw_bytes - o : kH2DPiece;
+    FEI_CUDA(cudaMemcpyAsync(d_raw.as<uint8_t>() + o, raw + o, nb, cudaMemcpyHostToDevice, s));
+  }
   FEI_CUDA(cudaEventRecord(c->ev_load[1], s));
   FEI_CUDA(cudaMemsetAsync((uint8_t*)d_raw.p + raw_bytes, 0, 64, s));
   unsigned long long* d_summary = reinterpret_cast<unsigned long long*>(d_ms.as<uint8_t>() + (n ? n : 1) * sizeof(RawMeasure));

@@ -190,7 +190,7 @@ class _Arena:
     """Address space for a cold read whose total size is not known in advance (fei_host_arena_alloc: NORESERVE, only what is read
     becomes resident).  Finished stretches are page-locked by a background thread while the next directory is being read, so the
     upload that follows runs at the pinned-memory rate."""
-    _PAGE = 2 << 20
+    BLOCK = 64 << 20                                               # = kH2DPiece of csrc/ingest.cu
 
     def __init__(self, cap: int):
         self.cap = cap
@@ -216,11 +216,14 @@ class _Arena:
                 self._pinned.append((lo, hi))
 
     def pin_finished(self, final: bool = False) -> None:
-        """Everything below the cursor is final once the directory that wrote it has returned."""
+        """Everything below the cursor is final once the directory that wrote it has returned.  Registrations are whole BLOCKs at
+        BLOCK-aligned offsets (the last one shorter): the upload copies BLOCK by BLOCK (fei_corpus_load_raw), and a copy must not
+        straddle two registrations."""
         hi = int(self.cursor.value)
-        hi = min(self.cap, -(-hi // self._PAGE) * self._PAGE) if final else (hi // self._PAGE) * self._PAGE
+        hi = min(self.cap, -(-hi // 4096) * 4096) if final else (hi // self.BLOCK) * self.BLOCK
         if hi > self._pin_to and os.environ.get("FEI_PIN_COLD", "1") != "0":
-            self._jobs.put((self._pin_to, hi))
+            for lo in range(self._pin_to, hi, self.BLOCK):
+                self._jobs.put((lo, min(lo + self.BLOCK, hi)))
             self._pin_to = hi
         if final:
             self._jobs.put(None)
@@ -574,24 +577,28 @@ class PackedMemdir:
         """Names-only listing + open/fstat/read/close into the arena: no stat pass (see fei_read_dir_packed)."""
         t_list = t_read = 0.0
         begins, lens, errs = [], [], []
-        for key in order:
-            t = time.perf_counter()
-            listing, mt = self._list(*key, want_stat=False)
-            seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.zeros(listing.n, dtype=np.int64)
-            segs[key] = seg
-            t1 = time.perf_counter(); t_list += t1 - t
-            if listing.n:
-                b, l, e = read_dir_packed(self._dir(*key), listing, arena)
-                arena.pin_finished()
-                begins.append(b); lens.append(l); errs.append(e)
-            t_read += time.perf_counter() - t1
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(1) as ex:                              # the next directory is listed while this one is being read
+            fut = ex.submit(self._list, *order[0], want_stat=False) if order else None
+            for k, key in enumerate(order):
+                t = time.perf_counter()
+                listing, mt = fut.result()
+                fut = ex.submit(self._list, *order[k + 1], want_stat=False) if k + 1 < len(order) else None
+                seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.zeros(listing.n, dtype=np.int64)
+                segs[key] = seg
+                t1 = time.perf_counter(); t_list += t1 - t
+                if listing.n:
+                    b, l, e = read_dir_packed(self._dir(*key), listing, arena)
+                    arena.pin_finished()
+                    begins.append(b); lens.append(l); errs.append(e)
+                t_read += time.perf_counter() - t1
         total = int(arena.cursor.value)
         if total > MAX_RAW_BATCH:
             raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
         t = time.perf_counter()
         arena.pin_finished(final=True)
         cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
-        self.timing = {"list_s": t_list, "read_s": t_read, "pin_tail_s": time.perf_counter() - t, "cold_path": "names-only listing, open+fstat+read+close into an arena"}
+        self.timing = {"list_s": t_list, "read_s": t_read, "pin_tail_s": time.perf_counter() - t, "cold_path": "names-only listing (of the next directory, under the current read), open+fstat+read+close into an arena; list_s = listing time not hidden"}
         return arena.buf[:max(1, total)], cat(begins, np.uint64), cat(lens, np.uint64), cat(errs, np.int32)
 
     def _cold_read_listed(self, order, segs):

@@ -1,28 +1,29 @@
 #!/usr/bin/env python3
-"""Where does MemoryChain.validate_chain() on Python block objects spend its time?  tools/prof_validate.py [blocks]
-(FEI_DEBUG_TIMING=1 adds the library's own split: JSON serialisation / H2D + padding / kernel)"""
+"""Driver for ncu captures / timing of MemoryChain.validate_chain() on reference-shaped Python block objects:
+tools/prof_validate.py [blocks].  The blocks are the deterministic synthetic chain (hashes fetched from the device generator);
+constructing the chain marshals them into typed columns and builds the canonical JSON on the GPU (k_json_size / k_json_write),
+validate_chain() then runs k_prepare_links / k_sha256_validate on resident data."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 from fei_b200 import _abi, synth
 from fei_b200.memdir_tools import memorychain as mc
-from oracle import chain_oracle as co
 import bench
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+_abi.init(); lib = _abi.lib()
+ch = C.c_void_p(); _abi.check(lib.fei_chain_create(C.byref(ch)))
+_abi.check(lib.fei_chain_synth(ch, bench.CHAIN_SEED, 0, n, -1))
+hh = np.zeros(64 * n, dtype=np.uint8); moff = np.zeros(n + 1, dtype=np.uint64)
+_abi.check(lib.fei_chain_fetch(ch, 0, n, None, 0, _abi.ptr(moff), _abi.ptr(hh), None))
+lib.fei_chain_destroy(ch)
+hashes = hh.tobytes().decode()
 blocks = []
-for ob in co.build_chain(synth.chain_specs(bench.CHAIN_SEED, 0, n)):
-    b = mc.MemoryBlock(ob.index, ob.timestamp, ob.memory_data, ob.previous_hash, ob.responsible_node, ob.proposer_node)
-    b.nonce = ob.nonce; b.hash = ob.hash
+for i, sp in enumerate(synth.chain_specs(bench.CHAIN_SEED, 0, n)):
+    b = mc.MemoryBlock(sp["index"], sp["timestamp"], sp["memory_data"], "0" if i == 0 else hashes[64 * i - 64:64 * i], sp["responsible_node"], sp["proposer_node"])
+    b.hash = hashes[64 * i:64 * i + 64]
     blocks.append(b)
-ch = mc.MemoryChain(blocks=blocks)
-assert ch.validate_chain()
-for rep in range(3):
-    t0 = time.perf_counter(); nat = mc.chain_columns_native(blocks); t1 = time.perf_counter()
-    cols, stored = mc.chain_columns(blocks); hb, ho = mc._str_blob(stored); t2 = time.perf_counter()
-    arr = mc._cols_struct(nat[0] if nat else cols)
-    fb, kind = C.c_int64(-1), C.c_int32(0)
-    t3 = time.perf_counter()
-    _abi.check(_abi.lib().fei_chain_validate_cols(arr, _abi.ptr(hb), _abi.ptr(ho), n, 0, C.byref(fb), C.byref(kind), None, None, 0, None)); t4 = time.perf_counter()
-    t5 = time.perf_counter(); ok = ch.validate_chain(); t6 = time.perf_counter()
-    print("marshal native %.1f ms | python %.1f ms | C call %.1f ms | validate_chain() total %.1f ms = %.3g blocks/s" %
-          ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t4 - t3) * 1e3, (t6 - t5) * 1e3, n / (t6 - t5)))
+t0 = time.perf_counter(); chain = mc.MemoryChain(blocks=blocks); t1 = time.perf_counter()
+ok = chain.validate_chain(); t2 = time.perf_counter()
+ok2 = chain.validate_chain(); t3 = time.perf_counter()
+print(f"{n} blocks: construction {1e3 * (t1 - t0):.1f} ms, first validate {1e3 * (t2 - t1):.2f} ms ({ok}), resident validate {1e3 * (t3 - t2):.2f} ms ({ok2})")
