@@ -269,6 +269,46 @@ def test_in_place_rewrite_delete_and_bad_file_reporting(gpu, tmp_path, capsys):
         U.set_memdir_base(old)
 
 
+def test_cold_pack_without_stat_pass_equals_default(gpu, tmp_path, capsys, monkeypatch):
+    """FEI_COLD_ARENA=1: names-only listing + open/fstat/read/close into an arena + fei_corpus_load_raw_spans.  Same listing, same
+    hits, same report of an undecodable file, and the incremental sync that follows works on the keys taken from the open files."""
+    import os
+    from fei_b200 import packer, synth
+    from fei_b200.memdir_tools import utils as U
+    from fei_b200.memdir_tools.search import search_memories
+    base = str(tmp_path / "Memdir")
+    synth.write_memdir(base, [synth.record(35, i) for i in range(5000)])
+    with open(os.path.join(base, ".Projects/AI", "cur", "1700009999.badbad03.host:2,"), "wb") as f:
+        f.write(b"Subject: x\n---\n\xff\xfe")
+    old = U.MEMDIR_BASE
+    U.set_memdir_base(base)
+    try:
+        conds = [("content", "matches", "python|rust"), ("flags", "has_flag", "S")]
+        want = _oracle_keys(base, conds)
+        results = {}
+        for arena in ("0", "1"):
+            monkeypatch.setenv("FEI_COLD_ARENA", arena)
+            packer.drop()
+            got = search_memories(_query(conds, True))
+            pm = packer.packed()
+            assert "badbad03" in capsys.readouterr().out
+            assert pm.timing["cold_path"].startswith("names-only" if arena == "1" else "listing with stat")
+            assert [key_of(m) for m in got] == want != []
+            results[arena] = [(m["filename"], m["headers"], m["content"]) for m in got]
+        assert results["0"] == results["1"]
+        victim = search_memories(_query([("flags", "has_flag", "F")], False))[0]          # still on the arena-packed corpus
+        path = os.path.join(U.get_memory_path(victim["folder"], victim["status"]), victim["filename"])
+        text = open(path).read()
+        with open(path, "w") as f:
+            f.write(text.replace("---", "Tags: zzarena\n---", 1) if "Tags: " not in text else text.replace("Tags: ", "Tags: zzarena,", 1))
+        got = search_memories(_query([("Tags", "has_tag", "zzarena")], False))
+        assert [key_of(m) for m in got] == [key_of(victim)]
+        assert pm.files_read == 1 and packer.packed() is pm
+    finally:
+        packer.drop()
+        U.set_memdir_base(old)
+
+
 def test_one_changed_file_in_100k_repacks_one_window(gpu, tmp_path, capsys):
     """Incremental sync at scale: 100 k files packed once; one new file, one rewritten file and one flag change later at most one
     4096-record window is (re)packed and exactly the files whose content is new are read.  Results equal a fresh listing by the oracle."""
