@@ -53,8 +53,8 @@ class Corpus:
             v = a.get(k)
             setattr(h, k, _abi.ptr(np.ascontiguousarray(v)) if v is not None else None)
         valid = np.zeros(max(1, h.n), dtype=np.uint8)
-        if "raw_begin" in a:                                            # files anywhere in the buffer (fei_read_dir_packed's arena)
-            rc = _abi.lib().fei_corpus_load_raw_spans(self._h, C.byref(h), _abi.ptr(a["raw"]), int(a["raw_bytes"]), _abi.ptr(a["raw_begin"]),
+        if "raw_begin" in a:                                            # files anywhere in the buffer; raw None = already staged on the device
+            rc = _abi.lib().fei_corpus_load_raw_spans(self._h, C.byref(h), _abi.ptr(a["raw"]) if a["raw"] is not None else None, int(a["raw_bytes"]), _abi.ptr(a["raw_begin"]),
                                                       _abi.ptr(a["raw_len"]), _abi.ptr(valid))
         else:
             rc = _abi.lib().fei_corpus_load_raw(self._h, C.byref(h), _abi.ptr(a["raw"]), _abi.ptr(a["raw_off"]), _abi.ptr(valid))
@@ -65,6 +65,10 @@ class Corpus:
             self._keep = None                  # every host array was consumed before the call returned (the text may be a transient arena)
             self.n, self.global_base = h.n, h.global_base
         return valid
+
+    def stage_text(self, total: int, piece: np.ndarray, offset: int) -> None:
+        """Uploads raw[offset : offset + len(piece)] of a text of `total` bytes ahead of load_raw (fei_corpus_stage_text)."""
+        _abi.check(_abi.lib().fei_corpus_stage_text(self._h, int(total), piece.ctypes.data if len(piece) else None, int(offset), int(len(piece))))
 
     def fetch_meta(self) -> Dict[str, np.ndarray]:
         n = self.n

@@ -73,6 +73,7 @@ struct fei_corpus {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_load[3] = {nullptr, nullptr, nullptr};   // load_raw: before / after the text copy, end of the pack kernels
   bool load_timed = false; uint64_t load_raw_bytes = 0;
+  uint64_t staged_text_bytes = ~0ull;    // size of the text fei_corpus_stage_text is filling stage_raw with (~0: none)
   cudaStream_t load_stream = nullptr;    // loads of this handle (H2D + pack kernels): own stream, so that batches streamed through several handles overlap
   cudaEvent_t ev_chunk[16] = {nullptr};
   cudaEvent_t ev_side = nullptr;

@@ -257,7 +257,8 @@ static int load_raw_impl(fei_corpus* c, const fei_corpus_host* h, const uint8_t*
   if (!c) { set_error("null corpus"); return FEI_E_BADARG; }
   std::lock_guard<std::mutex> lock(c->mu);
   FEI_TRY(require_ready());
-  if (!c || !h || !raw_off || (h->n && !raw)) { set_error("null argument"); return FEI_E_BADARG; }
+  if (!c || !h || !raw_off) { set_error("null argument"); return FEI_E_BADARG; }
+  const bool staged = h->n && !raw;                                     // raw == NULL: the text was put on the device by fei_corpus_stage_text
   if (h->n >= 0xFFFFFFFFull) { set_error("at most 2^32-2 records per shard"); return FEI_E_BADARG; }
   if (h->n && (!h->ts || !h->wall || !h->flags8 || !h->fsb)) { set_error("missing meta array"); return FEI_E_BADARG; }
   // loads run on the copy stream: a batch can be uploaded / normalised / tiled into one handle while another handle is being
@@ -271,6 +272,10 @@ static int load_raw_impl(fei_corpus* c, const fei_corpus_host* h, const uint8_t*
     for (uint64_t i = 0; i < n; ++i)
       if (raw_off[i] > raw_bytes || raw_len[i] > raw_bytes - raw_off[i]) { set_error("record %llu: span outside the %llu raw bytes", (unsigned long long)i, (unsigned long long)raw_bytes); return FEI_E_BADARG; }
   c->load_raw_bytes = raw_bytes;
+  if (staged && (c->staged_text_bytes != raw_bytes || c->stage_raw.bytes < raw_bytes + 64)) {
+    set_error("raw == NULL but the staged text (%llu bytes) is not the %llu bytes the offsets describe", (unsigned long long)c->staged_text_bytes, (unsigned long long)raw_bytes);
+    return FEI_E_STATE;
+  }
   FEI_TRY(corpus_load_events(c));
   DevBuf& d_raw = c->stage_raw; DevBuf& d_raw_off = c->stage_raw_off; DevBuf& d_ms = c->stage_ms; DevBuf& d_hlen = c->stage_hlen; DevBuf& d_blen = c->stage_blen;
   FEI_TRY(d_raw.ensure(raw_bytes + 64)); FEI_TRY(d_raw_off.ensure((n + 1) * 8 * (raw_len ? 2 : 1)));
@@ -299,7 +304,8 @@ static int load_raw_impl(fei_corpus* c, const fei_corpus_host* h, const uint8_t*
   FEI_CUDA(cudaEventRecord(c->ev_load[0], s));
   // in pieces at fixed offsets: the host buffer may be page-locked block by block (the packer's arena: a copy must not straddle two
   // registrations), and a failed registration leaves one block pageable without slowing the others
-  for (uint64_t o = 0; o < raw_bytes; o += kH2DPiece) {
+  if (!staged) c->staged_text_bytes = ~0ull;                             // whatever was staged is overwritten now
+  for (uint64_t o = 0; o < raw_bytes && !staged; o += kH2DPiece) {
     const uint64_t nb = raw_bytes - o < kH2DPiece ? raw_bytes - o : kH2DPiece;
     FEI_CUDA(cudaMemcpyAsync(d_raw.as<uint8_t>() + o, raw + o, nb, cudaMemcpyHostToDevice, s));
   }
@@ -345,9 +351,29 @@ static int load_raw_impl(fei_corpus* c, const fei_corpus_host* h, const uint8_t*
   FEI_TRY(build_tiles(c, body.as<uint8_t>(), body_off.as<uint64_t>(), s));
   FEI_TRY(build_header_dir(c, s));
   FEI_CUDA(cudaEventRecord(c->ev_load[2], s));
-  if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); d_raw.release(); }
+  if (body.bytes > (8ull << 30)) { body.release(); body_off.release(); c->tmp_len.release(); c->tmp_gunits.release(); d_raw.release(); c->staged_text_bytes = ~0ull; }
   c->loaded = true;
   c->load_timed = true;
+  return FEI_OK;
+}
+
+/* Uploads a stretch of the file text ahead of fei_corpus_load_raw (which is then called with raw == NULL): the packer sends each
+ * directory's bytes while it reads the next directory, so that the (pageable) copy is off the critical path.  total_bytes is the
+ * size of the whole text; the stretches may come in any order and from any thread, one at a time per handle. */
+extern "C" int fei_corpus_stage_text(fei_corpus* c, uint64_t total_bytes, const uint8_t* src, uint64_t offset, uint64_t bytes) {
+  if (!c || (bytes && !src)) { set_error("null argument"); return FEI_E_BADARG; }
+  std::lock_guard<std::mutex> lock(c->mu);
+  FEI_TRY(require_ready());
+  if (offset > total_bytes || bytes > total_bytes - offset) { set_error("stretch outside the text"); return FEI_E_BADARG; }
+  cudaStream_t s = corpus_load_stream(c);
+  if (c->stage_raw.bytes < total_bytes + 64 || c->staged_text_bytes != total_bytes) {
+    if (c->stage_raw.bytes < total_bytes + 64) { FEI_CUDA(cudaStreamSynchronize(s)); FEI_TRY(c->stage_raw.alloc(total_bytes + 64)); }
+    c->staged_text_bytes = total_bytes;
+  }
+  for (uint64_t o = 0; o < bytes; o += kH2DPiece) {
+    const uint64_t nb = bytes - o < kH2DPiece ? bytes - o : kH2DPiece;
+    FEI_CUDA(cudaMemcpyAsync(c->stage_raw.as<uint8_t>() + offset + o, src + o, nb, cudaMemcpyHostToDevice, s));
+  }
   return FEI_OK;
 }
 

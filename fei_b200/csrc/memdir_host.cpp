@@ -14,6 +14,7 @@
 #include <thread>
 #include <vector>
 #include <dirent.h>
+#include <sched.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -217,6 +218,7 @@ extern "C" int fei_read_dir_packed(const char* dir, const uint8_t* names, const 
   std::atomic<uint64_t> next{0};
   constexpr uint64_t kBatch = 64;
   auto work = [&]() {
+    if (!getenv("FEI_SHARED_FDS")) unshare(CLONE_FILES);               // private fd table per worker, see fei_read_files
     std::string nm;
     int fds[kBatch]; uint64_t sz[kBatch];
     for (;;) {
@@ -256,8 +258,7 @@ extern "C" int fei_read_dir_packed(const char* dir, const uint8_t* names, const 
     }
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
-  work();
+  for (int t = 0; t < threads; ++t) pool.emplace_back(work);
   for (auto& t : pool) t.join();
   close(dfd);
   return FEI_OK;
@@ -274,7 +275,10 @@ extern "C" int fei_read_files(const char* dir, const uint8_t* names, const uint6
   const int dfd = open(dir, O_RDONLY | O_DIRECTORY);
   if (dfd < 0) { set_error("open(%s): %s", dir, strerror(errno)); return FEI_E_BADARG; }
   std::atomic<uint64_t> next{0};
-  auto work = [&]() {
+  auto work = [&](bool own_fd_table) {
+    // every open / close takes the process-wide fd-table lock; a worker with a private copy of the table (unshare(CLONE_FILES):
+    // dfd stays valid in the copy, the copy dies with the thread) does not contend with the others
+    if (own_fd_table && !getenv("FEI_SHARED_FDS")) unshare(CLONE_FILES);
     std::string nm;
     for (;;) {
       const uint64_t i0 = next.fetch_add(64);
@@ -299,8 +303,7 @@ extern "C" int fei_read_files(const char* dir, const uint8_t* names, const uint6
     }
   };
   std::vector<std::thread> pool;
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
-  work();
+  for (int t = 0; t < threads; ++t) pool.emplace_back(work, true);     // the caller's thread keeps the shared table and only waits
   for (auto& t : pool) t.join();
   close(dfd);
   return FEI_OK;

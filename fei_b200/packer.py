@@ -515,15 +515,16 @@ class PackedMemdir:
                 arena = _Arena(MAX_RAW_BATCH + (1 << 30))
             except _abi.FeiError:
                 arena = None                                           # no address space to spare: list with sizes, read into an exact buffer
+        corpus = Corpus()
         try:
+            staged = False
             if arena is not None:
                 raw, begin, ln, err = self._cold_read_packed(order, segs, arena)
             else:
-                raw, begin, ln, err = self._cold_read_listed(order, segs)
+                raw, begin, ln, err, staged = self._cold_read_listed(order, segs, corpus)
             n = len(begin)
             self.files_read = n
             t2 = time.perf_counter()
-            corpus = Corpus()
             keep = err == 0
             pos = 0
             for key in order:                                          # files that could not be read: reported and skipped (utils.py:247-248)
@@ -535,10 +536,13 @@ class PackedMemdir:
                 pos += L.n
             while True:
                 arrays = self._raw_arrays(segs, order, keep, raw, begin, ln)
+                if staged:
+                    arrays["raw"] = None                               # every directory's bytes went up while the next one was being read
                 valid = corpus.load_raw(arrays)
                 if valid.all():
                     break
                 alive = np.nonzero(keep)[0]
+                staged = False                                         # the second attempt uploads from the host buffer
                 for j in alive[~valid].tolist():                       # undecodable files: reported and skipped (utils.py:247-248)
                     keep[j] = False
                     key, i = self._locate(segs, order, j)
@@ -601,8 +605,9 @@ class PackedMemdir:
         self.timing = {"list_s": t_list, "read_s": t_read, "pin_tail_s": time.perf_counter() - t, "cold_path": "names-only listing (of the next directory, under the current read), open+fstat+read+close into an arena; list_s = listing time not hidden"}
         return arena.buf[:max(1, total)], cat(begins, np.uint64), cat(lens, np.uint64), cat(errs, np.int32)
 
-    def _cold_read_listed(self, order, segs):
-        """Listing with a stat of every entry, then reads into one exact buffer (the default)."""
+    def _cold_read_listed(self, order, segs, corpus=None):
+        """Listing with a stat of every entry, then reads into one exact buffer (the default).  Each directory's bytes are uploaded
+        (fei_corpus_stage_text, a pageable copy on its own thread) while the next directory is being read."""
         t0 = time.perf_counter()
         total = 0
         for key in order:                                              # 1. list every directory (readdir + parallel stat, native)
@@ -618,23 +623,50 @@ class PackedMemdir:
         raw_off = np.zeros(n + 1, dtype=np.uint64)
         pos = base_off = 0
         exact = True
-        for key in order:
-            L = segs[key].listing
-            if not L.n:
-                continue
-            r, off, problems = read_files(self._dir(*key), L, out=raw if exact else None, out_base=base_off)
-            segs[key].bad.extend(msg for _i, msg in problems)
-            if exact and r.base is not raw and r is not raw and int(off[-1]) and not np.shares_memory(r, raw):
-                exact = False                                          # a file changed size under us: fall back to pieces
-                pieces = [raw[:base_off].copy()]
-            if not exact:
-                pieces.append(r[:int(off[-1])].copy())
-            raw_off[pos + 1:pos + L.n + 1] = off[1:] + np.uint64(base_off)
-            pos += L.n; base_off += int(off[-1])
+        stage = corpus is not None and total > 0 and os.environ.get("FEI_STAGE_UPLOAD", "1") != "0"
+        jobs: "queue.Queue[Optional[Tuple[int, int]]]" = queue.Queue()
+        failed: List[BaseException] = []
+
+        def uploader():
+            while True:
+                job = jobs.get()
+                if job is None:
+                    return
+                if not failed:
+                    try:
+                        corpus.stage_text(total, raw[job[0]:job[1]], job[0])
+                    except BaseException as e:                          # noqa: BLE001 -- reported by falling back to the plain upload
+                        failed.append(e)
+        th = threading.Thread(target=uploader, daemon=True) if stage else None
+        if th:
+            th.start()
+        try:
+            for key in order:
+                L = segs[key].listing
+                if not L.n:
+                    continue
+                r, off, problems = read_files(self._dir(*key), L, out=raw if exact else None, out_base=base_off)
+                segs[key].bad.extend(msg for _i, msg in problems)
+                if exact and r.base is not raw and r is not raw and int(off[-1]) and not np.shares_memory(r, raw):
+                    exact = False                                      # a file changed size under us: fall back to pieces
+                    pieces = [raw[:base_off].copy()]
+                if not exact:
+                    pieces.append(r[:int(off[-1])].copy())
+                elif th:
+                    jobs.put((base_off, base_off + int(off[-1])))
+                raw_off[pos + 1:pos + L.n + 1] = off[1:] + np.uint64(base_off)
+                pos += L.n; base_off += int(off[-1])
+        finally:
+            t_reads_done = time.perf_counter()
+            if th:
+                jobs.put(None)
+                th.join()
         if not exact:
             raw = np.concatenate(pieces) if pieces else np.zeros(1, dtype=np.uint8)
-        self.timing = {"list_s": t1 - t0, "read_s": time.perf_counter() - t1, "cold_path": "listing with stat, reads into one exact buffer"}
-        return raw, raw_off[:-1].copy(), (raw_off[1:] - raw_off[:-1]), np.zeros(n, dtype=np.int32)
+        staged = bool(th) and exact and not failed and base_off == total
+        self.timing = {"list_s": t1 - t0, "read_s": t_reads_done - t1, "upload_tail_s": time.perf_counter() - t_reads_done,
+                       "cold_path": "listing with stat, reads into one exact buffer" + (", each directory uploaded under the next read" if staged else "")}
+        return raw, raw_off[:-1].copy(), (raw_off[1:] - raw_off[:-1]), np.zeros(n, dtype=np.int32), staged
 
     @staticmethod
     def _locate(segs, order, j):

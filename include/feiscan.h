@@ -106,6 +106,10 @@ int fei_corpus_load(fei_corpus* c, const fei_corpus_host* h);
  * nothing is loaded and FEI_E_BADARG is returned so the caller can drop them (the reference reports and skips
  * such files, utils.py:247-248) and call again.                                                                */
 int fei_corpus_load_raw(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, const uint64_t* raw_off, uint8_t* valid_out);
+/* Uploads raw[offset .. offset + bytes) of a text of total_bytes ahead of fei_corpus_load_raw[_spans], which is then called with
+ * raw == NULL: lets a caller that produces the text piece by piece (one directory at a time) overlap the upload with producing
+ * the next piece.  One stretch at a time per handle; fei_corpus_load_raw fails with FEI_E_STATE if the sizes do not agree. */
+int fei_corpus_stage_text(fei_corpus* c, uint64_t total_bytes, const uint8_t* src, uint64_t offset, uint64_t bytes);
 /* The same with file i at raw[begin[i] .. begin[i] + len[i]) (any order, gaps allowed: what fei_read_dir_packed leaves in its arena);
  * raw_bytes = the extent of raw to upload. */
 int fei_corpus_load_raw_spans(fei_corpus* c, const fei_corpus_host* h, const uint8_t* raw, uint64_t raw_bytes, const uint64_t* begin,
