@@ -535,10 +535,13 @@ class PackedMemdir:
                     seg.bad.append(f"Error processing {L.name(i)}: {why}")
                 pos += L.n
             while True:
+                ta = time.perf_counter()
                 arrays = self._raw_arrays(segs, order, keep, raw, begin, ln)
                 if staged:
                     arrays["raw"] = None                               # every directory's bytes went up while the next one was being read
+                tb = time.perf_counter()
                 valid = corpus.load_raw(arrays)
+                stage_times = {"pack_host_arrays_s": tb - ta, "pack_load_raw_call_s": time.perf_counter() - tb}
                 if valid.all():
                     break
                 alive = np.nonzero(keep)[0]
@@ -573,6 +576,13 @@ class PackedMemdir:
         t3 = time.perf_counter()
         self._rebuild_listing()
         self.timing.update({"pack_s": t3 - t2, "listing_arrays_s": time.perf_counter() - t3, "files": n, "raw_bytes": raw_bytes})
+        self.timing.update(stage_times)
+        try:
+            st = np.zeros(3, dtype=np.float32)
+            _abi.check(_abi.lib().fei_corpus_last_load_timing(corpus.handle, _abi.ptr(st)))
+            self.timing.update({"device_text_h2d_ms": float(st[0]), "device_pack_kernels_ms": float(st[1])})
+        except _abi.FeiError:
+            pass
         for c in (old, old_delta):
             if c is not None:
                 c.close()
