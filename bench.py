@@ -586,7 +586,10 @@ def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
         times.append(time.perf_counter() - t0)
     pool.shutdown()
     stage = np.zeros(3, dtype=np.float32)
-    _abi.check(lib.fei_corpus_last_load_timing(cs[(nb - 1) % 3].handle, _abi.ptr(stage)))
+    stages_all = []
+    for back in range(min(3, nb) - 1, -1, -1):                      # the last three batches of the step, oldest first (one per handle)
+        _abi.check(lib.fei_corpus_last_load_timing(cs[(nb - 1 - back) % 3].handle, _abi.ptr(stage)))
+        stages_all.append({"batch": nb - 1 - back, "text_h2d_ms": float(stage[0]), "pack_kernels_ms": float(stage[1]), "text_h2d_gbs": float(stage[2])})
     for a in pinned:
         lib.fei_host_unregister(a.ctypes.data)
     for c in cs:
@@ -598,6 +601,7 @@ def run_e2e(args, corpus, prog, nq, lib, _abi, barrier):
             "frac_of_measured_h2d": (h2d * nb / dt / 1e9) / float(bw_h2d.value) if bw_h2d.value else None,
             "last_batch_device_stages": {"text_h2d_ms": float(stage[0]), "pack_kernels_ms": float(stage[1]), "text_h2d_gbs": float(stage[2]),
                                          "note": "CUDA events on the batch's load stream; the copy runs while the previous batch is packed and the one before it is scanned"},
+            "last_three_batches_device_stages": stages_all,
             "path": "pinned host buffers of raw file contents -> fei_corpus_load_raw (H2D + ingest + tiling + header directory, copy stream) "
                     "|| fei_scan_hits of the previous batch (k_body + compaction + 32 ordered hit lists D2H, compute stream); "
                     "%d batches of %d records per step (the same pinned batch is re-sent: every batch is copied, packed and scanned anew)" % (nb, n)}

@@ -94,7 +94,7 @@ _SIGS = {
     "fei_corpus_stage_text": (C.c_int, [_P, _U64, _P, _U64, _U64]),
     "fei_corpus_load_raw_spans": (C.c_int, [_P, _P, _P, _U64, _P, _P, _P]),
     "fei_dir_list_names": (C.c_int, [C.c_char_p, _P]),
-    "fei_host_arena_alloc": (C.c_int, [_U64, _P]),
+    "fei_host_arena_alloc": (C.c_int, [_U64, C.c_int, _P]),
     "fei_host_arena_free": (C.c_int, [_P, _U64]),
     "fei_read_dir_packed": (C.c_int, [C.c_char_p, _P, _P, _U64, _P, _U64, _P, _U64, C.c_int, _P, _P, _P, _P, _P]),
     "fei_corpus_synth": (C.c_int, [_P, _U64, _U64, _U64]),

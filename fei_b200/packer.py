@@ -195,7 +195,7 @@ class _Arena:
     def __init__(self, cap: int):
         self.cap = cap
         p = C.c_void_p()
-        _abi.check(_abi.lib().fei_host_arena_alloc(cap, C.byref(p)))
+        _abi.check(_abi.lib().fei_host_arena_alloc(cap, 1 if os.environ.get("FEI_ARENA_THP") else 0, C.byref(p)))
         self.addr = p.value
         self.cursor = C.c_uint64(0)
         self.buf = np.ctypeslib.as_array(C.cast(self.addr, C.POINTER(C.c_uint8)), shape=(cap,))
@@ -241,6 +241,24 @@ class _Arena:
         self.buf = None
         l.fei_host_arena_free(self.addr, self.cap)
         self.addr = None
+
+
+class _HostText:
+    """The exact host buffer of a cold pack: an anonymous mapping advised to use huge pages (where transparent huge pages are in
+    "madvise" mode a multi-GB numpy buffer is touched, and later unmapped, 4 KiB at a time: ~1 M page faults for 1 M files)."""
+
+    def __init__(self, n: int):
+        self.cap = max(1 << 21, -(-n // (1 << 21)) * (1 << 21))
+        p = C.c_void_p()
+        _abi.check(_abi.lib().fei_host_arena_alloc(self.cap, 0 if os.environ.get("FEI_HOST_THP", "1") == "0" else 1, C.byref(p)))
+        self.addr = p.value
+        self.buf = np.ctypeslib.as_array(C.cast(self.addr, C.POINTER(C.c_uint8)), shape=(self.cap,))[:max(1, n)]
+
+    def close(self) -> None:
+        if self.addr is not None:
+            self.buf = None
+            _abi.lib().fei_host_arena_free(self.addr, self.cap)
+            self.addr = None
 
 
 def read_dir_packed(path: str, d: DirListing, arena: _Arena) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -557,6 +575,9 @@ class PackedMemdir:
             raw = None
             if arena is not None:
                 arena.close()
+            if getattr(self, "_host_text", None) is not None:
+                self._host_text.close()
+                self._host_text = None
         pos = start = 0
         for key in order:                                              # drop the skipped entries from the listings; device id = listing position
             seg = segs[key]
@@ -629,7 +650,12 @@ class PackedMemdir:
             raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
         t1 = time.perf_counter()
         n = sum(segs[k].listing.n for k in order)
-        raw = np.empty(max(1, total), dtype=np.uint8)                  # 2. read every file into ONE buffer (native threads), directory by directory
+        try:
+            self._host_text = _HostText(total)
+            raw = self._host_text.buf                                  # 2. read every file into ONE buffer (native threads), directory by directory
+        except _abi.FeiError:
+            self._host_text = None
+            raw = np.empty(max(1, total), dtype=np.uint8)
         raw_off = np.zeros(n + 1, dtype=np.uint64)
         pos = base_off = 0
         exact = True

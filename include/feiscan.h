@@ -153,7 +153,7 @@ int fei_read_files(const char* dir, const uint8_t* names, const uint64_t* name_o
  * i, ino[i] / mtime_ns[i] come from the open file.  err[i] = errno; EFBIG = larger than max_file_bytes (len[i] = its size, not
  * read), ENOMEM = the arena is full.  fei_host_arena_alloc maps address space without committing memory (MAP_NORESERVE): size it
  * for the largest tree, only the bytes read become resident.                                                                  */
-int fei_host_arena_alloc(uint64_t bytes, void** out);
+int fei_host_arena_alloc(uint64_t bytes, int huge_pages, void** out);   /* huge_pages: madvise(MADV_HUGEPAGE) on the mapping */
 int fei_host_arena_free(void* p, uint64_t bytes);
 int fei_read_dir_packed(const char* dir, const uint8_t* names, const uint64_t* name_off, uint64_t n, uint8_t* arena, uint64_t arena_cap,
                         uint64_t* cursor, uint64_t max_file_bytes, int threads, uint64_t* begin, uint64_t* len, uint64_t* ino,

@@ -284,7 +284,7 @@ def test_cold_pack_without_stat_pass_equals_default(gpu, tmp_path, capsys, monke
     U.set_memdir_base(base)
     try:
         conds = [("content", "matches", "python|rust"), ("flags", "has_flag", "S")]
-        want = _oracle_keys(base, conds)
+        want = _oracle_keys(base, conds, True)
         results = {}
         for arena in ("0", "1"):
             monkeypatch.setenv("FEI_COLD_ARENA", arena)
