@@ -42,6 +42,7 @@ REC_NO_SEPARATOR, REC_NONASCII, REC_HAS_SIGMA, REC_HAS_IDOT = 1, 2, 4, 8
 _LIST_RE = re.compile(r"\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*")          # utils.py:223
 MAX_BODY = 32 << 20                                                # packed layout limit per record (corpus.cu)
 MAX_RAW_BATCH = 40 << 30                                           # raw bytes packed in one go
+LIST_CONCURRENCY = 4                                                # directories listed at the same time in a cold pack
 READ_THREADS = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
 _KEY_DT = np.dtype([("ino", "u8"), ("size", "u8"), ("mtime", "i8")])
 
@@ -572,12 +573,14 @@ class PackedMemdir:
                     segs[key].bad_files[L.name_bytes(i)] = (int(L.ino[i]), int(L.size[i]), int(L.mtime_ns[i]))
             raw_bytes = int(ln.sum())
         finally:
+            tf = time.perf_counter()
             raw = None
             if arena is not None:
                 arena.close()
             if getattr(self, "_host_text", None) is not None:
                 self._host_text.close()
                 self._host_text = None
+            free_s = time.perf_counter() - tf
         pos = start = 0
         for key in order:                                              # drop the skipped entries from the listings; device id = listing position
             seg = segs[key]
@@ -598,6 +601,7 @@ class PackedMemdir:
         self._rebuild_listing()
         self.timing.update({"pack_s": t3 - t2, "listing_arrays_s": time.perf_counter() - t3, "files": n, "raw_bytes": raw_bytes})
         self.timing.update(stage_times)
+        self.timing["free_host_text_s"] = free_s
         try:
             st = np.zeros(3, dtype=np.float32)
             _abi.check(_abi.lib().fei_corpus_last_load_timing(corpus.handle, _abi.ptr(st)))
@@ -641,8 +645,10 @@ class PackedMemdir:
         (fei_corpus_stage_text, a pageable copy on its own thread) while the next directory is being read."""
         t0 = time.perf_counter()
         total = 0
-        for key in order:                                              # 1. list every directory (readdir + parallel stat, native)
-            listing, mt = self._list(*key)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max(1, min(LIST_CONCURRENCY, len(order)))) as ex:   # 1. list every directory (readdir + parallel stat, native):
+            listed = list(ex.map(lambda k: self._list(*k), order))                  #    readdir is serial per directory, so several at a time
+        for key, (listing, mt) in zip(order, listed):
             seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.zeros(listing.n, dtype=np.int64)
             segs[key] = seg
             total += int(listing.size.sum())
@@ -755,9 +761,14 @@ class PackedMemdir:
         rem_key: List[Tuple[int, int, int]] = []
         new_entries: List[Tuple[Tuple[str, str], np.ndarray]] = []
         any_change = False
-        for key in changed:
+        if len(changed) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(min(LIST_CONCURRENCY, len(changed))) as ex:
+                listed = list(ex.map(lambda k: self._list(*k), changed))
+        else:
+            listed = [self._list(*k) for k in changed]
+        for key, (listing, mt) in zip(changed, listed):
             old = self.segs.get(key)
-            listing, mt = self._list(*key)
             seg = _Seg(); seg.listing = listing; seg.mtime_ns = mt; seg.bad = list(listing.bad); seg.bad_files = {}; seg.dev = np.full(listing.n, -1, dtype=np.int64)
             fresh[key] = seg
             if (old is not None and old.listing.n == listing.n and old.listing.names == listing.names
