@@ -42,6 +42,8 @@ REC_NO_SEPARATOR, REC_NONASCII, REC_HAS_SIGMA, REC_HAS_IDOT = 1, 2, 4, 8
 _LIST_RE = re.compile(r"\d+\.[a-z0-9]+\.[^:]+:2,[A-Z]*")          # utils.py:223
 MAX_BODY = 32 << 20                                                # packed layout limit per record (corpus.cu)
 MAX_RAW_BATCH = 40 << 30                                           # raw bytes packed in one go
+COLD_CHUNK_BYTES = 256 << 20                                        # cold pack: bytes per host chunk
+COLD_SLOTS = 3                                                      # reused chunk buffers (one being read into, up to two being uploaded)
 LIST_CONCURRENCY = 4                                                # directories listed at the same time in a cold pack
 READ_THREADS = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
 _KEY_DT = np.dtype([("ino", "u8"), ("size", "u8"), ("mtime", "i8")])
@@ -140,6 +142,24 @@ def list_dir(path: str, want_stat: bool = True) -> DirListing:
         d.spans = np.insert(d.spans, pos, np.array(f["spans"], dtype=np.uint16), axis=0)
         d.n += 1
     return d
+
+
+def read_range_into(path: str, d: DirListing, lo: int, hi: int, out: np.ndarray) -> bool:
+    """Entries [lo, hi) of the listing read back to back into out[0 : sum(sizes)] (native threads).  False if any file could not
+    be read or no longer has its listed size (the caller then takes the careful path)."""
+    k = hi - lo
+    if k <= 0:
+        return True
+    a, b = int(d.name_off[lo]), int(d.name_off[hi])
+    nbuf = np.frombuffer(d.names, dtype=np.uint8)[a:b] if b > a else np.zeros(1, dtype=np.uint8)
+    name_off = np.ascontiguousarray(d.name_off[lo:hi + 1] - np.uint64(a))
+    sizes = d.size[lo:hi]
+    off = np.zeros(k + 1, dtype=np.uint64)
+    np.cumsum(sizes, out=off[1:])
+    got = np.zeros(k, dtype=np.uint64); err = np.zeros(k, dtype=np.int32)
+    _abi.check(_abi.lib().fei_read_files(os.fsencode(path), nbuf.ctypes.data, _abi.ptr(name_off), k, out.ctypes.data, _abi.ptr(off), READ_THREADS,
+                                        _abi.ptr(got), _abi.ptr(err)))
+    return not err.any() and bool((got == sizes).all())
 
 
 def read_files(path: str, d: DirListing, sel: Optional[np.ndarray] = None, out: Optional[np.ndarray] = None, out_base: int = 0
@@ -564,12 +584,20 @@ class PackedMemdir:
                 if valid.all():
                     break
                 alive = np.nonzero(keep)[0]
-                staged = False                                         # the second attempt uploads from the host buffer
+                staged = staged and raw is None                        # with a host buffer the second attempt uploads from it; without, the staged text stays
                 for j in alive[~valid].tolist():                       # undecodable files: reported and skipped (utils.py:247-248)
                     keep[j] = False
                     key, i = self._locate(segs, order, j)
                     L = segs[key].listing
-                    segs[key].bad.append(f"Error processing {L.name(i)}: {_decode_error(raw[int(begin[j]):int(begin[j] + ln[j])].tobytes())}")
+                    if raw is not None:
+                        blob = raw[int(begin[j]):int(begin[j] + ln[j])].tobytes()
+                    else:                                              # the text only exists on the device: read this one file again for the message
+                        try:
+                            with open(os.path.join(self._dir(*key), L.name(i)), "rb") as f:
+                                blob = f.read()
+                        except OSError:
+                            blob = b"\xff"
+                    segs[key].bad.append(f"Error processing {L.name(i)}: {_decode_error(blob)}")
                     segs[key].bad_files[L.name_bytes(i)] = (int(L.ino[i]), int(L.size[i]), int(L.mtime_ns[i]))
             raw_bytes = int(ln.sum())
         finally:
@@ -641,8 +669,11 @@ class PackedMemdir:
         return arena.buf[:max(1, total)], cat(begins, np.uint64), cat(lens, np.uint64), cat(errs, np.int32)
 
     def _cold_read_listed(self, order, segs, corpus=None):
-        """Listing with a stat of every entry, then reads into one exact buffer (the default).  Each directory's bytes are uploaded
-        (fei_corpus_stage_text, a pageable copy on its own thread) while the next directory is being read."""
+        """The default cold read: a listing with a stat of every entry (sizes known), then the files are read CHUNK by CHUNK into a
+        few reused host buffers; a side thread sends each finished chunk to its place in the device text (fei_corpus_stage_text, a
+        pageable copy) while the next chunk is being read.  The host never holds the whole text: ~1 GB of pages are touched (and
+        unmapped) instead of one page per file.  Any surprise (a file that vanished or changed size since it was listed) falls back
+        to the one-buffer path below."""
         t0 = time.perf_counter()
         total = 0
         from concurrent.futures import ThreadPoolExecutor
@@ -656,6 +687,90 @@ class PackedMemdir:
             raise NotImplementedError("tree larger than one packing batch; shard it over several corpora")
         t1 = time.perf_counter()
         n = sum(segs[k].listing.n for k in order)
+        if corpus is not None and total > 0 and os.environ.get("FEI_STAGE_UPLOAD", "1") != "0" and os.environ.get("FEI_COLD_CHUNKS", "1") != "0":
+            got = self._cold_read_chunked(order, segs, corpus, n, total)
+            if got is not None:
+                self.timing.update({"list_s": t1 - t0})
+                return got
+        return self._cold_read_one_buffer(order, segs, corpus, n, total, t0, t1)
+
+    def _cold_read_chunked(self, order, segs, corpus, n: int, total: int):
+        t1 = time.perf_counter()
+        slots: List[_HostText] = []
+        try:
+            for _ in range(COLD_SLOTS):
+                slots.append(_HostText(COLD_CHUNK_BYTES + MAX_BODY))
+        except _abi.FeiError:
+            for sl in slots:
+                sl.close()
+            return None
+        free: "queue.Queue[int]" = queue.Queue()
+        for k in range(COLD_SLOTS):
+            free.put(k)
+        jobs: "queue.Queue[Optional[Tuple[int, int, int]]]" = queue.Queue()
+        failed: List[BaseException] = []
+
+        def uploader():
+            while True:
+                job = jobs.get()
+                if job is None:
+                    return
+                slot, offset, nbytes = job
+                if not failed:
+                    try:
+                        corpus.stage_text(total, slots[slot].buf[:nbytes], offset)     # returns once the pageable source has been consumed
+                    except BaseException as e:                          # noqa: BLE001 -- the caller falls back to the one-buffer path
+                        failed.append(e)
+                free.put(slot)
+        th = threading.Thread(target=uploader, daemon=True)
+        th.start()
+        ok = True
+        base_off = 0
+        sizes_all = []
+        try:
+            for key in order:
+                L = segs[key].listing
+                if not L.n:
+                    continue
+                sizes_all.append(L.size)
+                cs = np.zeros(L.n + 1, dtype=np.int64)
+                np.cumsum(L.size.astype(np.int64), out=cs[1:])
+                lo = 0
+                while lo < L.n and ok and not failed:
+                    hi = int(np.searchsorted(cs, cs[lo] + COLD_CHUNK_BYTES, side="right")) - 1
+                    hi = min(L.n, max(hi, lo + 1))
+                    slot = free.get()
+                    nbytes = int(cs[hi] - cs[lo])
+                    ok = read_range_into(self._dir(*key), L, lo, hi, slots[slot].buf)
+                    if not ok:
+                        free.put(slot)
+                        break
+                    jobs.put((slot, base_off + int(cs[lo]), nbytes))
+                    lo = hi
+                if not ok or failed:
+                    break
+                base_off += int(cs[L.n])
+        finally:
+            t_reads_done = time.perf_counter()
+            jobs.put(None)
+            th.join()
+            tf = time.perf_counter()
+            for sl in slots:
+                sl.close()
+            t_freed = time.perf_counter()
+        if not ok or failed or base_off != total:
+            return None
+        sizes = np.concatenate(sizes_all).astype(np.uint64) if sizes_all else np.zeros(0, dtype=np.uint64)
+        begin = np.zeros(n, dtype=np.uint64)
+        if n > 1:
+            np.cumsum(sizes[:-1], out=begin[1:])
+        self._cold_total = total
+        self.timing = {"read_s": t_reads_done - t1, "upload_tail_s": tf - t_reads_done, "free_chunk_buffers_s": t_freed - tf,
+                       "cold_path": "listing with stat; files read in %d MiB chunks into %d reused host buffers, each chunk uploaded under the next read" % (COLD_CHUNK_BYTES >> 20, COLD_SLOTS)}
+        return None, begin, sizes, np.zeros(n, dtype=np.int32), True
+
+    def _cold_read_one_buffer(self, order, segs, corpus, n: int, total: int, t0: float, t1: float):
+        """Reads into one exact buffer (the careful path: per-file re-reads when something changed under the listing)."""
         try:
             self._host_text = _HostText(total)
             raw = self._host_text.buf                                  # 2. read every file into ONE buffer (native threads), directory by directory
@@ -748,7 +863,7 @@ class PackedMemdir:
             name_off = np.zeros(len(idx) + 1, dtype=np.uint64); np.cumsum(nlen[idx], out=name_off[1:])
             ts, wall, f8, fsb, spans = ts[idx], wall[idx], f8[idx], fsb[idx], spans[idx]
         n = len(ts)
-        return {"n": n, "global_base": 0, "raw": raw, "raw_bytes": len(raw), "raw_begin": np.ascontiguousarray(sel_begin, dtype=np.uint64),
+        return {"n": n, "global_base": 0, "raw": raw, "raw_bytes": len(raw) if raw is not None else int(self._cold_total), "raw_begin": np.ascontiguousarray(sel_begin, dtype=np.uint64),
                 "raw_len": np.ascontiguousarray(sel_len, dtype=np.uint64), "name": name if n else None,
                 "name_off": name_off if n else None, "name_spans": np.ascontiguousarray(spans.reshape(-1)) if n else None,
                 "ts": np.ascontiguousarray(ts), "wall": np.ascontiguousarray(wall), "flags8": np.ascontiguousarray(f8), "fsb": np.ascontiguousarray(fsb)}

@@ -286,16 +286,21 @@ def test_cold_pack_without_stat_pass_equals_default(gpu, tmp_path, capsys, monke
         conds = [("content", "matches", "python|rust"), ("flags", "has_flag", "S")]
         want = _oracle_keys(base, conds, True)
         results = {}
-        for arena in ("0", "1"):
-            monkeypatch.setenv("FEI_COLD_ARENA", arena)
+        for arena in ("0", "tiny-chunks", "one-buffer", "1"):
+            monkeypatch.setenv("FEI_COLD_ARENA", "1" if arena == "1" else "0")
+            monkeypatch.setenv("FEI_COLD_CHUNKS", "0" if arena == "one-buffer" else "1")
+            monkeypatch.setattr(packer, "COLD_CHUNK_BYTES", 50_000 if arena == "tiny-chunks" else 256 << 20)   # many chunks per directory, slots reused
             packer.drop()
             got = search_memories(_query(conds, True))
             pm = packer.packed()
             assert "badbad03" in capsys.readouterr().out
-            assert pm.timing["cold_path"].startswith("names-only" if arena == "1" else "listing with stat")
+            path_name = pm.timing["cold_path"]
+            assert path_name.startswith("names-only" if arena == "1" else "listing with stat")
+            assert ("reused host buffers" in path_name) == (arena in ("0", "tiny-chunks")) and ("one exact buffer" in path_name) == (arena == "one-buffer")
             assert [key_of(m) for m in got] == want != []
             results[arena] = [(m["filename"], m["headers"], m["content"]) for m in got]
-        assert results["0"] == results["1"]
+        assert results["0"] == results["1"] == results["tiny-chunks"] == results["one-buffer"]
+        monkeypatch.setenv("FEI_COLD_ARENA", "1"); monkeypatch.setenv("FEI_COLD_CHUNKS", "1")
         victim = search_memories(_query([("flags", "has_flag", "F")], False))[0]          # still on the arena-packed corpus
         path = os.path.join(U.get_memory_path(victim["folder"], victim["status"]), victim["filename"])
         text = open(path).read()
