@@ -168,7 +168,13 @@ __device__ __forceinline__ bool cmp_i64(int64_t v, int64_t o, uint32_t op) {
 }
 __device__ __forceinline__ bool eval_meta_cond(const HeadArgs& a, uint64_t rec, const fei_prog_cond& cd, uint32_t flags_acc, int64_t wall, uint32_t fsb) {
   switch (cd.kind) {
-    case FEI_C_RECBITS: return (a.aux[cd.ref & (FEI_MAX_AUX - 1)][rec] != 0) != (cd.negate != 0);
+    case FEI_C_RECBITS: {
+      // selected, not indexed: a dynamic index into the by-value kernel argument makes ptxas copy the whole struct to local memory
+      const uint32_t k = cd.ref & (FEI_MAX_AUX - 1);
+      static_assert(FEI_MAX_AUX == 4, "aux column select below");
+      const uint8_t* col = k == 0 ? a.aux[0] : k == 1 ? a.aux[1] : k == 2 ? a.aux[2] : a.aux[3];
+      return (col[rec] != 0) != (cd.negate != 0);
+    }
     case FEI_C_TS_CMP: return cmp_i64(a.ts[rec], cd.i64, cd.cmp_op);
     case FEI_C_CONST: return cd.bit != 0;
     case FEI_C_FLAGS: return ((flags_acc >> cd.bit) & 1u) != cd.negate;
@@ -219,6 +225,24 @@ __device__ __forceinline__ uint32_t format_datetime(int64_t wall, uint8_t* out) 
   out[11] = '0' + hh / 10; out[12] = '0' + hh % 10; out[13] = ':'; out[14] = '0' + mi / 10; out[15] = '0' + mi % 10; out[16] = ':';
   out[17] = '0' + ss / 10; out[18] = '0' + ss % 10;
   return 19;
+}
+
+// File-name fields and the strings Python would format from the metadata (rare predicates): kept out of line so that their
+// buffers and divisions do not cost the common header path registers.  (Arguments by value: a reference to the kernel's by-value
+// HeadArgs, like a dynamic index into one of its arrays, makes ptxas copy the whole struct to local memory -- that, via the aux
+// column array, took the cfg2 head pass from 0.18 to 0.41 ms before it was noticed in the bench.)
+struct NameArgs { const uint8_t* prog; const uint8_t* name; const uint64_t* name_off; const uint16_t* name_spans; const int64_t* ts; const int64_t* wall; bool prog_in_smem; };
+__device__ __noinline__ void eval_name_fields(const NameArgs a, const fei_prog_hdr* ph, uint64_t rec, uint32_t* name_acc) {
+  for (int k = 0; k < 3; ++k) {
+    if (!ph->off_name_dfa[k]) continue;
+    const uint8_t* nb = a.name + a.name_off[rec];
+    uint32_t nl = (uint32_t)(a.name_off[rec + 1] - a.name_off[rec]);
+    if (k > 0) { const uint16_t* sp = a.name_spans + 4 * rec + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
+    name_acc[k] = dfa_run_at(a.prog, ph->off_name_dfa[k], a.prog_in_smem, nb, nl);
+  }
+  // str(timestamp) and str(datetime.fromtimestamp(ts))
+  if (ph->off_meta_dfa[0]) { uint8_t buf[24]; const uint32_t nl = format_u64(a.ts[rec] < 0 ? 0ull : (unsigned long long)a.ts[rec], buf); name_acc[3] = dfa_run_at(a.prog, ph->off_meta_dfa[0], a.prog_in_smem, buf, nl); }
+  if (ph->off_meta_dfa[1]) { uint8_t buf[24]; const uint32_t nl = format_datetime(a.wall[rec], buf); name_acc[4] = dfa_run_at(a.prog, ph->off_meta_dfa[1], a.prog_in_smem, buf, nl); }
 }
 
 // Phase 2 for one record: header fields (if `parse`), name fields, evaluation of the queries left in `pre`.
@@ -346,18 +370,7 @@ __device__ void head_finish(const HeadArgs& a, uint64_t rec, uint32_t pre, uint3
       present |= 1u << s;
     }
   uint32_t name_acc[FEI_NAME_FIELDS] = {0, 0, 0, 0, 0};
-  if (pre & ph->name_mask) {
-    for (int k = 0; k < 3; ++k) {
-      if (!ph->off_name_dfa[k]) continue;
-      const uint8_t* nb = a.name + a.name_off[rec];
-      uint32_t nl = (uint32_t)(a.name_off[rec + 1] - a.name_off[rec]);
-      if (k > 0) { const uint16_t* sp = a.name_spans + 4 * rec + 2 * (k - 1); nb += sp[0]; nl = sp[1]; }
-      name_acc[k] = dfa_run_at(a.prog, ph->off_name_dfa[k], a.prog_in_smem, nb, nl);
-    }
-    // strings Python would format from the metadata: str(timestamp) and str(datetime.fromtimestamp(ts))
-    if (ph->off_meta_dfa[0]) { uint8_t buf[24]; const uint32_t nl = format_u64(a.ts[rec] < 0 ? 0ull : (unsigned long long)a.ts[rec], buf); name_acc[3] = dfa_run_at(a.prog, ph->off_meta_dfa[0], a.prog_in_smem, buf, nl); }
-    if (ph->off_meta_dfa[1]) { uint8_t buf[24]; const uint32_t nl = format_datetime(a.wall[rec], buf); name_acc[4] = dfa_run_at(a.prog, ph->off_meta_dfa[1], a.prog_in_smem, buf, nl); }
-  }
+  if (pre & ph->name_mask) eval_name_fields(NameArgs{a.prog, a.name, a.name_off, a.name_spans, a.ts, a.wall, (bool)a.prog_in_smem}, ph, rec, name_acc);
   uint32_t alive = 0;
   for (uint32_t q = 0; q < ph->n_queries; ++q) {
     if (!(pre >> q & 1)) continue;

@@ -1148,28 +1148,40 @@ class PackedMemdir:
             if not len(sel):
                 continue
             hdr, ho, body, bo = corpus.fetch_records(dev[sel] - lo, want_body=include_content)
+            ho_l = ho.tolist()
+            bo_l = bo.tolist() if include_content else None
             for k, j in enumerate(sel.tolist()):
-                hdr_text[j] = hdr[int(ho[k]):int(ho[k + 1])].decode("utf-8")
+                hdr_text[j] = hdr[ho_l[k]:ho_l[k + 1]].decode("utf-8")
                 if include_content:
-                    body_text[j] = body[int(bo[k]):int(bo[k + 1])].decode("utf-8")
+                    body_text[j] = body[bo_l[k]:bo_l[k + 1]].decode("utf-8")
         keys, starts = self._segment_index()
         which = np.searchsorted(starts, positions, side="right") - 1
-        out = []
-        for j, p in enumerate(positions.tolist()):
-            key = keys[int(which[j])]
+        out: List[Optional[Dict[str, Any]]] = [None] * m
+        fromts = datetime.fromtimestamp
+        for w in np.unique(which).tolist():                             # per directory: pull the columns of its hits out as Python lists once
+            key = keys[w]
             L = self.segs[key].listing
-            i = p - self.segments[key][0]
-            nb = L.name_bytes(i)
-            sp = L.spans[i]
-            flags = int(L.flags8[i])
-            mem = {"filename": os.fsdecode(nb), "folder": key[0], "status": key[1], "headers": _headers_of(hdr_text[j]),
-                   "metadata": {"timestamp": int(L.ts[i]), "unique_id": os.fsdecode(nb[int(sp[0]):int(sp[0]) + int(sp[1])]),
-                                "hostname": os.fsdecode(nb[int(sp[2]):int(sp[2]) + int(sp[3])]),
-                                "flags": [chr((flags >> (8 * k)) & 0xFF) for k in range(flags >> 56)], "date": datetime.fromtimestamp(int(L.ts[i]))}}
-            if include_content:
-                mem["content"] = body_text[j]
-            out.append(mem)
-        return out
+            js = np.nonzero(which == w)[0]
+            idx = positions[js] - self.segments[key][0]
+            no = L.name_off
+            a_l, b_l = no[idx].tolist(), no[idx + 1].tolist()
+            sp_l = L.spans[idx].tolist()
+            ts_l = L.ts[idx].tolist()
+            f8_l = L.flags8[idx].tolist()
+            names = L.names
+            folder, status = key
+            for t, j in enumerate(js.tolist()):
+                nb = names[a_l[t]:b_l[t]]
+                s0, l0, s1, l1 = sp_l[t]
+                flags = f8_l[t]
+                ts = ts_l[t]
+                mem = {"filename": os.fsdecode(nb), "folder": folder, "status": status, "headers": _headers_of(hdr_text[j]),
+                       "metadata": {"timestamp": ts, "unique_id": os.fsdecode(nb[s0:s0 + l0]), "hostname": os.fsdecode(nb[s1:s1 + l1]),
+                                    "flags": [chr((flags >> (8 * k)) & 0xFF) for k in range(flags >> 56)], "date": fromts(ts)}}
+                if include_content:
+                    mem["content"] = body_text[j]
+                out[j] = mem
+        return out  # type: ignore[return-value]
 
     # ---- per-record header values for conditions only Python can judge (search.py:126-130)
     def header_values(self, field: str) -> Tuple[np.ndarray, np.ndarray, List[str]]:
