@@ -338,11 +338,16 @@ def main():
                         "SURVEY 8(d)'s 3626 B/memory figure includes ~152 B of header text"}
 
     workload = "memdir-32pattern-batch (BASELINE configs[2]): 32 `content matches` regexes, one pass; per step: hit masks + ordered per-query hit lists on the device"
+    exchange_how = None
     if world > 1:
+        exchange_how = ("the warp that completes a 4096-record window stores its hit masks into every rank's buffer from inside the scan kernel (peer memory over NVLink, CUDA IPC)"
+                        if p2p and lib.fei_comm_last_exchange_in_kernel() else
+                        "a finished chunk's masks leave with peer-memory copies (copy engines, CUDA IPC) under the next chunk's scan" if p2p else
+                        "a finished chunk's masks leave with a grouped ncclBroadcast under the next chunk's scan")
         workload = ("memdir-32pattern-batch over %d range shards (BASELINE configs[4] / cfg5 batch leg): every rank scans its shard (masks + ordered local lists, the "
                     "single-GPU work) and the step ENDS when every rank holds the hit masks of all shards (rank-major = global listing order) and the global "
-                    "per-query totals; masks are the wire format because 97-100 %% of the records hit (8 B/hit lists would be 16x larger); the exchange of a "
-                    "finished chunk (%s) runs under the next chunk's scan" % (world, "peer-memory copies over NVLink, CUDA IPC" if p2p else "grouped ncclBroadcast"))
+                    "per-query totals; masks are the wire format because 97-100 %% of the records hit (8 B/hit lists would be 16x larger); the exchange is "
+                    "fused into the scan: %s" % (world, exchange_how))
     line = {
         "metric": METRIC, "value": value, "unit": "memories/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",

@@ -130,6 +130,7 @@ _SIGS = {
     "fei_comm_allgather_hits": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "fei_comm_allreduce_first_bad": (C.c_int, [_P, _P]),
     "fei_comm_bind_corpus": (C.c_int, [_P]),
+    "fei_comm_last_exchange_in_kernel": (C.c_int, []),
     "fei_comm_is_p2p": (C.c_int, []),
     "fei_comm_scan_gather": (C.c_int, [_P, _P, _U64, _P]),
     "fei_comm_gathered_checksum": (C.c_int, [C.c_uint32, _P, _P, _P]),

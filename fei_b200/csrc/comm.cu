@@ -49,9 +49,11 @@ struct Nccl {
   uint64_t n_max = 0, n_total = 0;
   DevBuf gathered_masks, totals_dev;
   std::vector<void*> peer_masks;
+  DevBuf peer_ptrs;                      // the same pointers as a device array (what the scan kernel stores through)
   bool p2p = false;
   uint64_t* totals_host = nullptr;       // pinned
   // ---- what the last gather left on the device (fei_comm_gathered_checksum / fei_comm_global_lists)
+  bool last_pushed = false;              // the last fei_comm_scan_gather moved its masks from inside the scan kernel
   int last_kind = 0;                     // 0 none, 1 dense masks in gathered_masks, 2 sparse lists in `gathered`, 3 dense masks in `gathered` (fei_comm_allgather_hits)
   uint32_t last_nq = 0;
   uint64_t last_tot[32] = {0}, last_qbase[33] = {0};
@@ -93,6 +95,7 @@ struct GatherHook : ChunkHook {
   fei_corpus* c; uint32_t chunks;
   int on_chunk(uint32_t k, uint32_t n_chunks, uint64_t rb, uint64_t re, cudaStream_t side) override {
     const int R = g.nranks, me = g.rank;
+    if (g.p2p && pushed) return FEI_OK;                              // the scan kernel stores each finished window into the peers itself
     if (g.p2p) {
       if (re > rb)
         for (int i = 0; i < R; ++i) {
@@ -146,6 +149,7 @@ extern "C" int fei_comm_bind_corpus(fei_corpus* c) {
   FEI_CUDA(cudaStreamSynchronize(s));
   g.shard_n.assign(R, 0); g.shard_base.assign(R, 0); g.n_max = 0; g.n_total = 0;
   for (int r = 0; r < R; ++r) { g.shard_n[r] = info[2 * r]; g.shard_base[r] = info[2 * r + 1]; g.n_total += g.shard_n[r]; if (g.shard_n[r] > g.n_max) g.n_max = g.shard_n[r]; }
+  g.n_max = (g.n_max + 3) & ~3ull;                                // rank segments start 16-byte aligned: the scan kernel stores whole windows with 16-byte stores
   FEI_TRY(g.gathered_masks.alloc(((size_t)R * g.n_max + 1) * sizeof(uint32_t)));     // a fresh allocation: the IPC handle names exactly this buffer
   FEI_TRY(g.totals_dev.ensure(32 * sizeof(uint64_t)));
   if (!g.totals_host) FEI_CUDA(cudaMallocHost(&g.totals_host, 32 * sizeof(uint64_t)));
@@ -177,12 +181,20 @@ extern "C" int fei_comm_bind_corpus(fei_corpus* c) {
   FEI_CUDA(cudaMemcpyAsync(&flag, g.totals_dev.p, 8, cudaMemcpyDeviceToHost, s));
   FEI_CUDA(cudaStreamSynchronize(s));
   g.p2p = flag != 0;
+  if (g.p2p) {
+    FEI_TRY(g.peer_ptrs.ensure((size_t)R * sizeof(void*)));
+    FEI_CUDA(cudaMemcpyAsync(g.peer_ptrs.p, g.peer_masks.data(), (size_t)R * sizeof(void*), cudaMemcpyHostToDevice, s));
+    FEI_CUDA(cudaStreamSynchronize(s));
+  }
   if (!g.p2p) { for (int r = 0; r < R; ++r) if (r != g.rank && g.peer_masks[r]) { cudaIpcCloseMemHandle(g.peer_masks[r]); g.peer_masks[r] = nullptr; } }
   g.bound = c;
   return FEI_OK;
 }
 
 extern "C" int fei_comm_is_p2p(void) { return g.p2p ? 1 : 0; }
+/* 1 if the last fei_comm_scan_gather exchanged its hit masks with stores from inside the scan kernel (peer memory), 0 if copy
+ * engines / NCCL moved them chunk by chunk. */
+extern "C" int fei_comm_last_exchange_in_kernel(void) { return g.last_pushed ? 1 : 0; }
 
 // Collective.  Scan + ordered local lists exactly like fei_scan_count, cut into chunks; the masks of a finished chunk
 // travel to every rank while the next chunk is scanned.  On return every rank holds the hit masks of ALL shards
@@ -201,7 +213,12 @@ extern "C" int fei_comm_scan_gather(fei_corpus* c, const uint8_t* prog, uint64_t
   if (chunks > kMaxHookChunks) chunks = kMaxHookChunks;
   if (chunks < 1) chunks = 1;
   GatherHook hook; hook.c = c; hook.chunks = chunks;
+  const char* kp = getenv("FEI_COMM_KERNEL_PUSH");
+  if (g.p2p && !(kp && kp[0] == '0')) {                            // fused exchange: peer stores from inside the scan kernel
+    hook.push_peers = reinterpret_cast<uint32_t* const*>(g.peer_ptrs.p); hook.push_n = (uint32_t)g.nranks; hook.push_off = (uint64_t)g.rank * g.n_max;
+  }
   FEI_TRY(run_scan(c, prog, prog_len, kScanCompactLists, &hook, chunks));
+  g.last_pushed = hook.pushed;
   FEI_TRY(finish_timing(c, true));
   g.last_kind = 1; g.last_nq = c->last_nq; g.last_nmax = g.n_max; g.last_n = g.shard_n; g.last_base = g.shard_base;
   for (uint32_t q = 0; q < 32; ++q) g.last_tot[q] = q < c->last_nq ? g.totals_host[q] : 0;

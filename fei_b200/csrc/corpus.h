@@ -90,6 +90,10 @@ int exclusive_scan_u32_u64(const uint32_t* in, uint64_t n, uint64_t* out, DevBuf
 // Hook of a chunked scan: on_chunk is called on the host right after the work that makes the hit masks of records
 // [rec_begin, rec_end) final has been queued, with `side` already waiting for it; on_done after the last chunk.
 struct ChunkHook {
+  // multi-GPU: if set, the scan kernel itself stores every finished window's hit masks into these peer buffers (device array of
+  // push_n pointers, one per rank incl. this one; this rank's records start at element push_off of each).  run_scan sets `pushed`
+  // when the launch it queued does that (k_body / k_body_sticky with window counters); otherwise on_chunk must move the masks.
+  uint32_t* const* push_peers = nullptr; uint32_t push_n = 0; uint64_t push_off = 0; bool pushed = false;
   virtual int on_chunk(uint32_t k, uint32_t n_chunks, uint64_t rec_begin, uint64_t rec_end, cudaStream_t side) = 0;
   virtual int on_done(cudaStream_t side) { return FEI_OK; }
   virtual ~ChunkHook() {}

@@ -586,13 +586,44 @@ struct BodyArgs {
   // window w (groups [w * kWindow / 32, (w + 1) * kWindow / 32)) is finished when win_done[w] reaches kWindow / 32: the side stream
   // waits on these counters (k_wait_windows) to compact / send a finished run of windows while this kernel is still scanning
   unsigned int* win_done;
+  // multi-GPU, fused exchange: the warp that completes a window stores the window's 4096 hit masks into every rank's rank-major
+  // mask buffer (peer memory over NVLink / NVSwitch, mapped with CUDA IPC) -- the transfer of a finished window runs under the scan
+  // of the next ones, from inside the scan kernel.  push_peers is a DEVICE array (a dynamic index into this by-value struct would
+  // make ptxas copy it to local memory).
+  uint32_t* const* push_peers; uint32_t push_n; unsigned long long push_off, n_records;
 };
 constexpr uint32_t kGroupsPerWindow = kWindow / 32;
+__device__ __noinline__ void publish_window(const uint32_t* __restrict__ hits, uint32_t* const* __restrict__ peers, uint32_t n_peers,
+                                            unsigned long long off, unsigned long long n_records, unsigned long long w, int lane) {
+  __threadfence();                                   // acquire side of the window counter: the other groups' masks are visible now
+  const unsigned long long r0 = w * kWindow;
+  const uint32_t cnt = (uint32_t)((n_records - r0) < kWindow ? (n_records - r0) : kWindow);
+  const uint32_t* src = hits + r0;                   // 16 KiB aligned; the destination is 16-byte aligned too (n_max is a multiple of 4)
+  for (uint32_t p = 0; p < n_peers; ++p) {
+    uint32_t* dst = peers[(p + (uint32_t)w) % n_peers];        // successive windows start with different ranks
+    if (!dst) continue;
+    dst += off + r0;
+    for (uint32_t i = lane * 4u; i < cnt; i += 128u) {
+      if (i + 4u <= cnt) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));        // L2: another SM wrote them
+        *reinterpret_cast<uint4*>(dst + i) = v;
+      } else {
+        for (uint32_t j = i; j < cnt; ++j) dst[j] = __ldcg(src + j);
+      }
+    }
+  }
+  __threadfence_system();                            // the remote stores are ordered before this kernel's completion is observed
+}
 __device__ __forceinline__ void signal_group_done(const BodyArgs& a, unsigned long long g, int lane) {
   if (!a.win_done) return;
   __threadfence();                                   // this lane's hit mask is visible device-wide ...
   __syncwarp();
-  if (lane == 0) atomicAdd(a.win_done + g / kGroupsPerWindow, 1u);   // ... before the group counts as done
+  unsigned int old = 0;
+  if (lane == 0) old = atomicAdd(a.win_done + g / kGroupsPerWindow, 1u);   // ... before the group counts as done
+  if (a.push_n) {
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old + 1u == kGroupsPerWindow) publish_window(a.hits, a.push_peers, a.push_n, a.push_off, a.n_records, g / kGroupsPerWindow, lane);
+  }
 }
 
 constexpr int kBodyThreads = 1024;
@@ -1497,7 +1528,9 @@ int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_
     k_body_gather<<<grid, kBodyThreads, smem, s>>>(a, c->live_list.as<uint32_t>(), c->rec_pos.as<uint32_t>());
     launches += 2;
   }
-  if (watermark && plan.n > 1) {
+  const bool push = watermark && hook && hook->push_peers && hook->push_n;
+  if (watermark && (plan.n > 1 || push)) {
+    if (push) { a.push_peers = hook->push_peers; a.push_n = hook->push_n; a.push_off = hook->push_off; a.n_records = n; hook->pushed = true; }
     FEI_TRY(c->win_done.ensure((n_windows + 1) * sizeof(unsigned int)));
     FEI_CUDA(cudaMemsetAsync(c->win_done.p, 0, (n_windows + 1) * sizeof(unsigned int), s));
     a.win_done = c->win_done.as<unsigned int>();

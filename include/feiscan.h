@@ -347,6 +347,7 @@ int fei_comm_allgather_hits(fei_corpus* c, uint32_t nq, uint64_t* const* hits, c
  * failed mapping on any rank, keeps the exchange on NCCL.  fei_comm_is_p2p() says which.        */
 int fei_comm_bind_corpus(fei_corpus* c);
 int fei_comm_is_p2p(void);
+int fei_comm_last_exchange_in_kernel(void);   /* 1: the last fei_comm_scan_gather stored its masks into the peers from inside the scan kernel */
 /* Collective: the scan of fei_scan_count (masks + ordered local lists) with the hit all-gather
  * folded in: the scan runs in chunks, and the masks of a finished chunk are written into every
  * peer's buffer by copy-engine transfers (or a grouped ncclBroadcast) while the next chunk is

@@ -84,9 +84,10 @@ def main():
             print(f"[multi_gpu_check] {name}: all-gatherv over {world} ranks ok ({[int(x) for x in tot[:nq]]} hits)", flush=True)
         dist.barrier()
         # ---- the scan with the gather folded in, over peer memory and over NCCL, with several chunks
-        for p2p in ("1", "0"):
-            os.environ["FEI_COMM_P2P"] = p2p
-            os.environ["FEI_SCAN_CHUNKS"] = "3"
+        for p2p, push, chunks in (("1", "1", "3"), ("1", "1", "1"), ("1", "0", "3"), ("0", "1", "3")):
+            os.environ["FEI_COMM_P2P"] = p2p                 # peer memory (CUDA IPC) or NCCL
+            os.environ["FEI_COMM_KERNEL_PUSH"] = push        # peer stores from inside the scan kernel, or copy engines chunk by chunk
+            os.environ["FEI_SCAN_CHUNKS"] = chunks
             _abi.check(lib.fei_comm_bind_corpus(corpus.handle))
             tot2 = np.zeros(32, dtype=np.uint64)
             _abi.check(lib.fei_comm_scan_gather(corpus.handle, prog, len(prog), _abi.ptr(tot2)))
@@ -100,9 +101,12 @@ def main():
                     assert checksum(want[q]) == (int(ga[q]), int(gs[q])), (name, p, "checksum of the gathered masks")
                     mine = [i for i in want[q] if a <= i < b]
                     assert checksum(mine) == (int(la[q]), int(ls[q])), (name, p, "local lists")
-                print(f"[multi_gpu_check] {name}: scan+gather ({'peer memory' if lib.fei_comm_is_p2p() else 'NCCL'}, 3 chunks) ok", flush=True)
+                how = "NCCL" if not lib.fei_comm_is_p2p() else "peer stores inside the scan kernel" if lib.fei_comm_last_exchange_in_kernel() else "peer copies per chunk"
+                print(f"[multi_gpu_check] {name}: scan+gather ({how}, {chunks} chunk(s)) ok", flush=True)
+            if lib.fei_comm_is_p2p():
+                assert bool(lib.fei_comm_last_exchange_in_kernel()) == (push == "1"), "which path moved the masks"
             dist.barrier()
-        os.environ.pop("FEI_SCAN_CHUNKS"); os.environ.pop("FEI_COMM_P2P")
+        os.environ.pop("FEI_SCAN_CHUNKS"); os.environ.pop("FEI_COMM_P2P"); os.environ.pop("FEI_COMM_KERNEL_PUSH")
     # a query with header predicates: the head pass runs first, the content pass is chunked
     pb = ProgramBuilder()
     pb.add_query([Cond(C_FLAGS, pattern=Pattern("exact_contains", "F")), Cond(C_BODY, pattern=Pattern("regex", "python|rust", re.IGNORECASE))])
