@@ -59,8 +59,8 @@ class Corpus:
         else:
             rc = _abi.lib().fei_corpus_load_raw(self._h, C.byref(h), _abi.ptr(a["raw"]), _abi.ptr(a["raw_off"]), _abi.ptr(valid))
         valid = valid[:h.n].astype(bool)
-        if rc != 0 and valid.all():
-            _abi.check(rc)
+        if rc != 0 and not (_abi.lib().fei_last_error() or b"").startswith(b"some files are not valid UTF-8"):
+            _abi.check(rc)                     # anything but "drop the undecodable files and load again" is an error
         if rc == 0:
             self._keep = None                  # every host array was consumed before the call returned (the text may be a transient arena)
             self.n, self.global_base = h.n, h.global_base

@@ -384,6 +384,56 @@ def test_raw_ingest_fuzz_long_records(gpu):
         assert bool(bits[i] & 4) == ("Σ" in text) and bool(bits[i] & 8) == ("İ" in text), i
 
 
+def test_staged_text_and_spans_load_equal_plain_load(gpu):
+    """fei_corpus_stage_text + fei_corpus_load_raw_spans(raw=NULL): the text uploaded in pieces (any order) and files described by
+    (begin, len) spans -- with a gap and in shuffled order -- give the same corpus as the plain one-call load; a size mismatch
+    between what was staged and what the spans describe is refused."""
+    from fei_b200 import _abi
+    from fei_b200.corpus import Corpus
+    recs = []
+    for i in range(300):
+        r = synth.record(21, i); r["raw"] = synth.file_text(r).encode()
+        recs.append(r)
+    base = synth.arrays_from_records(recs)
+    meta = {k: base[k] for k in ("ts", "wall", "flags8", "fsb")}
+    lens = np.array([len(r["raw"]) for r in recs], dtype=np.uint64)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64); np.cumsum(lens, out=off[1:])
+    blob = np.frombuffer(b"".join(r["raw"] for r in recs), dtype=np.uint8).copy()
+    plain = Corpus()
+    assert plain.load_raw(dict(meta, n=len(recs), raw=blob, raw_off=off)).all()
+    want = plain.fetch(0, len(recs))
+    # spans: file i lives at a shuffled position behind a 1000-byte gap
+    rng = np.random.default_rng(5)
+    order = rng.permutation(len(recs))
+    begin = np.zeros(len(recs), dtype=np.uint64)
+    pos = 1000
+    for i in order.tolist():
+        begin[i] = pos; pos += int(lens[i]) + (int(i) % 3)
+    total = pos
+    scattered = np.full(total, ord("-"), dtype=np.uint8)                        # the gaps hold dashes: a reader that strays finds separators
+    for i in range(len(recs)):
+        scattered[int(begin[i]):int(begin[i] + lens[i])] = np.frombuffer(recs[i]["raw"], dtype=np.uint8)
+    spans = Corpus()
+    assert spans.load_raw(dict(meta, n=len(recs), raw=scattered, raw_bytes=total, raw_begin=begin, raw_len=lens)).all()
+    staged = Corpus()
+    cut = [0, total // 3, total // 2, total]
+    for a, b in reversed(list(zip(cut, cut[1:]))):                             # pieces in reverse order
+        staged.stage_text(total, scattered[a:b], a)
+    assert staged.load_raw(dict(meta, n=len(recs), raw=None, raw_bytes=total, raw_begin=begin, raw_len=lens)).all()
+    for c in (spans, staged):
+        got = c.fetch(0, len(recs))
+        for k in ("hdr", "hdr_off", "body", "body_off", "ts", "wall", "flags8", "fsb"):
+            assert np.array_equal(got[k], want[k]), k
+    pb = ProgramBuilder(); pb.add_query([Cond(C_BODY, pattern=Pattern("regex", "python|docker", re.IGNORECASE))])
+    assert staged.scan_hits(pb.build(), 1)[0].tolist() == plain.scan_hits(pb.build(), 1)[0].tolist() != []
+    bad = Corpus()
+    bad.stage_text(total + 8, scattered[:100], 0)
+    with pytest.raises(_abi.FeiError):
+        bad.load_raw(dict(meta, n=len(recs), raw=None, raw_bytes=total, raw_begin=begin, raw_len=lens))
+    with pytest.raises(_abi.FeiError):                                         # a span that leaves the buffer
+        bad.load_raw(dict(meta, n=len(recs), raw=scattered, raw_bytes=total - 5000, raw_begin=begin, raw_len=lens))
+
+
 def test_random_headers_differential(gpu):
     """Seeded fuzz of the device header parser (k_head / k_head_parse) against the oracle: random key spellings,
     duplicate keys, odd whitespace (incl. multi-byte), missing colons, colons in values, empty keys / values."""
