@@ -614,13 +614,16 @@ __device__ __noinline__ void publish_window(const uint32_t* __restrict__ hits, u
   }
   __threadfence_system();                            // the remote stores are ordered before this kernel's completion is observed
 }
+// kPush: the multi-GPU instantiation; the single-GPU kernels do not carry the exchange code (it cost 0.5 % of the headline
+// when it was compiled into the one kernel: a shuffle and a branch per group, and a different register allocation)
+template <bool kPush>
 __device__ __forceinline__ void signal_group_done(const BodyArgs& a, unsigned long long g, int lane) {
   if (!a.win_done) return;
   __threadfence();                                   // this lane's hit mask is visible device-wide ...
   __syncwarp();
   unsigned int old = 0;
   if (lane == 0) old = atomicAdd(a.win_done + g / kGroupsPerWindow, 1u);   // ... before the group counts as done
-  if (a.push_n) {
+  if (kPush && a.push_n) {
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old + 1u == kGroupsPerWindow) publish_window(a.hits, a.push_peers, a.push_n, a.push_off, a.n_records, g / kGroupsPerWindow, lane);
   }
@@ -685,7 +688,7 @@ struct BodyDfa {
   }
 };
 
-template <bool kDirect, int kAcc>
+template <bool kDirect, int kAcc, bool kPush>
 __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     const bool live = alive != 0;
     if (__ballot_sync(0xffffffffu, live) == 0) {              // nobody in this group can still match: skip its bytes
       if (rec != kInvalidRec && !a.has_alive) a.hits[rec] = 0;
-      signal_group_done(a, g, lane);
+      signal_group_done<kPush>(a, g, lane);
       continue;
     }
     const uint8_t* row = a.tiles + a.grp_base[g] * 16;
@@ -774,7 +777,7 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body(BodyArgs a) {
     } else if (rec != kInvalidRec && !a.has_alive) {
       a.hits[rec] = 0;
     }
-    signal_group_done(a, g, lane);
+    signal_group_done<kPush>(a, g, lane);
   }
   if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
@@ -820,6 +823,7 @@ constexpr unsigned long long kGatherDiv = 16;       // k_body_gather takes over 
 constexpr uint32_t kStickyAddrLimit = 65535u;
 constexpr uint32_t kStickyAddrSlack = 4096u;     // head-room the host leaves for the shared-memory window base
 
+template <bool kPush>
 __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -1057,8 +1061,8 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_sticky(BodyArgs a) {
     ragged_pair(A, B);
     close_group(A);
     close_group(B);
-    signal_group_done(a, g, lane);
-    if (g + 1 < a.n_groups) signal_group_done(a, g + 1, lane);
+    signal_group_done<kPush>(a, g, lane);
+    if (g + 1 < a.n_groups) signal_group_done<kPush>(a, g + 1, lane);
   }
   if (lane == 0 && touched) { atomicAdd(a.counter + 1, touched); atomicAdd(a.counter + 3, bytes_read); }
 }
@@ -1161,8 +1165,13 @@ __global__ void __launch_bounds__(kBodyThreads, 1) k_body_gather(BodyArgs a, con
 
 template <bool kDirect, int kAcc>
 static int launch_body(const BodyArgs& a, unsigned grid, size_t smem, cudaStream_t s) {
-  FEI_CUDA(cudaFuncSetAttribute(k_body<kDirect, kAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_body<kDirect, kAcc><<<grid, kBodyThreads, smem, s>>>(a);
+  if (a.push_n) {
+    FEI_CUDA(cudaFuncSetAttribute(k_body<kDirect, kAcc, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_body<kDirect, kAcc, true><<<grid, kBodyThreads, smem, s>>>(a);
+  } else {
+    FEI_CUDA(cudaFuncSetAttribute(k_body<kDirect, kAcc, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_body<kDirect, kAcc, false><<<grid, kBodyThreads, smem, s>>>(a);
+  }
   return FEI_OK;
 }
 
@@ -1499,8 +1508,13 @@ int run_scan(fei_corpus* c, const uint8_t* prog, uint64_t prog_len, int compact_
     int rc = FEI_OK;
     if (sticky_kernel) {
       const size_t smem_sticky = ((smem + 127) & ~(size_t)127) + kStickyRingBytes;
-      FEI_CUDA(cudaFuncSetAttribute(k_body_sticky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
-      k_body_sticky<<<grid, kBodyThreads, smem_sticky, s>>>(a);
+      if (a.push_n) {
+        FEI_CUDA(cudaFuncSetAttribute(k_body_sticky<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
+        k_body_sticky<true><<<grid, kBodyThreads, smem_sticky, s>>>(a);
+      } else {
+        FEI_CUDA(cudaFuncSetAttribute(k_body_sticky<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sticky));
+        k_body_sticky<false><<<grid, kBodyThreads, smem_sticky, s>>>(a);
+      }
     } else if (direct) rc = acc_mode == 3 ? launch_body<true, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<true, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<true, 2>(a, grid, smem, s) : launch_body<true, 0>(a, grid, smem, s);
     else rc = acc_mode == 3 ? launch_body<false, 3>(a, grid, smem, s) : acc_mode == 1 ? launch_body<false, 1>(a, grid, smem, s) : acc_mode == 2 ? launch_body<false, 2>(a, grid, smem, s) : launch_body<false, 0>(a, grid, smem, s);
     FEI_TRY(rc);
