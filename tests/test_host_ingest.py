@@ -91,3 +91,76 @@ def test_packed_read_reports_vanished_oversized_and_full_arena(tree, monkeypatch
                 assert tiny.buf[int(begin[i]):int(begin[i] + ln[i])].tobytes() == f.read()
     finally:
         tiny.close()
+
+
+class _RecordingCorpus:
+    """Stands in for fei_b200.corpus.Corpus on a box without a GPU: keeps what fei_corpus_stage_text would have been given."""
+
+    def __init__(self):
+        self.text = None
+
+    def stage_text(self, total, piece, offset):
+        if self.text is None or len(self.text) != total:
+            self.text = np.full(total, 0xEE, dtype=np.uint8)
+        self.text[offset:offset + len(piece)] = piece
+
+
+def _cold_read(tree, monkeypatch, chunk_bytes):
+    from fei_b200.memdir_tools import utils as U
+    monkeypatch.setattr(packer, "COLD_CHUNK_BYTES", chunk_bytes)
+    pm = packer.PackedMemdir(tree)
+    pm._set_folders(pm._walk())
+    order = pm._order()
+    segs = {}
+    corpus = _RecordingCorpus()
+    raw, begin, ln, err, staged = pm._cold_read_listed(order, segs, corpus)
+    return pm, order, segs, corpus, raw, begin, ln, err, staged
+
+
+@pytest.mark.parametrize("chunk_bytes", [10_000, 1 << 20, 256 << 20])
+def test_chunked_cold_read_stages_every_file_at_its_offset(tree, monkeypatch, chunk_bytes):
+    """The default cold read (listing with stat, chunks into reused buffers, each chunk staged at its offset in the device text):
+    whatever the chunk size, the staged text is the files back to back in listing order and (begin, len) point at them."""
+    pm, order, segs, corpus, raw, begin, ln, err, staged = _cold_read(tree, monkeypatch, chunk_bytes)
+    assert staged and raw is None and not err.any()
+    assert "reused host buffers" in pm.timing["cold_path"]
+    j = 0
+    for key in order:
+        L = segs[key].listing
+        for i in range(L.n):
+            with open(os.path.join(pm._dir(*key), L.name(i)), "rb") as f:
+                want = f.read()
+            assert int(ln[j]) == len(want) and corpus.text[int(begin[j]):int(begin[j] + ln[j])].tobytes() == want, (key, L.name(i))
+            j += 1
+    assert j == len(begin) > 3000 and int(begin[-1] + ln[-1]) == len(corpus.text)
+    assert not (corpus.text == 0xEE).all()
+
+
+def test_chunked_cold_read_falls_back_when_a_file_changes_under_the_listing(tree, monkeypatch):
+    """A file that shrank between the listing and the read: the chunked path gives up and the one-buffer path re-reads it."""
+    real_list = packer.list_dir
+    victim = {}
+
+    def list_then_truncate(path, want_stat=True):
+        L = real_list(path, want_stat)
+        if path.endswith(os.path.join("new")) and L.n and not victim:
+            victim["path"] = os.path.join(path, L.name(0)); victim["keep"] = open(victim["path"], "rb").read()
+            with open(victim["path"], "wb") as f:
+                f.write(victim["keep"][:10])
+        return L
+    monkeypatch.setattr(packer, "list_dir", list_then_truncate)
+    try:
+        pm, order, segs, corpus, raw, begin, ln, err, staged = _cold_read(tree, monkeypatch, 1 << 20)
+        assert victim and "one exact buffer" in pm.timing["cold_path"]
+        assert raw is not None
+        j = 0
+        for key in order:
+            L = segs[key].listing
+            for i in range(L.n):
+                with open(os.path.join(pm._dir(*key), L.name(i)), "rb") as f:
+                    assert raw[int(begin[j]):int(begin[j] + ln[j])].tobytes() == f.read()
+                j += 1
+    finally:
+        if victim:
+            with open(victim["path"], "wb") as f:
+                f.write(victim["keep"])
