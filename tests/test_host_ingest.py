@@ -164,3 +164,51 @@ def test_chunked_cold_read_falls_back_when_a_file_changes_under_the_listing(tree
         if victim:
             with open(victim["path"], "wb") as f:
                 f.write(victim["keep"])
+
+
+def test_native_listing_agrees_with_the_oracle_on_adversarial_file_names(tmp_path, capsys):
+    """fei_dir_list's file-name grammar (memdir_host.cpp parse_name; names it cannot judge go to Python) against the oracle's
+    read_folder (utils.py:216-251 restated): which names are listed, in which order, and timestamp / unique_id / hostname / flags."""
+    import random
+    from oracle import memdir_oracle as mo
+    rng = random.Random(77)
+    d = tmp_path / "Memdir" / "cur"
+    d.mkdir(parents=True)
+    fixed = ["1700000000.abc.host:2,", "1700000000.abc.host:2,FRS", "1700000001.a1b2.h.o.s.t:2,S", "1700000002.abc.host:2,Fjunk", "1700000003.abc.host:2,FSPRXYZQ",
+             "1700000004.ABC.host:2,S", "1700000005.abc.:2,S", "1700000006.abc.host:3,S", "1700000007..host:2,S", ".1700000008.abc.host:2,S", "x1700000009.abc.host:2,S",
+             "1700000010.abc.host:2", "1700000011.abc.ho:st:2,S", "1700000012.abc.host:2,S:2,T", "0.a.b:2,", "00000000000000000012.abc.host:2,S", "17000000130000000000000.abc.host:2,S",
+             "1700000014.abc.hôst:2,S", "١٧٠٠٠٠٠٠١٥.abc.host:2,S", "1700000016.abc.host :2,S", "1700000017.abc.host:2,s", "1700000018.ab_c.host:2,S",
+             "1700000019.abc.host:2,SSSSSSS", "1700000019.abd.host:2,", "1700000019.abb.host:2,", "999999999999.abc.host:2,S", "not-a-memory.txt", "1700000020.abc.host:2,F\nx"]
+    names = set(fixed)
+    while len(names) < 400:
+        ts = rng.choice(["17%08d" % rng.randrange(10 ** 8), str(rng.randrange(10 ** rng.randrange(1, 12))), "1700000100"])
+        uid = "".join(rng.choice("abc019xyzAB_.") for _ in range(rng.randrange(0, 6)))
+        host = "".join(rng.choice("hostä:.-2,") for _ in range(rng.randrange(0, 6)))
+        tail = rng.choice([":2,", ":2,S", ":2,FRS", ":2,Fx", ":2", ":1,S", "", ":2,SS:2,F"])
+        n = f"{ts}.{uid}.{host}{tail}"
+        if "/" not in n and "\0" not in n and 0 < len(n.encode()) < 200:
+            names.add(n)
+    for k, n in enumerate(sorted(names)):
+        (d / n).write_bytes(b"Subject: %d\n---\nbody %d\n" % (k, k))
+    want = mo.read_folder(str(tmp_path / "Memdir"), "", "cur", False)
+    printed = capsys.readouterr().out
+    L = packer.list_dir(str(d), True)
+    got = [L.name(i) for i in range(L.n)]
+    # year > 9999 etc.: the oracle prints "Error processing" and skips; the native listing reports the same names as bad
+    def reported(messages):
+        return sorted(n for n in names if any(m.startswith(f"Error processing {n}: ") for m in messages))
+    bad_native = reported(L.bad)
+    bad_oracle = reported(printed.splitlines())
+    unpackable = [n for n in bad_native if n not in bad_oracle]                  # > 7 flag letters: refused by the packed layout, loudly (DESIGN.md 6)
+    assert all(len(mo.split_filename(n)["flags"]) > 7 for n in unpackable), unpackable
+    assert [n for n in bad_native if n not in unpackable] == bad_oracle
+    want_names = [m["filename"] for m in want if m["filename"] not in unpackable]
+    # ties in timestamp keep os.listdir order in both (stable sorts over the same readdir order)
+    assert got == want_names
+    for i, m in enumerate(x for x in want if x["filename"] not in unpackable):
+        nb = L.name_bytes(i); sp = L.spans[i]; f8 = int(L.flags8[i])
+        assert int(L.ts[i]) == m["metadata"]["timestamp"], m["filename"]
+        assert os.fsdecode(nb[int(sp[0]):int(sp[0] + sp[1])]) == m["metadata"]["unique_id"], m["filename"]
+        assert os.fsdecode(nb[int(sp[2]):int(sp[2] + sp[3])]) == m["metadata"]["hostname"], m["filename"]
+        assert [chr((f8 >> (8 * k)) & 0xFF) for k in range(f8 >> 56)] == m["metadata"]["flags"], m["filename"]
+    assert len(got) > 50 and len(names) - len(got) > 100          # both sides of the grammar are exercised
