@@ -212,3 +212,47 @@ def test_native_listing_agrees_with_the_oracle_on_adversarial_file_names(tmp_pat
         assert os.fsdecode(nb[int(sp[2]):int(sp[2] + sp[3])]) == m["metadata"]["hostname"], m["filename"]
         assert [chr((f8 >> (8 * k)) & 0xFF) for k in range(f8 >> 56)] == m["metadata"]["flags"], m["filename"]
     assert len(got) > 50 and len(names) - len(got) > 100          # both sides of the grammar are exercised
+
+
+_WALL_CHECK = r"""
+import calendar, os, sys
+from datetime import datetime
+sys.path.insert(0, sys.argv[1])
+from fei_b200 import packer
+d = sys.argv[2]
+L = packer.list_dir(d, True)
+assert L.n > 500, L.n
+bad = 0
+for i in range(L.n):
+    ts = int(L.ts[i])
+    want = calendar.timegm(datetime.fromtimestamp(ts).timetuple())           # naive local wall clock, as utils.py:94 builds it
+    if int(L.wall[i]) != want:
+        bad += 1
+        print("MISMATCH", ts, int(L.wall[i]), want)
+print("checked", L.n, "bad", bad)
+sys.exit(1 if bad else 0)
+"""
+
+
+@pytest.mark.parametrize("tz", ["Europe/Prague", "America/New_York", "Australia/Lord_Howe", "UTC", "Asia/Kolkata"])
+def test_listing_wall_clock_equals_datetime_fromtimestamp_across_dst(tmp_path, tz):
+    """The listing's `wall` column (per-day UTC-offset cache in memdir_host.cpp) against datetime.fromtimestamp under zones with DST
+    (including Lord Howe's half-hour shift): timestamps packed around every transition of 2023-2025, on both sides, to the second."""
+    import subprocess, sys
+    if not os.path.exists(os.path.join("/usr/share/zoneinfo", tz)):
+        pytest.skip("no tzdata for " + tz)
+    d = tmp_path / "cur"
+    d.mkdir()
+    stamps = set()
+    for year in (2023, 2024, 2025):
+        for month, day in ((3, 10), (3, 12), (3, 26), (3, 31), (4, 2), (4, 7), (10, 1), (10, 6), (10, 27), (10, 29), (11, 3), (11, 5), (1, 1), (7, 1), (12, 31)):
+            base = int(__import__("calendar").timegm((year, month, day, 0, 0, 0)))
+            for h in range(-14, 40):
+                for delta in (-1, 0, 1, 1799, 1800, 1801, 3599):
+                    stamps.add(base + 3600 * h + delta)
+    stamps.update((0, 1, 59, 86399, 86400, 2 ** 31 - 1, 2 ** 31, 4102444800, 253402300799 - 86400 * 30))
+    for k, ts in enumerate(sorted(stamps)):
+        (d / f"{ts}.u{k}.host:2,S").write_bytes(b"x")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _WALL_CHECK, repo, str(d)], env=dict(os.environ, TZ=tz), capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
