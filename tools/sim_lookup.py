@@ -128,6 +128,18 @@ def main():
         print(f"  top-{K} rows private per lane ({K * 32 * 2 * 32 // 1024} KB) + shared class-indexed table: {np.mean(share):.2f} of the lanes hot; "
               f"one mixed LDS {np.mean(one):.2f} wavefronts, hot and cold as two LDS {np.mean(two):.2f} (plus the byte -> class lookup)")
 
+    # ---- splitting the pattern set (one read of the bytes feeds k sub-automata, each with its own table and its own lookup per byte)
+    for k in (2, 4):
+        parts = [bench.BATCH32[i::k] for i in range(k)]
+        subs = [compile_patterns([Pattern("regex", p, re.IGNORECASE) for p in part]) for part in parts]
+        states = [x.ctrans.shape[0] for x in subs]
+        u8 = all(n_ <= 256 for n_ in states)
+        kb = sum(n_ * 32 * (1 if u8 else 2) for n_ in states) / 1024
+        copies = int(227 // kb) if kb else 0
+        per = 1.0 if copies >= 32 else 2.0 if copies >= 16 else 2.9 if copies >= 8 else 3.2
+        print(f"  {k} sub-automata of {32 // k} patterns: {states} states, class-indexed {'u8' if u8 else 'u16'} tables {kb:.1f} KB together -> at most {copies} bank-confined copies "
+              f"(~{per:.1f} wavefronts per lookup), but {k} lookups per byte = ~{k * per:.1f} wavefronts per byte (plus the byte -> class lookup)")
+
 
 if __name__ == "__main__":
     main()
